@@ -1,0 +1,189 @@
+/*
+ * fx_b200.h -- C ABI of the B200-native feature-extraction hot path.
+ *
+ * The reference (Septimus4/semi-supervised-image-processing) is pure Python and has no FFI of its
+ * own; the boundary it offers is the module surface of src/feature_extraction.py.  Each entry
+ * point below names the reference lines it stands in for.  Everything is `extern "C"`, plain
+ * pointers and sizes; no torch / C++ types cross the boundary.
+ *
+ * Conventions
+ *   - every call returns FX_OK (0) or a negative fx_status; nothing throws across the ABI;
+ *     fx_last_error(h) gives the text of the last failure on that handle (fx_last_error(NULL)
+ *     for a failed fx_create);
+ *   - one handle per GPU, not thread-safe per handle, re-entrant across handles;
+ *   - "dev" pointers are device memory on the handle's GPU, "host" pointers are host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); device
+ *     entry points are asynchronous on it, the *_host entry points synchronise before returning;
+ *   - the caller owns every buffer it passes; the library owns its workspace and TMA descriptors.
+ *   - there is no CPU fallback: without a usable sm_100 device fx_create fails.
+ */
+#ifndef FX_B200_H
+#define FX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FX_ABI_VERSION 1
+
+typedef struct fx_engine *fx_handle;
+
+typedef enum fx_status {
+    FX_OK = 0,
+    FX_ERR_INVALID = -1,     /* bad argument (null pointer, n > max_batch, bad layer table ...) */
+    FX_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed; text in fx_last_error       */
+    FX_ERR_UNSUPPORTED = -3, /* wrong channel count / image too small or too large / no sm_100  */
+    FX_ERR_NOMEM = -4,
+    FX_ERR_STATE = -5        /* call order: weights not loaded, nothing staged, ...              */
+} fx_status;
+
+/* Arithmetic of the trunk.  BF16 = tcgen05 tensor-core path (bf16 operands, fp32 accumulate);
+ * FP32 = the tight-tolerance mode (fp32 operands and accumulate on the CUDA cores). */
+typedef enum fx_precision { FX_PRECISION_BF16 = 0, FX_PRECISION_FP32 = 1 } fx_precision;
+
+/* Geometry constants of the path: src/feature_extraction.py:64-67. */
+#define FX_RESIZE 256
+#define FX_CROP 224
+#define FX_EMBED_DIM 512
+#define FX_NUM_CONV_LAYERS 20
+
+/*
+ * One decoded image inside a packed uint8 buffer, exactly what PIL hands the reference's
+ * transform in preprocess_image (src/feature_extraction.py:233-240): HWC, 8 bits per channel,
+ * row pitch = width*channels, no mode conversion.
+ * channels == 3: mode "RGB" (the only mode the reference's Normalize accepts).
+ * channels == 1: opt-in "gray carriage" of a file whose three stored channels are identical
+ *                (R==G==B); the plane is replicated and each replica gets its own mean/std, which
+ *                is arithmetically what the reference computes on such a file.  The Python host
+ *                only uses it when asked to; a true mode-"L" file still raises as the reference.
+ */
+typedef struct fx_image_desc {
+    uint64_t offset;  /* byte offset of pixel (0,0,0) from the `src` pointer of the call */
+    int32_t height;
+    int32_t width;
+    int32_t channels; /* 3 or 1 */
+    int32_t reserved;
+} fx_image_desc;
+
+/*
+ * One convolution + its BatchNorm, as stored in a torchvision ResNet state_dict
+ * (torchvision/models/resnet.py:59-105,197-243): conv weight OIHW fp32 (bias=False), BN affine
+ * and running statistics.  The library folds BN into the conv in fp64
+ * (s = gamma/sqrt(var+eps), W' = W*s, b' = beta - mean*s), then packs W' for its kernels.
+ * All pointers are HOST memory and only read during fx_load_weights.
+ */
+typedef struct fx_conv_bn {
+    const float *weight; /* [cout][cin][kh][kw] */
+    const float *gamma;  /* [cout] */
+    const float *beta;
+    const float *mean;
+    const float *var;
+    float eps; /* 1e-5 */
+    int32_t cout, cin, kh, kw, stride, pad;
+} fx_conv_bn;
+
+/* Layer order expected by fx_load_weights (children()[:-1] of resnet18, i.e. what load_model
+ * keeps at src/feature_extraction.py:219-225):
+ *  0 conv1
+ *  1 layer1.0.conv1   2 layer1.0.conv2   3 layer1.1.conv1   4 layer1.1.conv2
+ *  5 layer2.0.conv1   6 layer2.0.conv2   7 layer2.0.downsample   8 layer2.1.conv1   9 layer2.1.conv2
+ * 10 layer3.0.conv1  11 layer3.0.conv2  12 layer3.0.downsample  13 layer3.1.conv1  14 layer3.1.conv2
+ * 15 layer4.0.conv1  16 layer4.0.conv2  17 layer4.0.downsample  18 layer4.1.conv1  19 layer4.1.conv2
+ */
+
+const char *fx_version(void);
+int fx_abi_version(void);
+
+/* Text of the last error on `h` (or of the last failed fx_create when h == NULL). */
+const char *fx_last_error(fx_handle h);
+
+/*
+ * Replaces load_model(device) (src/feature_extraction.py:210-227) together with fx_load_weights:
+ * binds a GPU, allocates the activation workspace for up to `max_batch` images per call.
+ */
+int fx_create(fx_handle *out, int device, int max_batch, int precision);
+void fx_destroy(fx_handle h);
+
+/* The frozen trunk's parameters: resnet18 minus fc (src/feature_extraction.py:217-225). */
+int fx_load_weights(fx_handle h, const fx_conv_bn *layers, int n_layers);
+
+/*
+ * Replaces build_transform()/preprocess_image for a batch
+ * (src/feature_extraction.py:184-207,233-240): Resize(256) with Pillow's fixed-point antialiased
+ * bilinear, CenterCrop(224), ToTensor, Normalize -- one fused kernel.
+ * Writes exactly the tensor the reference stacks at src/feature_extraction.py:289:
+ * fp32 NCHW [n][3][224][224], bit-identical to the reference transform.
+ */
+int fx_preprocess_nchw_f32(fx_handle h, const uint8_t *src_dev, const fx_image_desc *descs_host, int n,
+                           float *out_dev, void *stream);
+
+/*
+ * Same transform, written into the engine's conv1 staging buffer (channel-padded, spatially
+ * padded NHWC in the trunk's precision).  Follow with fx_forward.
+ */
+int fx_preprocess(fx_handle h, const uint8_t *src_dev, const fx_image_desc *descs_host, int n, void *stream);
+
+/*
+ * Replaces `model(batch_tensor)` + torch.flatten (src/feature_extraction.py:290-293) on the `n`
+ * images staged by the last fx_preprocess / fx_stage_nchw_f32: writes fp32 [n][512] at emb_dev
+ * (which may point into a larger gather buffer).
+ */
+int fx_forward(fx_handle h, int n, float *emb_dev, void *stream);
+
+/* Stage an already normalised fp32 NCHW [n][3][224][224] batch (the reference's own
+ * batch_tensor) instead of running the preprocess kernel; lets the trunk be checked alone. */
+int fx_stage_nchw_f32(fx_handle h, const float *in_dev, int n, void *stream);
+
+/* fx_preprocess + fx_forward. */
+int fx_embed(fx_handle h, const uint8_t *src_dev, const fx_image_desc *descs_host, int n, float *emb_dev,
+             void *stream);
+
+/*
+ * The whole of src/feature_extraction.py:289-294 for one batch with HOST buffers: host->device
+ * copy of the packed uint8 images (total_bytes), preprocess, trunk, device->host copy of the
+ * [n][512] fp32 embeddings.  Synchronous.  Pinned host memory makes the copies asynchronous
+ * inside the call but is not required.
+ */
+int fx_embed_host(fx_handle h, const uint8_t *src_host, size_t total_bytes, const fx_image_desc *descs_host,
+                  int n, float *emb_host);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+uint64_t fx_launch_count(fx_handle h);
+
+/* ---- test / inspection entry points (used by tests/ for per-layer parity) ---- */
+
+/*
+ * Fold, pack and run ONE conv+bn group (any 3x3 / 1x1 / strided shape the trunk kernels support,
+ * or the 7x7 stem) on a caller supplied activation: in_dev is fp32 NHWC [n][hin][win][cin];
+ * residual_dev (may be NULL) and out_dev are fp32 NHWC [n][ho][wo][cout].  In BF16 precision the
+ * input/residual are rounded to bf16, the tcgen05 kernel runs, and its bf16 result is widened back
+ * to fp32.  Synchronises `stream` before returning.
+ */
+int fx_debug_conv(fx_handle h, const fx_conv_bn *layer, int hin, int win, const float *in_dev,
+                  const float *residual_dev, int n, int relu, float *out_dev, void *stream);
+
+/* Copy out the folded parameters of loaded layer `layer` as the kernels see them (fp32,
+ * [cout][kh][kw][cin] order, bf16-rounded in BF16 precision) -- host pointers, either may be NULL. */
+int fx_debug_folded(fx_handle h, int layer, float *weight_host, float *bias_host);
+
+/* One 4-D bf16 TMA box load (tensor map built from the arguments) -> raw shared-memory bytes
+ * copied to out_dev.  Pins the TMA behaviours the conv kernel relies on (zero fill out of bounds,
+ * element strides, 16-byte-strided overlapping windows, swizzle patterns). */
+int fx_debug_tma_probe(fx_handle h, const void *base_dev, const uint64_t *dims, const uint64_t *strides_bytes,
+                       const uint32_t *box, const uint32_t *elem_strides, int swizzle, const int *coords,
+                       int bytes, uint8_t *out_dev);
+
+/* Host-side integer pieces of the preprocess (no GPU needed): torchvision's Resize(256) output
+ * size, CenterCrop(224)'s round-half-even offset, Pillow's fixed-point coefficient table
+ * (returns taps per output sample; with NULL arrays only returns that count). */
+int fx_host_resized_size(int h, int w, int *oh, int *ow);
+int fx_host_crop_offset(int size);
+int fx_host_coeffs(int in_size, int out_size, int32_t *xmin, int32_t *count, int32_t *taps, int taps_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FX_B200_H */

@@ -1,0 +1,545 @@
+// bf16 implicit-GEMM convolution on the Blackwell tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Stands in for every Conv2d+BatchNorm2d(+ReLU)(+residual add) group of the frozen ResNet-18 trunk
+// the reference runs at src/feature_extraction.py:290-291 (torchvision/models/resnet.py:89-105,
+// 197-206,266-282).  BN is folded into the weights/bias on the host (engine.cu).
+//
+// GEMM view: M = n*ho*wo output pixels, N = cout, K = (kh, kw, cin) with cin innermost.
+//   * activations are NHWC bf16, so the K-slice of one filter tap (r, s) and 64 input channels of
+//     a rectangular patch of output pixels is a 4-D box {64 c, Wt w, Ht h, Nt n} of the input
+//     tensor: ONE tiled TMA load (cp.async.bulk.tensor.4d) brings it in as a 128-row x 128-byte
+//     K-major SWIZZLE_128B operand tile.  Conv zero padding = TMA out-of-bounds zero fill;
+//     stride-2 convs = TMA element strides.  No im2col buffer ever exists.
+//   * weights are packed [cout][K] bf16; one 2-D TMA load per K-slice gives the B operand tile.
+//   * conv1 (7x7/s2, cin 3) reads the channel-padded, spatially padded staging tensor the
+//     preprocess kernel writes ([230][232][4] per image): the 8-pixel x 4-channel window of one
+//     filter row is 64 contiguous bytes, windows of neighbouring outputs overlap by 48 bytes,
+//     which a tensor map with a 16-byte stride on the `ow` dimension describes directly
+//     (K = 7 rows x 32, SWIZZLE_64B).
+//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered fp32
+//     accumulator in TMEM; 4 epilogue warps read it back with tcgen05.ld, add the folded-BN bias
+//     and the residual, apply ReLU, and store bf16 NHWC (or fp32 for the layer feeding avgpool).
+//   * warp-specialised, persistent over output tiles: warp 0 = TMA producer, warp 1 = MMA issuer,
+//     warp 2 = TMEM allocator, warps 4-7 = epilogue; mbarrier rings smem(full/empty) and
+//     tmem(full/empty).
+#include <algorithm>
+#include <cstring>
+
+#include <cudaTypedefs.h>
+
+#include "fx_common.cuh"
+
+namespace fx {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Parity wait with a watchdog: a protocol bug must end in a trap (the launch fails with an
+// error) rather than in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin == 64) t0 = global_ns();
+        if (spin > 64 && (spin & 63) == 0 && global_ns() - t0 > 2000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :
+        : "r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand whose K extent is exactly one swizzle atom
+// (BK*2 bytes = 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).  8-row groups are `8*BK*2` bytes apart.
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    constexpr uint64_t sbo = (8 * BK * 2) >> 4;
+    constexpr uint64_t layout = BK == 64 ? 2 : 4;  // SWIZZLE_128B : SWIZZLE_64B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// Instruction descriptor: c=f32, a=b=bf16, both K-major, M=128, N=BN.
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel
+// ------------------------------------------------------------------------------------------
+struct TcConvParams {
+    int wt_log2, ht_log2, nt_log2;  // output tile = (1<<wt) x (1<<ht) pixels of (1<<nt) images = 128 rows
+    int tiles_w, tiles_h, tiles_g;  // tiles along ow, oh, image groups
+    int n_tiles_n;                  // cout / BN
+    int total_tiles;
+    int batch, ho, wo, cout;
+    int kh, kw, cchunks;               // K loop: taps x (cin / BK)
+    int cw_mul, ch_mul, pad_w, pad_h;  // A box start: w = ow0*cw_mul - pad_w + s, h = oh0*ch_mul - pad_h + r
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    float* out_f32;
+    int relu;
+};
+
+constexpr int kTcThreads = 256;
+
+template <int BN, int BK, int STAGES>
+struct TcSmem {
+    static constexpr int kA = 128 * BK * 2;
+    static constexpr int kB = BN * BK * 2;
+    static constexpr int kBars = (2 * STAGES + 4) * 8;
+    static constexpr int kTotal = 1024 /*align slack*/ + STAGES * (kA + kB) + kBars + 16;
+};
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
+    using L = TcSmem<BN, BK, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = sbase, sB = sbase + STAGES * L::kA;
+    const uint32_t bars = sB + STAGES * L::kB;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tslot = tempty0 + 16;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tslot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    const int num_kb = p.kh * p.kw * p.cchunks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int n_tile = t % p.n_tiles_n;
+                int m_tile = t / p.n_tiles_n;
+                const int tw = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th = m_tile % p.tiles_h;
+                const int tg = m_tile / p.tiles_h;
+                const int w0 = (tw << p.wt_log2) * p.cw_mul - p.pad_w;
+                const int h0 = (th << p.ht_log2) * p.ch_mul - p.pad_h;
+                const int n0 = tg << p.nt_log2;
+                int kb = 0;
+                for (int r = 0; r < p.kh; ++r)
+                    for (int s = 0; s < p.kw; ++s)
+                        for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
+                            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                            mbar_expect_tx(full0 + 8 * stage, L::kA + L::kB);
+                            tma_load_4d(sA + stage * L::kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                            tma_load_2d(sB + stage * L::kB, &map_b, full0 + 8 * stage, kb * BK, n_tile * BN);
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<BN>();
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc<BK>(sA + stage * L::kA);
+                    const uint64_t db = make_smem_desc<BK>(sB + stage * L::kB);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(empty0 + 8 * stage);  // frees the smem slot once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int wl = row & ((1 << p.wt_log2) - 1);
+        const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
+        const int nl = row >> (p.wt_log2 + p.ht_log2);
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int n_tile = t % p.n_tiles_n;
+            int m_tile = t / p.n_tiles_n;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int tg = m_tile / p.tiles_h;
+            const int ow = (tw << p.wt_log2) + wl, oh = (th << p.ht_log2) + hl, img = (tg << p.nt_log2) + nl;
+            const bool valid = ow < p.wo && oh < p.ho && img < p.batch;
+            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
+            const size_t obase = pix * p.cout + (size_t)n_tile * BN;
+
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b = __ldg(bp + j);
+                        f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                    }
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint4 rv = __ldg(rp + j);
+                            const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                f[8 * j + 2 * k] += __uint_as_float(u[k] << 16);
+                                f[8 * j + 2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (p.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 o;
+                            unsigned* u = &o.x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                                u[k] = *reinterpret_cast<const unsigned*>(&h2);
+                            }
+                            op[j] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * as);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA probe (test entry point): one box load -> shared memory -> global, raw bytes.
+// ------------------------------------------------------------------------------------------
+__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap map, int c0, int c1, int c2, int c3, int bytes,
+                                 uint8_t* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t bar = sbase + ((bytes + 15) & ~15);
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) sptr[i] = 0xCD;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, bytes);
+        tma_load_4d(sbase, &map, bar, c0, c1, c2, c3);
+    }
+    mbar_wait(bar, 0);
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = sptr[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+struct TcState {
+    PFN_cuTensorMapEncodeTiled encode = nullptr;
+};
+
+static int encode_map(fx_engine* e, CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, CUtensorMapSwizzle sw,
+                      const char* what) {
+    TcState* st = static_cast<TcState*>(e->tc_state);
+    CUresult r = st->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                            strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(e, FX_ERR_CUDA, std::string("cuTensorMapEncodeTiled(") + what + ") failed with CUresult " + std::to_string((int)r));
+    return FX_OK;
+}
+
+template <int BN, int BK, int STAGES>
+static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, cudaStream_t stream) {
+    using L = TcSmem<BN, BK, STAGES>;
+    static bool attr_done[16] = {};
+    if (!attr_done[e->device & 15]) {
+        FX_CUDA(e, cudaFuncSetAttribute(tc_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        attr_done[e->device & 15] = true;
+    }
+    const int grid = std::min(p.total_tiles, e->sm_count);
+    tc_conv_kernel<BN, BK, STAGES><<<grid, kTcThreads, L::kTotal, stream>>>(ma, mb, p);
+    FX_LAUNCH_CHECK(e, "tc_conv_kernel");
+    return FX_OK;
+}
+
+int tc_init(fx_engine* e) {
+    TcState* st = new TcState();
+    e->tc_state = st;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FX_CUDA(e, cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+        return set_error(e, FX_ERR_CUDA, "driver does not export cuTensorMapEncodeTiled");
+    st->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    return FX_OK;
+}
+
+void tc_free(fx_engine* e) {
+    delete static_cast<TcState*>(e->tc_state);
+    e->tc_state = nullptr;
+}
+
+// Pick the power-of-two output box (Wt, Ht, Nt), Wt*Ht*Nt = 128, that wastes the fewest rows.
+static void choose_tile(int n, int ho, int wo, int& wt, int& ht, int& nt) {
+    long long best = -1;
+    for (int a = 0; a <= 7; ++a)
+        for (int b = 0; a + b <= 7; ++b) {
+            const int c = 7 - a - b;
+            const long long tiles = (long long)((wo + (1 << a) - 1) >> a) * ((ho + (1 << b) - 1) >> b) * ((n + (1 << c) - 1) >> c);
+            // fewer tiles first; then wider rows (longer contiguous TMA runs)
+            if (best < 0 || tiles < best || (tiles == best && a > wt)) {
+                best = tiles;
+                wt = a;
+                ht = b;
+                nt = c;
+            }
+        }
+}
+
+int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+                   __nv_bfloat16* out, float* out_f32, int n, int relu, cudaStream_t stream) {
+    const LayerGeom& g = L.g;
+    TcConvParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.batch = n;
+    p.ho = g.hout;
+    p.wo = g.wout;
+    p.cout = g.cout;
+    p.bias = L.bias;
+    p.residual = residual;
+    p.out = out;
+    p.out_f32 = out_f32;
+    p.relu = relu;
+    if (g.cout % 64 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: cout must be a multiple of 64");
+    const int bn = g.cout % 256 == 0 ? 256 : (g.cout % 128 == 0 ? 128 : 64);
+    p.n_tiles_n = g.cout / bn;
+    choose_tile(n, g.hout, g.wout, p.wt_log2, p.ht_log2, p.nt_log2);
+    p.tiles_w = (g.wout + (1 << p.wt_log2) - 1) >> p.wt_log2;
+    p.tiles_h = (g.hout + (1 << p.ht_log2) - 1) >> p.ht_log2;
+    p.tiles_g = (n + (1 << p.nt_log2) - 1) >> p.nt_log2;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_g * p.n_tiles_n;
+
+    CUtensorMap ma, mb;
+    const bool is_conv1 = g.cin == 3;
+    if (is_conv1) {
+        if (!(g.kh == 7 && g.kw == 7 && g.stride == 2 && g.pad == 3 && g.hin == kCrop && g.win == kCrop))
+            return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: a 3-channel input is only supported for the 7x7/s2/p3 stem on 224x224");
+        // A: the staging tensor [n][230][232][4] seen as {32 elems (8 px x 4 ch), ow, ih, n}: the window of
+        // output column ow starts at pixel 2*ow, i.e. 16 bytes further for each ow.
+        const uint64_t dims[4] = {32, (uint64_t)g.wout, (uint64_t)kIn0H, (uint64_t)n};
+        const uint64_t strides[3] = {16, (uint64_t)kIn0W * kIn0C * 2, (uint64_t)kIn0H * kIn0W * kIn0C * 2};
+        const uint32_t box[4] = {32, 1u << p.wt_log2, 2u << p.ht_log2, 1u << p.nt_log2};
+        const uint32_t estr[4] = {1, 1, 2, 1};
+        int rc = encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B, "conv1 A");
+        if (rc != FX_OK) return rc;
+        const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+        const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+        const uint32_t bbox[2] = {32, (uint32_t)bn};
+        const uint32_t be[2] = {1, 1};
+        rc = encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_64B, "conv1 B");
+        if (rc != FX_OK) return rc;
+        p.kh = 7;
+        p.kw = 1;
+        p.cchunks = 1;
+        p.cw_mul = 1;
+        p.ch_mul = 2;
+        p.pad_w = 0;
+        p.pad_h = 0;
+        if (bn != 64) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: stem must have 64 output channels");
+        return launch_tc<64, 32, 7>(e, ma, mb, p, stream);
+    }
+    if (g.cin % 64 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: cin must be 3 or a multiple of 64");
+    {
+        const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
+        const uint32_t box[4] = {64, (uint32_t)g.stride << p.wt_log2, (uint32_t)g.stride << p.ht_log2, 1u << p.nt_log2};
+        const uint32_t estr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
+        int rc = encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A");
+        if (rc != FX_OK) return rc;
+        const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+        const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+        const uint32_t bbox[2] = {64, (uint32_t)bn};
+        const uint32_t be[2] = {1, 1};
+        rc = encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B");
+        if (rc != FX_OK) return rc;
+    }
+    p.kh = g.kh;
+    p.kw = g.kw;
+    p.cchunks = g.cin / 64;
+    p.cw_mul = g.stride;
+    p.ch_mul = g.stride;
+    p.pad_w = g.pad;
+    p.pad_h = g.pad;
+    switch (bn) {
+        case 64: return launch_tc<64, 64, 8>(e, ma, mb, p, stream);
+        case 128: return launch_tc<128, 64, 6>(e, ma, mb, p, stream);
+        default: return launch_tc<256, 64, 4>(e, ma, mb, p, stream);
+    }
+}
+
+int tc_conv(fx_engine* e, int li, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, float* out_f32,
+            int n, int relu, cudaStream_t stream) {
+    return tc_conv_packed(e, e->layers[li], in, residual, out, out_f32, n, relu, stream);
+}
+
+// Test hook behind fx_debug_tma_probe (engine.cu): encode an arbitrary 4-D bf16 map, load one box.
+int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                 const uint32_t* estr, int swizzle, const int* coords, int bytes, uint8_t* out_dev, cudaStream_t stream) {
+    CUtensorMap m;
+    CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                            : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                            : CU_TENSOR_MAP_SWIZZLE_NONE;
+    int rc = encode_map(e, &m, base, 4, dims, strides, box, estr, sw, "probe");
+    if (rc != FX_OK) return rc;
+    const int smem = 1024 + ((bytes + 15) & ~15) + 16;
+    FX_CUDA(e, cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    tma_probe_kernel<<<1, 128, smem, stream>>>(m, coords[0], coords[1], coords[2], coords[3], bytes, out_dev);
+    FX_LAUNCH_CHECK(e, "tma_probe_kernel");
+    return FX_OK;
+}
+
+}  // namespace fx

@@ -1,0 +1,451 @@
+// C ABI of the library (include/fx_b200.h): handle lifetime, weight folding/packing, the
+// forward schedule of the truncated ResNet-18, host-buffer entry point.
+//
+// Reference lines replaced: load_model (src/feature_extraction.py:210-227) -> fx_create +
+// fx_load_weights; the body of the batch loop (src/feature_extraction.py:289-294) -> fx_embed /
+// fx_embed_host.  The network topology follows torchvision/models/resnet.py:166-282 with
+// layers=[2,2,2,2] (resnet.py:684-705) and children()[:-1] (fc dropped, avgpool kept).
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "fx_common.cuh"
+
+namespace fx {
+
+int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+                   __nv_bfloat16* out, float* out_f32, int n, int relu, cudaStream_t stream);
+int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
+                 const uint32_t* estr, int swizzle, const int* coords, int bytes, uint8_t* out_dev, cudaStream_t stream);
+
+static std::mutex g_err_mutex;
+static std::string g_create_error;
+
+int set_error(fx_engine* e, int code, const std::string& msg) {
+    if (e) {
+        e->err = msg;
+    } else {
+        std::lock_guard<std::mutex> lk(g_err_mutex);
+        g_create_error = msg;
+    }
+    return code;
+}
+
+// Input spatial size of every conv layer of the 224x224 network, in fx_load_weights order.
+static const int kLayerHin[kNumLayers] = {224, 56, 56, 56, 56, 56, 28, 56, 28, 28, 28, 14, 28, 14, 14, 14, 7, 14, 7, 7};
+
+static inline float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+static void free_layer(PackedLayer& L) {
+    cudaFree(L.w_f32);
+    cudaFree(L.w_bf16);
+    cudaFree(L.bias);
+    L.w_f32 = nullptr;
+    L.w_bf16 = nullptr;
+    L.bias = nullptr;
+}
+
+// Fold BN into the conv (fp64), reorder OIHW -> O,KH,KW,I, upload in the engine's precision.
+static int pack_layer(fx_engine* e, const fx_conv_bn& src, int hin, int win, PackedLayer& L) {
+    if (!src.weight || !src.gamma || !src.beta || !src.mean || !src.var)
+        return set_error(e, FX_ERR_INVALID, "layer table holds a null pointer");
+    if (src.cout <= 0 || src.cin <= 0 || src.kh <= 0 || src.kw <= 0 || src.stride <= 0 || src.pad < 0)
+        return set_error(e, FX_ERR_INVALID, "layer table holds a non-positive dimension");
+    free_layer(L);
+    LayerGeom& g = L.g;
+    g.cin = src.cin;
+    g.cout = src.cout;
+    g.kh = src.kh;
+    g.kw = src.kw;
+    g.stride = src.stride;
+    g.pad = src.pad;
+    g.hin = hin;
+    g.win = win;
+    g.hout = (hin + 2 * src.pad - src.kh) / src.stride + 1;
+    g.wout = (win + 2 * src.pad - src.kw) / src.stride + 1;
+    const bool bf16 = e->precision == FX_PRECISION_BF16;
+    const int taps = g.kh * g.kw;
+    L.host_w.assign((size_t)g.cout * taps * g.cin, 0.f);
+    L.host_b.assign(g.cout, 0.f);
+    for (int o = 0; o < g.cout; ++o) {
+        const double s = (double)src.gamma[o] / std::sqrt((double)src.var[o] + (double)src.eps);
+        L.host_b[o] = (float)((double)src.beta[o] - (double)src.mean[o] * s);
+        for (int i = 0; i < g.cin; ++i)
+            for (int t = 0; t < taps; ++t) {
+                const float w = (float)((double)src.weight[((size_t)o * g.cin + i) * taps + t] * s);
+                L.host_w[((size_t)o * taps + t) * g.cin + i] = bf16 ? bf16_round(w) : w;
+            }
+    }
+    FX_CUDA(e, cudaMalloc(&L.bias, sizeof(float) * g.cout));
+    FX_CUDA(e, cudaMemcpy(L.bias, L.host_b.data(), sizeof(float) * g.cout, cudaMemcpyHostToDevice));
+    const bool stem = g.cin == 3;
+    if (!bf16) {
+        // fp32 pack [cout][kh][kw][cin_pad]; the stem pads cin 3 -> 4 to match the staging tensor
+        const int cp = stem ? kIn0C : g.cin;
+        if (!stem && g.cin % 4 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "fp32 path: cin must be 3 or a multiple of 4");
+        if (g.cout % 4 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "fp32 path: cout must be a multiple of 4");
+        std::vector<float> w((size_t)g.cout * taps * cp, 0.f);
+        for (int o = 0; o < g.cout; ++o)
+            for (int t = 0; t < taps; ++t)
+                for (int i = 0; i < g.cin; ++i) w[((size_t)o * taps + t) * cp + i] = L.host_w[((size_t)o * taps + t) * g.cin + i];
+        FX_CUDA(e, cudaMalloc(&L.w_f32, sizeof(float) * w.size()));
+        FX_CUDA(e, cudaMemcpy(L.w_f32, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+        return FX_OK;
+    }
+    // bf16 GEMM-B pack [cout][K]
+    std::vector<__nv_bfloat16> w;
+    if (stem) {
+        // K = kh rows x (8 pixels x 4 channels); pixel 7 and channel 3 are zero
+        if (g.kw > 8) return set_error(e, FX_ERR_UNSUPPORTED, "stem kernel wider than 8");
+        L.k_bf16 = g.kh * 32;
+        w.assign((size_t)g.cout * L.k_bf16, __float2bfloat16_rn(0.f));
+        for (int o = 0; o < g.cout; ++o)
+            for (int r = 0; r < g.kh; ++r)
+                for (int s = 0; s < g.kw; ++s)
+                    for (int i = 0; i < g.cin; ++i)
+                        w[(size_t)o * L.k_bf16 + r * 32 + s * 4 + i] =
+                            __float2bfloat16_rn(L.host_w[((size_t)o * taps + r * g.kw + s) * g.cin + i]);
+    } else {
+        L.k_bf16 = taps * g.cin;
+        w.resize((size_t)g.cout * L.k_bf16);
+        for (size_t i = 0; i < w.size(); ++i) w[i] = __float2bfloat16_rn(L.host_w[i]);
+    }
+    FX_CUDA(e, cudaMalloc(&L.w_bf16, sizeof(__nv_bfloat16) * w.size()));
+    FX_CUDA(e, cudaMemcpy(L.w_bf16, w.data(), sizeof(__nv_bfloat16) * w.size(), cudaMemcpyHostToDevice));
+    return FX_OK;
+}
+
+// One conv layer on NHWC activations in the engine's precision.  Layer 0 reads the staging tensor.
+static int run_conv(fx_engine* e, int li, const void* in, const void* residual, void* out, float* out_f32, int n, int relu,
+                    cudaStream_t stream) {
+    const PackedLayer& L = e->layers[li];
+    if (e->precision == FX_PRECISION_BF16)
+        return tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
+                              static_cast<__nv_bfloat16*>(out), out_f32, n, relu, stream);
+    float* o = out_f32 ? out_f32 : static_cast<float*>(out);
+    if (li == 0)
+        return simt_conv(e, L, static_cast<const float*>(in), kIn0H, kIn0W, kIn0C, 0, static_cast<const float*>(residual), o, n,
+                         relu, stream);
+    return simt_conv(e, L, static_cast<const float*>(in), L.g.hin, L.g.win, L.g.cin, L.g.pad, static_cast<const float*>(residual),
+                     o, n, relu, stream);
+}
+
+// The truncated ResNet-18 on `n` staged images -> fp32 [n][512].
+static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
+    const bool bf16 = e->precision == FX_PRECISION_BF16;
+    void *A = e->act[0], *B = e->act[1], *C = e->act[2];
+    int rc;
+    // stem: conv1+bn1+relu -> maxpool            (resnet.py:268-271)
+    if ((rc = run_conv(e, 0, e->in0, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
+    if ((rc = maxpool_3x3s2(e, B, A, n, 112, 112, 64, bf16, stream)) != FX_OK) return rc;
+    // four stages of two BasicBlocks            (resnet.py:89-105, 273-276)
+    int li = 1;
+    for (int stage = 0; stage < 4; ++stage)
+        for (int blk = 0; blk < 2; ++blk) {
+            const bool down = stage > 0 && blk == 0;
+            const bool last = stage == 3 && blk == 1;
+            if (!down) {
+                // out = relu(conv2(relu(conv1(x))) + x)
+                if ((rc = run_conv(e, li, A, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
+                if ((rc = run_conv(e, li + 1, B, A, C, last ? e->final_f32 : nullptr, n, 1, stream)) != FX_OK) return rc;
+                std::swap(A, C);
+                li += 2;
+            } else {
+                // out = relu(conv2(relu(conv1(x))) + downsample(x))
+                if ((rc = run_conv(e, li, A, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
+                if ((rc = run_conv(e, li + 2, A, nullptr, C, nullptr, n, 0, stream)) != FX_OK) return rc;
+                if ((rc = run_conv(e, li + 1, B, C, A, nullptr, n, 1, stream)) != FX_OK) return rc;
+                li += 3;
+            }
+        }
+    // avgpool + flatten                         (resnet.py:278-279; src/feature_extraction.py:293)
+    return avgpool_7x7(e, e->final_f32, false, emb, n, 49, kEmbed, stream);
+}
+
+}  // namespace fx
+
+using namespace fx;
+
+extern "C" {
+
+const char* fx_version(void) { return "fx_b200 0.1.0 (sm_100a)"; }
+int fx_abi_version(void) { return FX_ABI_VERSION; }
+
+const char* fx_last_error(fx_handle h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    return g_create_error.c_str();
+}
+
+void fx_destroy(fx_handle e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& L : e->layers) free_layer(L);
+    preprocess_free(e);
+    tc_free(e);
+    cudaFree(e->in0);
+    for (auto& a : e->act) cudaFree(a);
+    cudaFree(e->final_f32);
+    cudaFree(e->h2d_dev);
+    cudaFree(e->emb_dev);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+int fx_create(fx_handle* out, int device, int max_batch, int precision) {
+    if (!out) return set_error(nullptr, FX_ERR_INVALID, "fx_create: null output pointer");
+    *out = nullptr;
+    if (max_batch < 1 || max_batch > 65536) return set_error(nullptr, FX_ERR_INVALID, "fx_create: max_batch out of range");
+    if (precision != FX_PRECISION_BF16 && precision != FX_PRECISION_FP32)
+        return set_error(nullptr, FX_ERR_INVALID, "fx_create: unknown precision");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return set_error(nullptr, FX_ERR_UNSUPPORTED,
+                         std::string("fx_create: no CUDA device (") + cudaGetErrorString(err) + "); this library has no CPU path");
+    if (device < 0 || device >= count) return set_error(nullptr, FX_ERR_INVALID, "fx_create: device index out of range");
+    cudaDeviceProp prop;
+    if ((err = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return set_error(nullptr, FX_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(err));
+    if (prop.major != 10)
+        return set_error(nullptr, FX_ERR_UNSUPPORTED,
+                         "fx_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                             "; this library is built for sm_100a (B200) only");
+    if ((err = cudaSetDevice(device)) != cudaSuccess)
+        return set_error(nullptr, FX_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(err));
+
+    fx_engine* e = new fx_engine();
+    e->device = device;
+    e->max_batch = max_batch;
+    e->precision = precision;
+    e->sm_count = prop.multiProcessorCount;
+    auto fail = [&](int rc) {
+        set_error(nullptr, rc, e->err);
+        fx_destroy(e);
+        return rc;
+    };
+    const size_t esz = precision == FX_PRECISION_BF16 ? 2 : 4;
+    const size_t in0_bytes = (size_t)max_batch * kIn0H * kIn0W * kIn0C * esz;
+    e->act_bytes = (size_t)max_batch * 112 * 112 * 64 * esz;  // largest activation: conv1 output
+    int rc = FX_OK;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc != FX_OK) return;
+        cudaError_t a = cudaMalloc(p, bytes);
+        if (a != cudaSuccess) rc = set_error(e, a == cudaErrorMemoryAllocation ? FX_ERR_NOMEM : FX_ERR_CUDA,
+                                             std::string("cudaMalloc: ") + cudaGetErrorString(a));
+    };
+    alloc(&e->in0, in0_bytes);
+    alloc(&e->act[0], (size_t)max_batch * 56 * 56 * 64 * esz);
+    alloc(&e->act[1], e->act_bytes);
+    alloc(&e->act[2], (size_t)max_batch * 56 * 56 * 64 * esz);
+    alloc(reinterpret_cast<void**>(&e->final_f32), (size_t)max_batch * 49 * kEmbed * sizeof(float));
+    alloc(reinterpret_cast<void**>(&e->emb_dev), (size_t)max_batch * kEmbed * sizeof(float));
+    if (rc != FX_OK) return fail(rc);
+    // the pad region of the staging tensor is conv zero padding and is never written again
+    if ((err = cudaMemset(e->in0, 0, in0_bytes)) != cudaSuccess) return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
+    if ((err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
+    if ((rc = preprocess_init(e)) != FX_OK) return fail(rc);
+    if ((rc = tc_init(e)) != FX_OK) return fail(rc);
+    *out = e;
+    return FX_OK;
+}
+
+int fx_load_weights(fx_handle e, const fx_conv_bn* layers, int n_layers) {
+    if (!e) return FX_ERR_INVALID;
+    if (!layers || n_layers != kNumLayers)
+        return set_error(e, FX_ERR_INVALID, "fx_load_weights: expected the 20 conv+bn groups of resnet18 minus fc");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    static const int cin[kNumLayers] = {3, 64, 64, 64, 64, 64, 128, 64, 128, 128, 128, 256, 128, 256, 256, 256, 512, 256, 512, 512};
+    static const int cout[kNumLayers] = {64, 64, 64, 64, 64, 128, 128, 128, 128, 128, 256, 256, 256, 256, 256, 512, 512, 512, 512, 512};
+    static const int ks[kNumLayers] = {7, 3, 3, 3, 3, 3, 3, 1, 3, 3, 3, 3, 1, 3, 3, 3, 3, 1, 3, 3};
+    static const int st[kNumLayers] = {2, 1, 1, 1, 1, 2, 1, 2, 1, 1, 2, 1, 2, 1, 1, 2, 1, 2, 1, 1};
+    e->weights_loaded = false;
+    for (int i = 0; i < kNumLayers; ++i) {
+        const fx_conv_bn& s = layers[i];
+        if (s.cin != cin[i] || s.cout != cout[i] || s.kh != ks[i] || s.kw != ks[i] || s.stride != st[i] || s.pad != ks[i] / 2)
+            return set_error(e, FX_ERR_INVALID, "fx_load_weights: layer " + std::to_string(i) + " does not match resnet18");
+        int rc = pack_layer(e, s, kLayerHin[i], kLayerHin[i], e->layers[i]);
+        if (rc != FX_OK) return rc;
+    }
+    e->weights_loaded = true;
+    return FX_OK;
+}
+
+int fx_preprocess_nchw_f32(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, int n, float* out_dev, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (n < 0 || n > e->max_batch || (n > 0 && (!src_dev || !descs || !out_dev)))
+        return set_error(e, FX_ERR_INVALID, "fx_preprocess_nchw_f32: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    return preprocess_run(e, src_dev, descs, n, PreOut::NCHW_F32, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int fx_preprocess(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, int n, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (n < 0 || n > e->max_batch || (n > 0 && (!src_dev || !descs))) return set_error(e, FX_ERR_INVALID, "fx_preprocess: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    e->staged = 0;
+    int rc = preprocess_run(e, src_dev, descs, n, e->precision == FX_PRECISION_BF16 ? PreOut::IN0_BF16 : PreOut::IN0_F32, e->in0,
+                            static_cast<cudaStream_t>(stream));
+    if (rc == FX_OK) e->staged = n;
+    return rc;
+}
+
+int fx_stage_nchw_f32(fx_handle e, const float* in_dev, int n, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (n < 0 || n > e->max_batch || (n > 0 && !in_dev)) return set_error(e, FX_ERR_INVALID, "fx_stage_nchw_f32: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    e->staged = 0;
+    int rc = stage_nchw_run(e, in_dev, n, static_cast<cudaStream_t>(stream));
+    if (rc == FX_OK) e->staged = n;
+    return rc;
+}
+
+int fx_forward(fx_handle e, int n, float* emb_dev, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (!e->weights_loaded) return set_error(e, FX_ERR_STATE, "fx_forward: fx_load_weights has not succeeded");
+    if (n < 0 || n > e->staged) return set_error(e, FX_ERR_STATE, "fx_forward: more images requested than staged");
+    if (n == 0) return FX_OK;
+    if (!emb_dev) return set_error(e, FX_ERR_INVALID, "fx_forward: null output");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    return forward(e, n, emb_dev, static_cast<cudaStream_t>(stream));
+}
+
+int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, int n, float* emb_dev, void* stream) {
+    int rc = fx_preprocess(e, src_dev, descs, n, stream);
+    if (rc != FX_OK) return rc;
+    return fx_forward(e, n, emb_dev, stream);
+}
+
+int fx_embed_host(fx_handle e, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n, float* emb_host) {
+    if (!e) return FX_ERR_INVALID;
+    if (n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || !emb_host)))
+        return set_error(e, FX_ERR_INVALID, "fx_embed_host: bad arguments");
+    if (n == 0) return FX_OK;
+    for (int i = 0; i < n; ++i) {
+        const size_t need = descs[i].offset + (size_t)descs[i].height * descs[i].width * descs[i].channels;
+        if (descs[i].height < 1 || descs[i].width < 1 || need > total_bytes)
+            return set_error(e, FX_ERR_INVALID, "fx_embed_host: image " + std::to_string(i) + " lies outside the buffer");
+    }
+    FX_CUDA(e, cudaSetDevice(e->device));
+    if (total_bytes > e->h2d_cap) {
+        FX_CUDA(e, cudaStreamSynchronize(e->own_stream));
+        cudaFree(e->h2d_dev);
+        e->h2d_dev = nullptr;
+        e->h2d_cap = 0;
+        const size_t cap = total_bytes + total_bytes / 4 + 256;
+        cudaError_t a = cudaMalloc(&e->h2d_dev, cap);
+        if (a != cudaSuccess) return set_error(e, FX_ERR_NOMEM, std::string("cudaMalloc(h2d staging): ") + cudaGetErrorString(a));
+        e->h2d_cap = cap;
+    }
+    cudaStream_t s = e->own_stream;
+    FX_CUDA(e, cudaMemcpyAsync(e->h2d_dev, src_host, total_bytes, cudaMemcpyHostToDevice, s));
+    int rc = fx_embed(e, e->h2d_dev, descs, n, e->emb_dev, s);
+    if (rc != FX_OK) return rc;
+    FX_CUDA(e, cudaMemcpyAsync(emb_host, e->emb_dev, sizeof(float) * kEmbed * n, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(e, cudaStreamSynchronize(s));
+    return FX_OK;
+}
+
+uint64_t fx_launch_count(fx_handle e) { return e ? e->launches : 0; }
+
+// ---- test / inspection entry points -------------------------------------------------------
+
+int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const float* in_dev, const float* residual_dev, int n,
+                  int relu, float* out_dev, void* stream_) {
+    if (!e) return FX_ERR_INVALID;
+    if (!layer || !in_dev || !out_dev || n < 1 || n > e->max_batch) return set_error(e, FX_ERR_INVALID, "fx_debug_conv: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PackedLayer L;
+    int rc = pack_layer(e, *layer, hin, win, L);
+    if (rc != FX_OK) {
+        free_layer(L);
+        return rc;
+    }
+    const LayerGeom& g = L.g;
+    const size_t in_count = (size_t)n * hin * win * g.cin, out_count = (size_t)n * g.hout * g.wout * g.cout;
+    const bool bf16 = e->precision == FX_PRECISION_BF16;
+    const bool stem = g.cin == 3;
+    if (stem && (hin != kCrop || win != kCrop)) {
+        free_layer(L);
+        return set_error(e, FX_ERR_UNSUPPORTED, "fx_debug_conv: 3-channel input must be 224x224");
+    }
+    const size_t small_cap = (size_t)e->max_batch * 56 * 56 * 64, big_cap = (size_t)e->max_batch * 112 * 112 * 64;
+    if ((!stem && in_count > small_cap) || out_count > big_cap || (residual_dev && out_count > small_cap)) {
+        free_layer(L);
+        return set_error(e, FX_ERR_INVALID, "fx_debug_conv: activation larger than the engine workspace");
+    }
+    do {
+        const void* in_act = in_dev;
+        if (stem) {
+            if ((rc = pad_nhwc3_to_in0(e, in_dev, e->in0, bf16, n, stream)) != FX_OK) break;
+            in_act = e->in0;
+        }
+        if (!bf16) {
+            if (stem)
+                rc = simt_conv(e, L, static_cast<const float*>(in_act), kIn0H, kIn0W, kIn0C, 0, residual_dev, out_dev, n, relu, stream);
+            else
+                rc = simt_conv(e, L, in_dev, hin, win, g.cin, g.pad, residual_dev, out_dev, n, relu, stream);
+            break;
+        }
+        __nv_bfloat16* bin = static_cast<__nv_bfloat16*>(e->act[0]);
+        __nv_bfloat16* bres = static_cast<__nv_bfloat16*>(e->act[2]);
+        __nv_bfloat16* bout = static_cast<__nv_bfloat16*>(e->act[1]);
+        if (!stem) {
+            if ((rc = f32_to_bf16(e, in_dev, bin, in_count, stream)) != FX_OK) break;
+            in_act = bin;
+        }
+        if (residual_dev && (rc = f32_to_bf16(e, residual_dev, bres, out_count, stream)) != FX_OK) break;
+        if ((rc = tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, nullptr, n,
+                                 relu, stream)) != FX_OK)
+            break;
+        rc = bf16_to_f32(e, bout, out_dev, out_count, stream);
+    } while (0);
+    cudaError_t serr = cudaStreamSynchronize(stream);  // the packed weights are freed below
+    free_layer(L);
+    if (rc == FX_OK && serr != cudaSuccess) rc = set_error(e, FX_ERR_CUDA, std::string("fx_debug_conv: ") + cudaGetErrorString(serr));
+    return rc;
+}
+
+int fx_debug_folded(fx_handle e, int layer, float* weight_host, float* bias_host) {
+    if (!e) return FX_ERR_INVALID;
+    if (!e->weights_loaded || layer < 0 || layer >= kNumLayers) return set_error(e, FX_ERR_INVALID, "fx_debug_folded: bad layer");
+    const PackedLayer& L = e->layers[layer];
+    if (weight_host) std::memcpy(weight_host, L.host_w.data(), sizeof(float) * L.host_w.size());
+    if (bias_host) std::memcpy(bias_host, L.host_b.data(), sizeof(float) * L.host_b.size());
+    return FX_OK;
+}
+
+int fx_debug_tma_probe(fx_handle e, const void* base_dev, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                       const uint32_t* elem_strides, int swizzle, const int* coords, int bytes, uint8_t* out_dev) {
+    if (!e) return FX_ERR_INVALID;
+    FX_CUDA(e, cudaSetDevice(e->device));
+    int rc = tc_tma_probe(e, base_dev, dims, strides_bytes, box, elem_strides, swizzle, coords, bytes, out_dev, nullptr);
+    if (rc != FX_OK) return rc;
+    FX_CUDA(e, cudaDeviceSynchronize());
+    return FX_OK;
+}
+
+// Host-side pieces of the preprocess, exposed so that CPU-only tests can check them without a GPU.
+int fx_host_resized_size(int h, int w, int* oh, int* ow) {
+    if (!oh || !ow || h < 1 || w < 1) return FX_ERR_INVALID;
+    resized_size(h, w, *oh, *ow);
+    return FX_OK;
+}
+int fx_host_crop_offset(int size) { return crop_offset(size); }
+int fx_host_coeffs(int in_size, int out_size, int32_t* xmin, int32_t* count, int32_t* taps, int taps_capacity) {
+    if (in_size < 1 || out_size < 1) return FX_ERR_INVALID;
+    std::vector<int32_t> mn, ct, kk;
+    int ks = 0;
+    pillow_coeffs(in_size, out_size, mn, ct, kk, ks);
+    if (!xmin || !count || !taps) return ks;
+    if (taps_capacity < ks * out_size) return FX_ERR_INVALID;
+    std::memcpy(xmin, mn.data(), sizeof(int32_t) * out_size);
+    std::memcpy(count, ct.data(), sizeof(int32_t) * out_size);
+    std::memcpy(taps, kk.data(), sizeof(int32_t) * kk.size());
+    return ks;
+}
+
+}  // extern "C"

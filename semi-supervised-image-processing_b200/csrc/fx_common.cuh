@@ -1,0 +1,164 @@
+// Shared declarations of the B200 feature-extraction library (internal; the public C ABI is
+// include/fx_b200.h).  sm_100a only.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/fx_b200.h"
+
+namespace fx {
+
+constexpr int kCrop = FX_CROP;      // 224
+constexpr int kResize = FX_RESIZE;  // 256
+constexpr int kEmbed = FX_EMBED_DIM;
+constexpr int kNumLayers = FX_NUM_CONV_LAYERS;
+
+// conv1 staging buffer: the normalised crop, channel-padded 3 -> 4 and spatially padded so that
+// conv1 (7x7, stride 2, pad 3) needs no out-of-bounds handling: pixel (y, x) of the crop lives at
+// [y + kIn0Pad][x + kIn0Pad].  230 x 232 x 4; the pad is zero (conv zero padding of the
+// NORMALISED tensor, torchvision/models/resnet.py:197).
+constexpr int kIn0Pad = 3;
+constexpr int kIn0H = kCrop + 6;  // 230
+constexpr int kIn0W = kCrop + 8;  // 232: 8-pixel windows starting at 2*ow stay inside the row
+constexpr int kIn0C = 4;
+
+struct LayerGeom {
+    int cin, cout, kh, kw, stride, pad;
+    int hin, win, hout, wout;  // logical activation sizes
+};
+
+// ---------------------------------------------------------------------------------------------
+// Preprocess geometry: Pillow's coefficient tables for one (height, width), already composed with
+// the centre crop.  Built on the host in double precision (preprocess.cu), cached per size.
+// ---------------------------------------------------------------------------------------------
+struct GeomTableHost {
+    int h, w;
+    int ksh, ksv;            // taps per output sample, horizontal / vertical
+    int band;                // output rows per thread block
+    int max_rows;            // source rows a band touches (upper bound)
+    int col_lo, col_hi;      // source pixel columns touched by the crop [lo, hi)
+    std::vector<int32_t> blob;  // packed device image, layout in preprocess.cu
+};
+
+struct GeomEntry {
+    int32_t* dev = nullptr;  // device copy of blob
+    int ksh = 0, ksv = 0, band = 0, max_rows = 0, col_lo = 0, col_hi = 0;
+};
+
+// Per-image record consumed by the preprocess kernel.
+struct ImgDev {
+    unsigned long long src_off;
+    const int32_t* geom;
+    int h, w, c;
+    int ksh, ksv, band, col_lo, col_hi;
+};
+
+struct PackedLayer {
+    LayerGeom g{};
+    // fp32 pack: [cout][kh][kw][cin_pad]  (cin_pad = 4 for conv1, else cin)
+    float* w_f32 = nullptr;
+    // bf16 pack: GEMM B matrix [cout][K], K ordered (kh, kw, cin) -- conv1: (kh, 8 px, 4 ch)
+    __nv_bfloat16* w_bf16 = nullptr;
+    float* bias = nullptr;
+    int k_bf16 = 0;
+    std::vector<float> host_w;  // folded, [cout][kh][kw][cin] (bf16-rounded in BF16 precision)
+    std::vector<float> host_b;
+};
+
+}  // namespace fx
+
+struct fx_engine {
+    int device = 0;
+    int max_batch = 0;
+    int precision = FX_PRECISION_BF16;
+    int sm_count = 148;
+    bool weights_loaded = false;
+    int staged = 0;  // images currently in the conv1 staging buffer
+    uint64_t launches = 0;
+    std::string err;
+
+    // preprocess
+    float* lut_f32 = nullptr;            // [3][256]
+    __nv_bfloat16* lut_bf16 = nullptr;   // [3][256]
+    std::map<std::pair<int, int>, fx::GeomEntry> geoms;
+    fx::ImgDev* img_dev = nullptr;       // [max_batch]
+    fx::ImgDev* img_host = nullptr;      // pinned, [max_batch]
+    cudaEvent_t img_host_free = nullptr; // img_host may be rewritten once this has fired
+
+    // trunk
+    fx::PackedLayer layers[fx::kNumLayers];
+    void* in0 = nullptr;       // [max_batch][230][232][4], bf16 or fp32
+    void* act[3] = {nullptr, nullptr, nullptr};  // ping-pong activations (NHWC)
+    float* final_f32 = nullptr;  // [max_batch][49][512]
+    size_t act_bytes = 0;
+    void* tc_state = nullptr;  // tcgen05 path: tensor maps etc. (conv_tc.cu)
+
+    // host staging for fx_embed_host
+    uint8_t* h2d_dev = nullptr;
+    size_t h2d_cap = 0;
+    float* emb_dev = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+namespace fx {
+
+int set_error(fx_engine* e, int code, const std::string& msg);
+const char* cuda_err_text(cudaError_t err);
+
+#define FX_CUDA(e, call)                                                                             \
+    do {                                                                                             \
+        cudaError_t _err = (call);                                                                   \
+        if (_err != cudaSuccess)                                                                     \
+            return fx::set_error((e), FX_ERR_CUDA,                                                   \
+                                 std::string(#call) + ": " + cudaGetErrorString(_err));              \
+    } while (0)
+
+#define FX_LAUNCH_CHECK(e, name)                                                                     \
+    do {                                                                                             \
+        cudaError_t _err = cudaGetLastError();                                                       \
+        if (_err != cudaSuccess)                                                                     \
+            return fx::set_error((e), FX_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(_err)); \
+        (e)->launches++;                                                                             \
+    } while (0)
+
+// preprocess.cu
+enum class PreOut : int { NCHW_F32 = 0, IN0_BF16 = 1, IN0_F32 = 2 };
+int preprocess_init(fx_engine* e);
+void preprocess_free(fx_engine* e);
+int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode,
+                   void* out, cudaStream_t stream);
+int stage_nchw_run(fx_engine* e, const float* in_dev, int n, cudaStream_t stream);
+// host-only helpers (also exported for tests through the debug ABI)
+void pillow_coeffs(int in_size, int out_size, std::vector<int32_t>& xmin, std::vector<int32_t>& cnt,
+                   std::vector<int32_t>& kk, int& ksize);
+void resized_size(int h, int w, int& oh, int& ow);
+int crop_offset(int size);
+
+// trunk_simt.cu (fp32 tight-tolerance path + pooling / layout kernels shared by both paths)
+int simt_conv(fx_engine* e, const PackedLayer& L, const float* in, int hin_phys, int win_phys, int cin_phys,
+              int pad, const float* residual, float* out, int n, int relu, cudaStream_t stream);
+int maxpool_3x3s2(fx_engine* e, const void* in, void* out, int n, int h, int w, int c, bool bf16,
+                  cudaStream_t stream);
+int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n, int hw, int c,
+                cudaStream_t stream);
+int f32_to_bf16(fx_engine* e, const float* in, __nv_bfloat16* out, size_t count, cudaStream_t stream);
+int bf16_to_f32(fx_engine* e, const __nv_bfloat16* in, float* out, size_t count, cudaStream_t stream);
+int pad_nhwc3_to_in0(fx_engine* e, const float* in_nhwc3, void* in0, bool bf16, int n, cudaStream_t stream);
+
+// conv_tc.cu (bf16 tcgen05 implicit-GEMM path)
+int tc_init(fx_engine* e);
+void tc_free(fx_engine* e);
+// Runs layer `li` on NHWC bf16 activations.  out_f32 != nullptr: write fp32 instead of bf16.
+int tc_conv(fx_engine* e, int li, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+            float* out_f32, int n, int relu, cudaStream_t stream);
+
+}  // namespace fx

@@ -1,0 +1,483 @@
+// Fused preprocess: Resize(256) [Pillow fixed-point antialiased bilinear] -> CenterCrop(224) ->
+// ToTensor -> Normalize, one kernel, uint8 HWC in HBM -> normalised tensor in HBM.
+//
+// Replaces build_transform()/preprocess_image of the reference (src/feature_extraction.py:184-207,
+// 233-240).  The arithmetic being reproduced is third-party (torchvision 0.26 transforms calling
+// Pillow 12.2 Image.resize(BILINEAR)); SURVEY.md Appendix A is the specification followed here:
+//   - 22-bit fixed-point coefficients derived in DOUBLE on the host, cached per (height, width);
+//   - horizontal pass first, rounded and clipped to uint8, then the vertical pass on that
+//     uint8 intermediate, rounded and clipped to uint8;
+//   - crop offsets with Python's round-half-to-even;
+//   - /255 and (x-mean)/std are per-value fp32 functions of a byte -> a 3x256 table built with
+//     the same fp32 operations torch performs.
+// Integer work: results are bit-exact, not "close".
+//
+// Data movement (HBM-bound kernel): a thread block owns one band of output rows of one image.
+// Each warp streams whole source rows (only the byte range the crop touches) from HBM into
+// shared memory with 16-byte loads, runs the horizontal pass out of shared memory into a shared
+// uint8 band, and after one barrier the block runs the vertical pass + table lookup and writes
+// the output with coalesced stores.  Every source byte the crop needs is read once per band
+// (bands overlap by the filter support, which stays in L2).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "fx_common.cuh"
+
+namespace fx {
+
+// ------------------------------------------------------------------------------------------
+// Host: coefficient tables
+// ------------------------------------------------------------------------------------------
+
+static inline double tri_filter(double x) {
+    if (x < 0.0) x = -x;
+    return x < 1.0 ? 1.0 - x : 0.0;
+}
+
+// One axis of the resampler: for every output index the first source index, the tap count and the
+// fixed-point taps (1 << 22 scale).
+void pillow_coeffs(int in_size, int out_size, std::vector<int32_t>& xmin, std::vector<int32_t>& cnt,
+                   std::vector<int32_t>& kk, int& ksize) {
+    const double scale = (double)in_size / (double)out_size;
+    const double fscale = scale < 1.0 ? 1.0 : scale;  // antialias only when shrinking
+    const double support = 1.0 * fscale;              // triangle filter support is 1.0
+    ksize = (int)std::ceil(support) * 2 + 1;
+    xmin.assign(out_size, 0);
+    cnt.assign(out_size, 0);
+    kk.assign((size_t)out_size * ksize, 0);
+    std::vector<double> w(ksize);
+    const double inv = 1.0 / fscale;
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = (xx + 0.5) * scale;
+        int lo = (int)(center - support + 0.5);
+        if (lo < 0) lo = 0;
+        int hi = (int)(center + support + 0.5);
+        if (hi > in_size) hi = in_size;
+        const int n = hi - lo;
+        double total = 0.0;
+        for (int x = 0; x < n; ++x) {
+            w[x] = tri_filter((x + lo - center + 0.5) * inv);
+            total += w[x];
+        }
+        for (int x = 0; x < n; ++x) {
+            if (total != 0.0) w[x] /= total;
+            const double v = w[x] * (double)(1 << 22);
+            kk[(size_t)xx * ksize + x] = v < 0 ? (int32_t)(-0.5 + v) : (int32_t)(0.5 + v);
+        }
+        xmin[xx] = lo;
+        cnt[xx] = n;
+    }
+}
+
+// torchvision _compute_resized_output_size for Resize(256): short side -> 256, long side truncated.
+void resized_size(int h, int w, int& oh, int& ow) {
+    const int short_side = w <= h ? w : h, long_side = w <= h ? h : w;
+    const int new_long = (int)((double)((long long)kResize * long_side) / (double)short_side);
+    if (w <= h) {
+        ow = kResize;
+        oh = new_long;
+    } else {
+        ow = new_long;
+        oh = kResize;
+    }
+}
+
+// int(round((size - 224) / 2.0)) with Python's banker's rounding.
+int crop_offset(int size) {
+    const int d = size - kCrop;
+    const int q = d / 2;
+    if ((d & 1) == 0) return q;
+    return (q & 1) == 0 ? q : q + 1;
+}
+
+// Device blob layout (int32 words):
+//   [0,224)    hx_min   first source column of output column x (crop-relative x)
+//   [224,448)  hx_cnt
+//   [448,672)  vy_min   first source row of output row y
+//   [672,896)  vy_cnt
+//   [896, 896+224*ksh)  horizontal taps
+//   [.., +224*ksv)      vertical taps
+constexpr int kGeomHdr = 4 * kCrop;
+constexpr int kMaxTmpRows = 48;
+
+static void axis_for_crop(int in_size, int out_size, int crop_off, std::vector<int32_t>& mn, std::vector<int32_t>& ct,
+                          std::vector<int32_t>& kk, int& ks) {
+    mn.resize(kCrop);
+    ct.resize(kCrop);
+    if (in_size == out_size) {  // Pillow skips the pass: identity, one tap of weight 1.0
+        ks = 1;
+        kk.assign(kCrop, 1 << 22);
+        for (int i = 0; i < kCrop; ++i) {
+            mn[i] = crop_off + i;
+            ct[i] = 1;
+        }
+        return;
+    }
+    std::vector<int32_t> amn, act, akk;
+    pillow_coeffs(in_size, out_size, amn, act, akk, ks);
+    kk.resize((size_t)kCrop * ks);
+    for (int i = 0; i < kCrop; ++i) {
+        mn[i] = amn[crop_off + i];
+        ct[i] = act[crop_off + i];
+        std::memcpy(&kk[(size_t)i * ks], &akk[(size_t)(crop_off + i) * ks], sizeof(int32_t) * ks);
+    }
+}
+
+static bool build_geom(int h, int w, GeomTableHost& g) {
+    int oh, ow;
+    resized_size(h, w, oh, ow);
+    if (oh < kCrop || ow < kCrop) return false;
+    const int top = crop_offset(oh), left = crop_offset(ow);
+    std::vector<int32_t> hmn, hct, hk, vmn, vct, vk;
+    axis_for_crop(w, ow, left, hmn, hct, hk, g.ksh);
+    axis_for_crop(h, oh, top, vmn, vct, vk, g.ksv);
+    g.h = h;
+    g.w = w;
+    g.col_lo = hmn[0];
+    g.col_hi = hmn[kCrop - 1] + hct[kCrop - 1];
+    g.band = 0;
+    for (int band = 16; band >= 1; band >>= 1) {
+        int worst = 0;
+        for (int y0 = 0; y0 < kCrop; y0 += band) {
+            const int y1 = std::min(kCrop, y0 + band) - 1;
+            worst = std::max(worst, vmn[y1] + vct[y1] - vmn[y0]);
+        }
+        if (worst <= kMaxTmpRows) {
+            g.band = band;
+            g.max_rows = worst;
+            break;
+        }
+    }
+    if (g.band == 0) return false;  // down-scaling factor too large for the shared-memory band
+    g.blob.resize(kGeomHdr + (size_t)kCrop * (g.ksh + g.ksv));
+    std::memcpy(&g.blob[0], hmn.data(), sizeof(int32_t) * kCrop);
+    std::memcpy(&g.blob[kCrop], hct.data(), sizeof(int32_t) * kCrop);
+    std::memcpy(&g.blob[2 * kCrop], vmn.data(), sizeof(int32_t) * kCrop);
+    std::memcpy(&g.blob[3 * kCrop], vct.data(), sizeof(int32_t) * kCrop);
+    std::memcpy(&g.blob[kGeomHdr], hk.data(), sizeof(int32_t) * hk.size());
+    std::memcpy(&g.blob[kGeomHdr + (size_t)kCrop * g.ksh], vk.data(), sizeof(int32_t) * vk.size());
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device
+// ------------------------------------------------------------------------------------------
+
+constexpr int kPreThreads = 256;
+constexpr int kPreWarps = kPreThreads / 32;
+constexpr int kRowBufCap = 6144;  // bytes of one staged source row per warp (2032 RGB pixels)
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int clip8(int acc) {
+    const int v = acc >> 22;
+    return min(max(v, 0), 255);
+}
+
+// MODE: 0 = fp32 NCHW [n][3][224][224]; 1 = bf16 conv1 staging; 2 = fp32 conv1 staging.
+template <int MODE>
+__global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ src,
+                                                                 const ImgDev* __restrict__ imgs,
+                                                                 void* __restrict__ out,
+                                                                 const float* __restrict__ lut_f32,
+                                                                 const __nv_bfloat16* __restrict__ lut_bf16,
+                                                                 int tmp_bytes, int rowbuf_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const ImgDev img = imgs[blockIdx.y];
+    const int y0 = blockIdx.x * img.band;
+    if (y0 >= kCrop) return;
+    const int y1 = min(kCrop, y0 + img.band);
+    const int C = img.c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    float* s_lut = reinterpret_cast<float*>(smem);                 // [3][256] fp32 (MODE 0/2)
+    __nv_bfloat16* s_lutb = reinterpret_cast<__nv_bfloat16*>(smem);  // [3][256] bf16 (MODE 1)
+    uint8_t* s_tmp = smem + 3072;                                   // [rows][224*C]
+    uint8_t* s_row = s_tmp + tmp_bytes + warp * rowbuf_bytes;       // per-warp staged source row
+
+    if (MODE == 1) {
+        for (int i = tid; i < 768; i += kPreThreads) s_lutb[i] = lut_bf16[i];
+    } else {
+        for (int i = tid; i < 768; i += kPreThreads) s_lut[i] = lut_f32[i];
+    }
+
+    const int32_t* __restrict__ g = img.geom;
+    const int32_t* hx_min = g;
+    const int32_t* hx_cnt = g + kCrop;
+    const int32_t* vy_min = g + 2 * kCrop;
+    const int32_t* vy_cnt = g + 3 * kCrop;
+    const int32_t* hk = g + kGeomHdr;
+    const int32_t* vk = hk + kCrop * img.ksh;
+
+    const int rlo = __ldg(vy_min + y0);
+    const int rhi = __ldg(vy_min + y1 - 1) + __ldg(vy_cnt + y1 - 1);
+    const int nrows = rhi - rlo;
+    const int rowpix = kCrop * C;
+    const size_t pitch = (size_t)img.w * C;
+    const uint8_t* base = src + img.src_off;
+    const int span_bytes = (img.col_hi - img.col_lo) * C;
+    const bool staged = span_bytes + 32 <= rowbuf_bytes;
+
+    // ---- horizontal pass: source rows -> uint8 band in shared memory -------------------------
+    for (int r = warp; r < nrows; r += kPreWarps) {
+        const uint8_t* grow = base + (size_t)(rlo + r) * pitch + (size_t)img.col_lo * C;
+        const uint8_t* rowp;
+        if (staged) {
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(grow);
+            const uintptr_t a0 = ga & ~(uintptr_t)15;
+            const int shift = (int)(ga - a0);
+            const int nvec = (shift + span_bytes + 15) >> 4;
+            // every 16-byte chunk read holds at least one byte of this row, so it cannot leave the
+            // allocation the row lives in (allocations are at least 16-byte granular)
+            for (int j = lane; j < nvec; j += 32)
+                reinterpret_cast<uint4*>(s_row)[j] = ldg_stream16(reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)j));
+            __syncwarp();
+            rowp = s_row + shift;
+        } else {
+            rowp = grow;  // very wide rows: taps straight from global / L1
+        }
+        uint8_t* trow = s_tmp + r * rowpix;
+        for (int x = lane; x < kCrop; x += 32) {
+            const int xm = (__ldg(hx_min + x) - img.col_lo) * C;
+            const int n = __ldg(hx_cnt + x);
+            const int32_t* k = hk + x * img.ksh;
+            if (C == 3) {
+                int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+                for (int i = 0; i < n; ++i) {
+                    const int kv = __ldg(k + i);
+                    const uint8_t* p = rowp + xm + 3 * i;
+                    a0 += kv * (int)p[0];
+                    a1 += kv * (int)p[1];
+                    a2 += kv * (int)p[2];
+                }
+                trow[3 * x + 0] = (uint8_t)clip8(a0);
+                trow[3 * x + 1] = (uint8_t)clip8(a1);
+                trow[3 * x + 2] = (uint8_t)clip8(a2);
+            } else {
+                int a0 = 1 << 21;
+                for (int i = 0; i < n; ++i) a0 += __ldg(k + i) * (int)rowp[xm + i];
+                trow[x] = (uint8_t)clip8(a0);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- vertical pass + table lookup + store -------------------------------------------------
+    const int nout = (y1 - y0) * kCrop;
+    const size_t img_idx = blockIdx.y;
+    for (int idx = tid; idx < nout; idx += kPreThreads) {
+        const int yy = idx / kCrop;
+        const int x = idx - yy * kCrop;
+        const int y = y0 + yy;
+        const int ym = __ldg(vy_min + y) - rlo;
+        const int n = __ldg(vy_cnt + y);
+        const int32_t* k = vk + y * img.ksv;
+        int v0, v1, v2;
+        if (C == 3) {
+            int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+            const uint8_t* p = s_tmp + ym * rowpix + 3 * x;
+            for (int j = 0; j < n; ++j) {
+                const int kv = __ldg(k + j);
+                a0 += kv * (int)p[0];
+                a1 += kv * (int)p[1];
+                a2 += kv * (int)p[2];
+                p += rowpix;
+            }
+            v0 = clip8(a0);
+            v1 = clip8(a1);
+            v2 = clip8(a2);
+        } else {
+            int a0 = 1 << 21;
+            const uint8_t* p = s_tmp + ym * rowpix + x;
+            for (int j = 0; j < n; ++j) {
+                a0 += __ldg(k + j) * (int)p[0];
+                p += rowpix;
+            }
+            v0 = v1 = v2 = clip8(a0);  // gray carriage: one plane, three normalisations
+        }
+        if (MODE == 0) {
+            float* o = reinterpret_cast<float*>(out) + img_idx * 3 * kCrop * kCrop + (size_t)y * kCrop + x;
+            o[0] = s_lut[v0];
+            o[kCrop * kCrop] = s_lut[256 + v1];
+            o[2 * kCrop * kCrop] = s_lut[512 + v2];
+        } else {
+            const size_t pix = (img_idx * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
+            if (MODE == 1) {
+                const unsigned short b0 = __bfloat16_as_ushort(s_lutb[v0]);
+                const unsigned short b1 = __bfloat16_as_ushort(s_lutb[256 + v1]);
+                const unsigned short b2 = __bfloat16_as_ushort(s_lutb[512 + v2]);
+                uint2 pk;
+                pk.x = (unsigned)b0 | ((unsigned)b1 << 16);
+                pk.y = (unsigned)b2;
+                reinterpret_cast<uint2*>(out)[pix] = pk;
+            } else {
+                reinterpret_cast<float4*>(out)[pix] = make_float4(s_lut[v0], s_lut[256 + v1], s_lut[512 + v2], 0.f);
+            }
+        }
+    }
+}
+
+// fp32 NCHW [n][3][224][224] (the reference's batch tensor) -> conv1 staging layout.
+template <bool BF16>
+__global__ void stage_nchw_kernel(const float* __restrict__ in, void* __restrict__ out, int n) {
+    const size_t total = (size_t)n * kCrop * kCrop;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / (kCrop * kCrop);
+        const int rem = (int)(i - img * kCrop * kCrop);
+        const int y = rem / kCrop, x = rem - y * kCrop;
+        const float* p = in + img * 3 * kCrop * kCrop + rem;
+        const float c0 = p[0], c1 = p[kCrop * kCrop], c2 = p[2 * kCrop * kCrop];
+        const size_t pix = (img * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
+        if (BF16) {
+            uint2 pk;
+            pk.x = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c0)) |
+                   ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c1)) << 16);
+            pk.y = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c2));
+            reinterpret_cast<uint2*>(out)[pix] = pk;
+        } else {
+            reinterpret_cast<float4*>(out)[pix] = make_float4(c0, c1, c2, 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host driver
+// ------------------------------------------------------------------------------------------
+
+int preprocess_init(fx_engine* e) {
+    // ToTensor + Normalize as torch computes them (fp32 division by 255, fp32 subtract, fp32
+    // true division): torchvision/transforms/functional.py:166-178, _functional_tensor.py:916-928.
+    static const float mean[3] = {0.485f, 0.456f, 0.406f};  // src/feature_extraction.py:64
+    static const float stdv[3] = {0.229f, 0.224f, 0.225f};  // src/feature_extraction.py:65
+    std::vector<float> lut(768);
+    std::vector<__nv_bfloat16> lutb(768);
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < 256; ++v) {
+            volatile float x = (float)v / 255.0f;
+            volatile float y = x - mean[c];
+            volatile float z = y / stdv[c];
+            lut[c * 256 + v] = z;
+            lutb[c * 256 + v] = __float2bfloat16_rn(z);
+        }
+    FX_CUDA(e, cudaMalloc(&e->lut_f32, sizeof(float) * 768));
+    FX_CUDA(e, cudaMalloc(&e->lut_bf16, sizeof(__nv_bfloat16) * 768));
+    FX_CUDA(e, cudaMemcpy(e->lut_f32, lut.data(), sizeof(float) * 768, cudaMemcpyHostToDevice));
+    FX_CUDA(e, cudaMemcpy(e->lut_bf16, lutb.data(), sizeof(__nv_bfloat16) * 768, cudaMemcpyHostToDevice));
+    FX_CUDA(e, cudaMalloc(&e->img_dev, sizeof(ImgDev) * e->max_batch));
+    FX_CUDA(e, cudaMallocHost(&e->img_host, sizeof(ImgDev) * e->max_batch));
+    FX_CUDA(e, cudaEventCreateWithFlags(&e->img_host_free, cudaEventDisableTiming));
+    const int max_smem = 3072 + kMaxTmpRows * kCrop * 3 + kPreWarps * kRowBufCap;
+    FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return FX_OK;
+}
+
+void preprocess_free(fx_engine* e) {
+    for (auto& kv : e->geoms) cudaFree(kv.second.dev);
+    e->geoms.clear();
+    cudaFree(e->lut_f32);
+    cudaFree(e->lut_bf16);
+    cudaFree(e->img_dev);
+    if (e->img_host) cudaFreeHost(e->img_host);
+    if (e->img_host_free) cudaEventDestroy(e->img_host_free);
+}
+
+static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
+    auto key = std::make_pair(h, w);
+    auto it = e->geoms.find(key);
+    if (it == e->geoms.end()) {
+        GeomTableHost g;
+        if (h < 1 || w < 1 || !build_geom(h, w, g))
+            return set_error(e, FX_ERR_UNSUPPORTED,
+                             "image " + std::to_string(h) + "x" + std::to_string(w) +
+                                 ": unsupported geometry (empty, or down-scaling factor beyond the band buffer)");
+        GeomEntry ent;
+        ent.ksh = g.ksh;
+        ent.ksv = g.ksv;
+        ent.band = g.band;
+        ent.max_rows = g.max_rows;
+        ent.col_lo = g.col_lo;
+        ent.col_hi = g.col_hi;
+        FX_CUDA(e, cudaMalloc(&ent.dev, sizeof(int32_t) * g.blob.size()));
+        FX_CUDA(e, cudaMemcpy(ent.dev, g.blob.data(), sizeof(int32_t) * g.blob.size(), cudaMemcpyHostToDevice));
+        it = e->geoms.emplace(key, ent).first;
+    }
+    *out = &it->second;
+    return FX_OK;
+}
+
+int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode, void* out,
+                   cudaStream_t stream) {
+    if (n == 0) return FX_OK;
+    FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
+    int min_band = 16, max_tmp = 0, max_span = 0;
+    for (int i = 0; i < n; ++i) {
+        const fx_image_desc& d = descs[i];
+        if (d.channels != 3 && d.channels != 1)
+            return set_error(e, FX_ERR_UNSUPPORTED,
+                             "image " + std::to_string(i) + ": " + std::to_string(d.channels) +
+                                 " channels; the transform normalises exactly 3 (or a 1-channel gray carriage)");
+        GeomEntry* ge = nullptr;
+        int rc = geom_lookup(e, d.height, d.width, &ge);
+        if (rc != FX_OK) return rc;
+        ImgDev& im = e->img_host[i];
+        im.src_off = d.offset;
+        im.geom = ge->dev;
+        im.h = d.height;
+        im.w = d.width;
+        im.c = d.channels;
+        im.ksh = ge->ksh;
+        im.ksv = ge->ksv;
+        im.band = ge->band;
+        im.col_lo = ge->col_lo;
+        im.col_hi = ge->col_hi;
+        min_band = std::min(min_band, ge->band);
+        max_tmp = std::max(max_tmp, ge->max_rows * kCrop * d.channels);
+        max_span = std::max(max_span, (ge->col_hi - ge->col_lo) * d.channels + 32);
+    }
+    FX_CUDA(e, cudaMemcpyAsync(e->img_dev, e->img_host, sizeof(ImgDev) * n, cudaMemcpyHostToDevice, stream));
+    FX_CUDA(e, cudaEventRecord(e->img_host_free, stream));
+    const int tmp_bytes = (max_tmp + 15) & ~15;
+    const int rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
+    const int smem = 3072 + tmp_bytes + kPreWarps * rowbuf;
+    dim3 grid((kCrop + min_band - 1) / min_band, n);
+    switch (mode) {
+        case PreOut::NCHW_F32:
+            preprocess_kernel<0><<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32,
+                                                                       e->lut_bf16, tmp_bytes, rowbuf);
+            break;
+        case PreOut::IN0_BF16:
+            preprocess_kernel<1><<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32,
+                                                                       e->lut_bf16, tmp_bytes, rowbuf);
+            break;
+        case PreOut::IN0_F32:
+            preprocess_kernel<2><<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32,
+                                                                       e->lut_bf16, tmp_bytes, rowbuf);
+            break;
+    }
+    FX_LAUNCH_CHECK(e, "preprocess_kernel");
+    return FX_OK;
+}
+
+int stage_nchw_run(fx_engine* e, const float* in_dev, int n, cudaStream_t stream) {
+    if (n == 0) return FX_OK;
+    const size_t total = (size_t)n * kCrop * kCrop;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)e->sm_count * 16);
+    if (e->precision == FX_PRECISION_BF16)
+        stage_nchw_kernel<true><<<blocks, 256, 0, stream>>>(in_dev, e->in0, n);
+    else
+        stage_nchw_kernel<false><<<blocks, 256, 0, stream>>>(in_dev, e->in0, n);
+    FX_LAUNCH_CHECK(e, "stage_nchw_kernel");
+    return FX_OK;
+}
+
+}  // namespace fx

@@ -1,0 +1,251 @@
+"""Python handle on the CUDA engine (libfx_b200.so).  PyTorch is used here only for device memory
+and streams; all compute happens inside the library's hand-written sm_100a kernels.
+
+Stands in for ``load_model`` + the body of the batch loop of the reference
+(src/feature_extraction.py:210-227, 289-294).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+# fx_load_weights order (include/fx_b200.h): (conv weight key, bn prefix, stride, pad)
+LAYER_TABLE: List[Tuple[str, str, int, int]] = [("conv1.weight", "bn1", 2, 3)]
+for _s in range(1, 5):
+    for _b in range(2):
+        _stride = 2 if (_s > 1 and _b == 0) else 1
+        LAYER_TABLE.append((f"layer{_s}.{_b}.conv1.weight", f"layer{_s}.{_b}.bn1", _stride, 1))
+        LAYER_TABLE.append((f"layer{_s}.{_b}.conv2.weight", f"layer{_s}.{_b}.bn2", 1, 1))
+        if _s > 1 and _b == 0:
+            LAYER_TABLE.append((f"layer{_s}.{_b}.downsample.0.weight", f"layer{_s}.{_b}.downsample.1", 2, 0))
+assert len(LAYER_TABLE) == N.NUM_CONV_LAYERS
+
+_PRECISIONS = {"bf16": N.PRECISION_BF16, "fp32": N.PRECISION_FP32}
+_ALIGN = 256
+
+
+def pack_images(images: Sequence[np.ndarray], out: Optional[np.ndarray] = None):
+    """Lay decoded HWC uint8 images end to end (256-byte aligned starts).
+
+    Returns (buffer uint8 [total], descs ctypes array, total_bytes).  A 2-D array is a 1-channel
+    gray carriage (see fx_image_desc in include/fx_b200.h).
+    """
+    n = len(images)
+    descs = (N.ImageDesc * max(n, 1))()
+    off = 0
+    for i, a in enumerate(images):
+        if a.dtype != np.uint8 or a.ndim not in (2, 3):
+            raise TypeError(f"image {i}: expected HWC uint8, got {a.dtype} with shape {a.shape}")
+        c = 1 if a.ndim == 2 else a.shape[2]
+        descs[i].offset, descs[i].height, descs[i].width, descs[i].channels = off, a.shape[0], a.shape[1], c
+        off += (a.size + _ALIGN - 1) // _ALIGN * _ALIGN
+    total = off
+    if out is None:
+        out = np.empty(max(total, 1), np.uint8)
+    elif out.size < total:
+        raise ValueError("staging buffer too small")
+    for i, a in enumerate(images):
+        o = descs[i].offset
+        out[o : o + a.size] = np.ascontiguousarray(a).reshape(-1)
+    return out, descs, total
+
+
+def uniform_descs(n: int, h: int, w: int, c: int = 3):
+    """Descriptor table of n same-size images stored back to back without padding."""
+    descs = (N.ImageDesc * max(n, 1))()
+    for i in range(n):
+        descs[i].offset, descs[i].height, descs[i].width, descs[i].channels = i * h * w * c, h, w, c
+    return descs
+
+
+class Engine:
+    """One engine per GPU (``fx_create``)."""
+
+    def __init__(self, device_index: int = 0, max_batch: int = 256, precision: str = "bf16"):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self._lib = N.lib()
+        self.device_index = int(device_index)
+        self.max_batch = int(max_batch)
+        self.precision = precision
+        self._h = ctypes.c_void_p()
+        N.check(self._lib.fx_create(ctypes.byref(self._h), self.device_index, self.max_batch, _PRECISIONS[precision]))
+        self.device = torch.device("cuda", self.device_index)
+        self._keep = None
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.fx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status: int) -> None:
+        N.check(status, self._h)
+
+    def _stream(self) -> ctypes.c_void_p:
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.fx_launch_count(self._h))
+
+    # -- weights ------------------------------------------------------------------------------
+    def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
+        """Takes a torchvision resnet18 ``state_dict`` (fc.* ignored); BN is folded in the library."""
+        table = (N.ConvBn * N.NUM_CONV_LAYERS)()
+        keep = []
+
+        def fptr(t: torch.Tensor):
+            a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+        for i, (wkey, bn, stride, pad) in enumerate(LAYER_TABLE):
+            w = state[wkey]
+            e = table[i]
+            e.weight = fptr(w)
+            e.gamma, e.beta = fptr(state[bn + ".weight"]), fptr(state[bn + ".bias"])
+            e.mean, e.var = fptr(state[bn + ".running_mean"]), fptr(state[bn + ".running_var"])
+            e.eps = 1e-5  # torchvision BatchNorm2d default, resnet.py:43
+            e.cout, e.cin, e.kh, e.kw = (int(x) for x in w.shape)
+            e.stride, e.pad = stride, pad
+        self._check(self._lib.fx_load_weights(self._h, table, N.NUM_CONV_LAYERS))
+
+    def folded(self, layer: int, shape: Tuple[int, int, int, int]):
+        """Folded (weight [cout,kh,kw,cin], bias [cout]) of a loaded layer as the kernels see them."""
+        cout, kh, kw, cin = shape
+        w = np.empty((cout, kh, kw, cin), np.float32)
+        b = np.empty(cout, np.float32)
+        self._check(self._lib.fx_debug_folded(self._h, layer, w.ctypes.data, b.ctypes.data))
+        return w, b
+
+    # -- preprocess ---------------------------------------------------------------------------
+    def preprocess_nchw(self, packed_dev: torch.Tensor, descs, n: int) -> torch.Tensor:
+        """Fused Resize/CenterCrop/ToTensor/Normalize -> fp32 [n,3,224,224] (the reference's batch tensor)."""
+        self._dev_u8(packed_dev)
+        out = torch.empty((n, 3, N.CROP, N.CROP), dtype=torch.float32, device=self.device)
+        self._check(self._lib.fx_preprocess_nchw_f32(self._h, packed_dev.data_ptr(), descs, n, out.data_ptr(), self._stream()))
+        return out
+
+    # -- trunk --------------------------------------------------------------------------------
+    def forward_nchw(self, x_dev: torch.Tensor) -> torch.Tensor:
+        """Trunk only, on an already normalised fp32 [n,3,224,224] CUDA tensor."""
+        if x_dev.dtype != torch.float32 or not x_dev.is_cuda or not x_dev.is_contiguous() or tuple(x_dev.shape[1:]) != (3, N.CROP, N.CROP):
+            raise TypeError("expected a contiguous fp32 CUDA tensor [n,3,224,224]")
+        n = x_dev.shape[0]
+        out = torch.empty((n, N.EMBED_DIM), dtype=torch.float32, device=self.device)
+        self._check(self._lib.fx_stage_nchw_f32(self._h, x_dev.data_ptr(), n, self._stream()))
+        self._check(self._lib.fx_forward(self._h, n, out.data_ptr(), self._stream()))
+        return out
+
+    # -- whole path ---------------------------------------------------------------------------
+    def embed_device(self, packed_dev: torch.Tensor, descs, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Preprocess + trunk on device-resident uint8 images -> fp32 [n,512] on the device."""
+        self._dev_u8(packed_dev)
+        if out is None:
+            out = torch.empty((n, N.EMBED_DIM), dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or out.numel() < n * N.EMBED_DIM:
+            raise TypeError("out must be a contiguous fp32 CUDA tensor with room for [n,512]")
+        self._check(self._lib.fx_embed(self._h, packed_dev.data_ptr(), descs, n, out.data_ptr(), self._stream()))
+        return out
+
+    def embed_host(self, packed_host, descs, n: int, total_bytes: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host uint8 images in, host fp32 [n,512] out; both copies happen inside the call."""
+        if isinstance(packed_host, torch.Tensor):
+            src_ptr = packed_host.data_ptr()
+        else:
+            src_ptr = packed_host.ctypes.data
+        if out is None:
+            out = np.empty((n, N.EMBED_DIM), np.float32)
+        dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        self._check(self._lib.fx_embed_host(self._h, src_ptr, total_bytes, descs, n, dst_ptr))
+        return out
+
+    def embed_images(self, images: Sequence[np.ndarray]) -> np.ndarray:
+        """Convenience: list of decoded HWC uint8 arrays -> [n,512] (chunks of max_batch)."""
+        chunks = []
+        for s in range(0, len(images), self.max_batch):
+            part = images[s : s + self.max_batch]
+            buf, descs, total = pack_images(part)
+            chunks.append(self.embed_host(buf, descs, len(part), total))
+        return np.concatenate(chunks, axis=0) if chunks else np.empty((0, N.EMBED_DIM), np.float32)
+
+    # -- test hooks ---------------------------------------------------------------------------
+    def debug_conv(self, weight: torch.Tensor, bn: Optional[Dict[str, torch.Tensor]], stride: int, pad: int,
+                   x_nhwc: torch.Tensor, residual_nhwc: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+        """Run one conv+bn group through the library: x fp32 NHWC CUDA -> fp32 NHWC CUDA."""
+        cout, cin, kh, kw = (int(v) for v in weight.shape)
+        n, hin, win, _ = (int(v) for v in x_nhwc.shape)
+        keep = []
+
+        def fptr(t):
+            a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+        if bn is None:
+            bn = {"weight": torch.ones(cout), "bias": torch.zeros(cout), "running_mean": torch.zeros(cout),
+                  "running_var": torch.ones(cout) - 1e-5}
+        e = N.ConvBn()
+        e.weight = fptr(weight)
+        e.gamma, e.beta, e.mean, e.var = fptr(bn["weight"]), fptr(bn["bias"]), fptr(bn["running_mean"]), fptr(bn["running_var"])
+        e.eps = 1e-5
+        e.cout, e.cin, e.kh, e.kw, e.stride, e.pad = cout, cin, kh, kw, stride, pad
+        ho, wo = (hin + 2 * pad - kh) // stride + 1, (win + 2 * pad - kw) // stride + 1
+        out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=self.device)
+        x = x_nhwc.contiguous()
+        r = residual_nhwc.contiguous() if residual_nhwc is not None else None
+        self._check(self._lib.fx_debug_conv(self._h, ctypes.byref(e), hin, win, x.data_ptr(), r.data_ptr() if r is not None else None,
+                                            n, int(relu), out.data_ptr(), self._stream()))
+        return out
+
+    def tma_probe(self, base: torch.Tensor, dims, strides_bytes, box, elem_strides, swizzle: int, coords, nbytes: int) -> torch.Tensor:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        a = (ctypes.c_uint64 * 4)(*dims)
+        s = (ctypes.c_uint64 * 3)(*strides_bytes)
+        b = (ctypes.c_uint32 * 4)(*box)
+        es = (ctypes.c_uint32 * 4)(*elem_strides)
+        c = (ctypes.c_int * 4)(*coords)
+        torch.cuda.synchronize(self.device)
+        self._check(self._lib.fx_debug_tma_probe(self._h, base.data_ptr(), a, s, b, es, swizzle, c, nbytes, out.data_ptr()))
+        return out
+
+    def _dev_u8(self, t: torch.Tensor) -> None:
+        if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous() or t.device.index != self.device_index:
+            raise TypeError(f"expected a contiguous uint8 tensor on cuda:{self.device_index}")
+
+
+def host_resized_size(h: int, w: int) -> Tuple[int, int]:
+    oh, ow = ctypes.c_int(), ctypes.c_int()
+    N.check(N.lib().fx_host_resized_size(h, w, ctypes.byref(oh), ctypes.byref(ow)))
+    return oh.value, ow.value
+
+
+def host_crop_offset(size: int) -> int:
+    return int(N.lib().fx_host_crop_offset(size))
+
+
+def host_coeffs(in_size: int, out_size: int):
+    """Pillow's fixed-point coefficient table as the library computes it (host code, no GPU)."""
+    L = N.lib()
+    ks = L.fx_host_coeffs(in_size, out_size, None, None, None, 0)
+    if ks < 0:
+        raise N.FxError(ks, "fx_host_coeffs")
+    xmin = np.zeros(out_size, np.int32)
+    cnt = np.zeros(out_size, np.int32)
+    taps = np.zeros((out_size, ks), np.int32)
+    rc = L.fx_host_coeffs(in_size, out_size, xmin.ctypes.data, cnt.ctypes.data, taps.ctypes.data, taps.size)
+    if rc < 0:
+        raise N.FxError(rc, "fx_host_coeffs")
+    return xmin, cnt, taps

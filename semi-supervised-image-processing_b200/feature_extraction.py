@@ -1,0 +1,548 @@
+"""Drop-in for ``src.feature_extraction`` of Septimus4/semi-supervised-image-processing, running
+the hot path on hand-written sm_100a CUDA (libfx_b200.so) instead of stock PyTorch.
+
+Same CLI (``--data-dir --device --batch-size --verbose``, src/feature_extraction.py:510-535), same
+importable names and the same five artifacts under ``outputs/``:
+
+    python -m ssip_b200.feature_extraction --data-dir mri_dataset_brain_cancer_oc --device cuda
+    torchrun --nproc-per-node 8 -m ssip_b200.feature_extraction --device cuda      # image-sharded
+
+What changes underneath: files are still decoded by Pillow on the host (a thread pool instead of
+a serial loop), but Resize(256)/CenterCrop(224)/ToTensor/Normalize is one fused CUDA kernel that
+reproduces the reference transform bit for bit, and the frozen ResNet-18 trunk runs as BN-folded
+implicit-GEMM convolutions on the tcgen05 tensor cores.  ``--device cpu`` is refused: this
+package has no CPU path (run the reference for that).
+
+Weights.  The reference hard-codes the IMAGENET1K_V1 download (src/feature_extraction.py:217-218)
+and so does this module by default.  Offline, point ``SSIP_B200_WEIGHTS`` at a torchvision
+resnet18 ``state_dict`` file, or set it to ``random:<seed>`` (``random-bn:<seed>`` additionally
+randomises the BatchNorm statistics) for a seeded random initialisation -- the parity tests and
+bench.py use that.  ``SSIP_B200_PRECISION`` = ``bf16`` (default) or ``fp32`` (tight tolerance).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import logging
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+from datetime import datetime, timezone
+from pathlib import Path
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from PIL import Image, UnidentifiedImageError
+
+from . import dist as fxdist
+from .engine import Engine, pack_images
+
+# --- constants: same names and values as src/feature_extraction.py:53-77 -------------------------
+DEFAULT_DATA_DIR = Path("mri_dataset_brain_cancer_oc")
+DEFAULT_OUTPUT_ROOT = Path("outputs")
+FEATURE_OUTPUT_DIR = DEFAULT_OUTPUT_ROOT / "features"
+LOG_OUTPUT_DIR = DEFAULT_OUTPUT_ROOT / "logs"
+NOTE_OUTPUT_DIR = DEFAULT_OUTPUT_ROOT / "notes"
+LOG_PATH = LOG_OUTPUT_DIR / "feature_extraction.log"
+EMBEDDING_ARRAY_PATH = FEATURE_OUTPUT_DIR / "embeddings.npy"
+EMBEDDING_CSV_PATH = FEATURE_OUTPUT_DIR / "embeddings.csv"
+METADATA_PATH = FEATURE_OUTPUT_DIR / "metadata.json"
+SUMMARY_NOTE_PATH = NOTE_OUTPUT_DIR / "feature_summary.md"
+
+IMAGENET_MEAN = [0.485, 0.456, 0.406]
+IMAGENET_STD = [0.229, 0.224, 0.225]
+TARGET_RESIZE = 256
+TARGET_CROP = 224
+BATCH_SIZE = 32
+NEIGHBOR_SAMPLE = 8
+RNG_SEED = 42
+
+LABELED_BUCKET = "avec_labels"
+UNLABELED_BUCKET = "sans_label"
+
+BACKBONE_NAME = "torchvision.resnet18"
+BACKBONE_WEIGHTS = "ResNet18_Weights.IMAGENET1K_V1"
+BACKBONE_LAYER = "global_avg_pool"
+
+WEIGHTS_ENV = "SSIP_B200_WEIGHTS"
+PRECISION_ENV = "SSIP_B200_PRECISION"
+GRAY_CARRIAGE_ENV = "SSIP_B200_GRAY_CARRIAGE"  # "1": ship R==G==B files as one plane
+DECODE_THREADS_ENV = "SSIP_B200_DECODE_THREADS"
+
+
+@dataclass(frozen=True)
+class ImageRecord:
+    """One dataset file (fields as src/feature_extraction.py:85-92)."""
+
+    absolute_path: Path
+    relative_path: Path
+    bucket: str
+    label: Optional[str]
+
+
+@dataclass
+class ExtractionResults:
+    """What extract_embeddings returns (fields as src/feature_extraction.py:95-102)."""
+
+    embeddings: np.ndarray
+    records: List[ImageRecord]
+    failures: List[Path]
+    per_file_times: List[float]
+
+
+# --- logging / discovery -------------------------------------------------------------------------
+
+
+def configure_logging(verbose: bool = False) -> None:
+    """File (rewritten every run) + stderr, reference format (src/feature_extraction.py:110-122)."""
+    LOG_OUTPUT_DIR.mkdir(parents=True, exist_ok=True)
+    logging.basicConfig(
+        level=logging.DEBUG if verbose else logging.INFO,
+        format="%(asctime)s [%(levelname)s] %(message)s",
+        handlers=[logging.FileHandler(LOG_PATH, mode="w", encoding="utf-8"), logging.StreamHandler()],
+    )
+
+
+def _files_under(root: Path) -> List[Path]:
+    return [p for p in sorted(root.rglob("*")) if p.is_file()]
+
+
+def discover_image_records(data_dir: Path) -> List[ImageRecord]:
+    """Deterministic record list: labeled (sorted label dirs, sorted files) then unlabeled.
+
+    Ordering, bucket names and error behaviour follow src/feature_extraction.py:125-181: every
+    regular file is a record (non-images become decode failures later), a missing bucket is a
+    warning, a missing directory FileNotFoundError, an empty dataset RuntimeError.
+    """
+    data_dir = Path(data_dir)
+    if not data_dir.exists():
+        raise FileNotFoundError(f"Data directory not found: {data_dir}")
+    found: List[ImageRecord] = []
+    labeled_root = data_dir / LABELED_BUCKET
+    if labeled_root.exists():
+        for label_dir in sorted(d for d in labeled_root.iterdir() if d.is_dir()):
+            found += [ImageRecord(f, f.relative_to(data_dir), "labeled", label_dir.name) for f in _files_under(label_dir)]
+    else:
+        logging.warning("Labeled bucket missing at %s", labeled_root)
+    n_labeled = len(found)
+    unlabeled_root = data_dir / UNLABELED_BUCKET
+    if unlabeled_root.exists():
+        found += [ImageRecord(f, f.relative_to(data_dir), "unlabeled", None) for f in _files_under(unlabeled_root)]
+    else:
+        logging.warning("Unlabeled bucket missing at %s", unlabeled_root)
+    if not found:
+        raise RuntimeError(f"No image files discovered under {data_dir}")
+    logging.info("Discovered %d images (labeled=%d, unlabeled=%d)", len(found), n_labeled, len(found) - n_labeled)
+    return found
+
+
+# --- engine management ---------------------------------------------------------------------------
+
+_ENGINES: Dict[Tuple[int, str, str], Engine] = {}
+
+
+def _cuda_index(device: torch.device) -> int:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(
+            f"device '{device}' requested, but ssip_b200 only runs on a B200 GPU (no CPU fallback); "
+            "use the reference's src.feature_extraction for CPU runs"
+        )
+    if device.index is not None:
+        return device.index
+    _, size, local_rank = fxdist.env_world()
+    return local_rank if size > 1 else torch.cuda.current_device()
+
+
+def _seeded_backbone(seed: int, randomize_bn: bool):
+    """torchvision resnet18 with a seeded random init (the offline stand-in for the download)."""
+    from torchvision import models
+
+    torch.manual_seed(seed)
+    net = models.resnet18(weights=None)
+    if randomize_bn:
+        gen = torch.Generator().manual_seed(seed + 1)
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                c = mod.num_features
+                mod.weight.data = 0.8 + 0.4 * torch.rand(c, generator=gen)
+                mod.bias.data = 0.1 * torch.randn(c, generator=gen)
+                mod.running_mean.data = 0.1 * torch.randn(c, generator=gen)
+                mod.running_var.data = 0.6 + 0.8 * torch.rand(c, generator=gen)
+    return net
+
+
+def resolve_state_dict(spec: Optional[str] = None) -> Dict[str, torch.Tensor]:
+    """State dict of the backbone: IMAGENET1K_V1 unless SSIP_B200_WEIGHTS says otherwise."""
+    spec = spec if spec is not None else os.environ.get(WEIGHTS_ENV, "")
+    if spec.startswith("random"):
+        kind, _, seed = spec.partition(":")
+        return _seeded_backbone(int(seed or "1234"), kind == "random-bn").state_dict()
+    if spec:
+        state = torch.load(spec, map_location="cpu", weights_only=True)
+        return state.get("state_dict", state) if isinstance(state, dict) else state
+    from torchvision import models
+
+    return models.resnet18(weights=models.ResNet18_Weights.IMAGENET1K_V1).state_dict()
+
+
+def get_engine(device: torch.device, min_batch: int = BATCH_SIZE, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+               precision: Optional[str] = None) -> Engine:
+    """Engine for `device`, created (and its weights loaded) on first use."""
+    index = _cuda_index(device)
+    precision = precision or os.environ.get(PRECISION_ENV, "bf16")
+    key = (index, precision, os.environ.get(WEIGHTS_ENV, "") if state_dict is None else f"id{id(state_dict)}")
+    eng = _ENGINES.get(key)
+    if eng is not None and eng.max_batch < min_batch:
+        eng.close()
+        eng = None
+    if eng is None:
+        eng = Engine(index, max(min_batch, 1), precision)
+        eng.load_state_dict(state_dict if state_dict is not None else resolve_state_dict())
+        _ENGINES[key] = eng
+    return eng
+
+
+# --- transform / model: same call shapes as the reference ----------------------------------------
+
+
+def _decoded_array(img: Image.Image) -> np.ndarray:
+    """The HWC uint8 array ToTensor would see, with the reference's failure modes.
+
+    The reference never converts modes (src/feature_extraction.py:233-240): anything that is not
+    three 8-bit bands makes Normalize raise.  Same exception types here.
+    """
+    bands = len(img.getbands())
+    if img.mode in ("I", "I;16", "I;16L", "I;16B", "F"):
+        raise TypeError(f"Input tensor should be a float tensor after ToTensor; mode {img.mode!r} images are not 8-bit")
+    if bands != 3:
+        raise RuntimeError(
+            f"output with shape [{bands}, {TARGET_CROP}, {TARGET_CROP}] doesn't match the broadcast shape "
+            f"[3, {TARGET_CROP}, {TARGET_CROP}] (image mode {img.mode!r}; the pipeline does no RGB conversion)"
+        )
+    arr = np.asarray(img)
+    if arr.dtype != np.uint8:
+        raise TypeError(f"unsupported pixel type {arr.dtype} for mode {img.mode!r}")
+    return arr
+
+
+class _CudaTransform:
+    """Callable returned by build_transform(): PIL image -> fp32 [3,224,224] (CPU tensor), computed
+    by the fused CUDA kernel, bit-identical to the reference's torchvision Compose."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        self._device = torch.device(device) if device is not None else torch.device("cuda")
+
+    def batch(self, arrays: Sequence[np.ndarray]) -> torch.Tensor:
+        eng = get_engine(self._device, min_batch=max(len(arrays), 1))
+        buf, descs, _ = pack_images(arrays)
+        with torch.cuda.device(eng.device):
+            dev = torch.from_numpy(buf).to(eng.device)
+            return eng.preprocess_nchw(dev, descs, len(arrays))
+
+    def __call__(self, img: Image.Image) -> torch.Tensor:
+        return self.batch([_decoded_array(img)])[0].cpu()
+
+    def __repr__(self) -> str:
+        return (f"FusedCudaTransform(Resize({TARGET_RESIZE}), CenterCrop({TARGET_CROP}), ToTensor(), "
+                f"Normalize(mean={IMAGENET_MEAN}, std={IMAGENET_STD}))")
+
+
+def build_transform() -> Callable[[Image.Image], torch.Tensor]:
+    """Deterministic preprocessing (src/feature_extraction.py:184-207) as one CUDA kernel."""
+    return _CudaTransform()
+
+
+class _CudaTrunk(torch.nn.Module):
+    """Callable returned by load_model(): [B,3,224,224] -> [B,512,1,1], frozen, eval-only."""
+
+    def __init__(self, device: torch.device):
+        super().__init__()
+        self._device = torch.device(device)
+        self.eval()
+
+    def forward(self, batch: torch.Tensor) -> torch.Tensor:
+        eng = get_engine(self._device, min_batch=max(int(batch.shape[0]), 1))
+        x = batch.detach().to(eng.device, torch.float32).contiguous()
+        out = torch.empty((x.shape[0], 512), dtype=torch.float32, device=eng.device)
+        with torch.cuda.device(eng.device):
+            for s in range(0, x.shape[0], eng.max_batch):
+                out[s : s + eng.max_batch] = eng.forward_nchw(x[s : s + eng.max_batch])
+        return out.view(-1, 512, 1, 1)
+
+
+def load_model(device: torch.device) -> torch.nn.Module:
+    """Frozen ResNet-18 minus fc (src/feature_extraction.py:210-227) on the CUDA engine."""
+    get_engine(device)  # fails here, loudly, if there is no B200 / no weights
+    return _CudaTrunk(device)
+
+
+def preprocess_image(path: Path, transform: Callable[[Image.Image], torch.Tensor]) -> torch.Tensor:
+    """Open one file and apply the transform; no mode conversion (src/feature_extraction.py:233-240)."""
+    with Image.open(path) as img:
+        return transform(img)
+
+
+def batched(iterable: Sequence, batch_size: int) -> Iterable[Sequence]:
+    """Consecutive slices of at most batch_size items (src/feature_extraction.py:243-248)."""
+    for lo in range(0, len(iterable), batch_size):
+        yield iterable[lo : lo + batch_size]
+
+
+# --- the hot loop --------------------------------------------------------------------------------
+
+
+def _load_file(path: Path):
+    """Decode one file on a pool thread -> HWC uint8 array, or the exception to report."""
+    try:
+        with Image.open(path) as img:
+            arr = _decoded_array(img)
+            if os.environ.get(GRAY_CARRIAGE_ENV) == "1" and (arr[..., 0] == arr[..., 1]).all() and (arr[..., 1] == arr[..., 2]).all():
+                arr = np.ascontiguousarray(arr[..., 0])
+            return arr
+    except (UnidentifiedImageError, OSError) as exc:  # the two the reference tolerates (:281)
+        return exc
+
+
+def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int):
+    """Single-GPU pass over `records`: device embeddings + bookkeeping."""
+    kept: List[int] = []
+    failures: List[Path] = []
+    times: List[float] = []
+    blocks: List[torch.Tensor] = []
+    threads = int(os.environ.get(DECODE_THREADS_ENV, "0")) or min(32, (os.cpu_count() or 8))
+    staging: Optional[torch.Tensor] = None
+    with ThreadPoolExecutor(max_workers=threads) as pool, torch.cuda.device(eng.device):
+        for lo in range(0, len(records), batch_size):
+            chunk = records[lo : lo + batch_size]
+            t0 = time.perf_counter()
+            decoded = list(pool.map(_load_file, [r.absolute_path for r in chunk]))
+            arrays, ok = [], []
+            for off, (rec, item) in enumerate(zip(chunk, decoded)):
+                if isinstance(item, BaseException):
+                    logging.error("Failed to decode %s: %s", rec.absolute_path, item)
+                    failures.append(rec.absolute_path)
+                else:
+                    arrays.append(item)
+                    ok.append(lo + off)
+            if not arrays:
+                continue
+            need = sum((a.size + 255) // 256 * 256 for a in arrays)
+            if staging is None or staging.numel() < need:
+                staging = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8).pin_memory()
+            buf, descs, total = pack_images(arrays, out=staging.numpy())
+            dev = staging[:total].to(eng.device, non_blocking=True)
+            emb = eng.embed_device(dev, descs, len(arrays))
+            blocks.append(emb)
+            torch.cuda.current_stream().synchronize()  # per-batch latency, like the reference's .cpu()
+            kept.extend(ok)
+            dt = time.perf_counter() - t0
+            times.extend([dt / len(ok)] * len(ok))
+    local = torch.cat(blocks, dim=0) if blocks else torch.empty((0, 512), dtype=torch.float32, device=eng.device)
+    return local, kept, failures, times
+
+
+def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_size: int = BATCH_SIZE) -> ExtractionResults:
+    """Feature extraction over `records` (signature of src/feature_extraction.py:251-255).
+
+    Under torchrun (WORLD_SIZE > 1) the records are sharded contiguously over the ranks, each rank
+    runs its shard on its own GPU, and one NCCL all-gather assembles [N,512]; every rank returns
+    the full result.  Row i of `embeddings` belongs to `records[i]` of the returned (kept) list.
+    """
+    eng = get_engine(device, min_batch=batch_size)
+    logging.info("Beginning feature extraction over %d records", len(records))
+    distributed = fxdist.ensure_process_group("nccl")
+    rank, size = fxdist.world()
+    lo, hi = fxdist.shard_bounds(len(records), rank, size) if distributed else (0, len(records))
+    local, kept, failures, times = _extract_local(records[lo:hi], eng, batch_size)
+    kept = [lo + k for k in kept]
+    if distributed:
+        full = fxdist.allgather_rows(local)
+        meta = fxdist.allgather_objects((kept, failures, times))
+        kept = fxdist.concat_in_rank_order([m[0] for m in meta])
+        failures = fxdist.concat_in_rank_order([m[1] for m in meta])
+        times = fxdist.concat_in_rank_order([m[2] for m in meta])
+    else:
+        full = local
+    if full.shape[0] == 0:
+        raise RuntimeError("No embeddings were generated; all images failed to decode?")
+    matrix = full.cpu().numpy()
+    logging.info("Computed embeddings with shape %s", matrix.shape)
+    return ExtractionResults(embeddings=matrix, records=[records[i] for i in kept], failures=failures, per_file_times=times)
+
+
+# --- post-processing and artifacts ---------------------------------------------------------------
+
+
+def compute_dataset_digest(records: Sequence[ImageRecord]) -> str:
+    """sha256 over (relative path, size, int(mtime)) in path order (src/feature_extraction.py:316-331)."""
+    h = hashlib.sha256()
+    for rec in sorted(records, key=lambda r: str(r.relative_path)):
+        st = rec.absolute_path.stat()
+        for piece in (str(rec.relative_path), str(st.st_size), str(int(st.st_mtime))):
+            h.update(piece.encode("utf-8"))
+    return h.hexdigest()
+
+
+def run_sanity_checks(embeddings: np.ndarray) -> Dict[str, float]:
+    """NaN/Inf guard + summary statistics (src/feature_extraction.py:334-356)."""
+    if np.isnan(embeddings).any():
+        raise ValueError("Embedding matrix contains NaN values")
+    if np.isinf(embeddings).any():
+        raise ValueError("Embedding matrix contains inf values")
+    stats = {
+        "num_vectors": int(embeddings.shape[0]),
+        "dimension": int(embeddings.shape[1]),
+        "mean_abs_mean": float(np.abs(embeddings.mean(axis=0)).mean()),
+        "mean_std": float(embeddings.std(axis=0).mean()),
+    }
+    logging.info("Embedding stats — vectors: %d, dim: %d, mean(|mean|): %.5f, mean(std): %.5f",
+                 stats["num_vectors"], stats["dimension"], stats["mean_abs_mean"], stats["mean_std"])
+    return stats
+
+
+def nearest_neighbor_probe(embeddings: np.ndarray, records: Sequence[ImageRecord], sample_size: int = NEIGHBOR_SAMPLE,
+                           seed: int = RNG_SEED) -> List[Dict[str, object]]:
+    """Cosine nearest neighbour of a few seeded queries (src/feature_extraction.py:359-398)."""
+    n = embeddings.shape[0]
+    k = min(sample_size, n - 1)
+    if n < 2 or k <= 0:
+        return []
+    queries = np.random.default_rng(seed).choice(n, size=k, replace=False)
+    unit = embeddings / np.clip(np.linalg.norm(embeddings, axis=1, keepdims=True), a_min=1e-12, a_max=None)
+    probe = []
+    for q in queries:
+        sims = unit[q] @ unit.T
+        sims[q] = -np.inf
+        best = int(np.argmax(sims))
+        probe.append({"query": str(records[q].relative_path), "neighbor": str(records[best].relative_path),
+                      "similarity": float(sims[best])})
+    logging.info("Nearest-neighbor probe completed for %d samples", len(probe))
+    return probe
+
+
+def _summary_markdown(results: ExtractionResults, stats: Dict[str, float], probe: List[Dict[str, object]], device) -> str:
+    lat = results.per_file_times
+    mean_lat = float(np.mean(lat)) if lat else float("nan")
+    med_lat = float(np.median(lat)) if lat else float("nan")
+    if probe:
+        table = ["| Query | Neighbor | Cosine |", "| --- | --- | --- |"]
+        table += [f"| {p['query']} | {p['neighbor']} | {p['similarity']:.4f} |" for p in probe]
+        neighbors = "\n".join(table)
+    else:
+        neighbors = "No neighbors computed (insufficient samples)."
+    failed = "\n".join(f"- {p}" for p in results.failures) if results.failures else "None"
+    dim = results.embeddings.shape[1]
+    lines = [
+        "# Feature Extraction Summary",
+        "",
+        f"- Backbone: {BACKBONE_NAME} ({BACKBONE_WEIGHTS})",
+        f"- Layer: global average pooled features ({dim}-D)",
+        f"- Input spec: resize {TARGET_RESIZE} → center crop {TARGET_CROP}, ImageNet normalization",
+        f"- Batch size: {BATCH_SIZE}",  # the reference prints the constant, not the CLI value (:481)
+        f"- Device: {device}",
+        f"- Total images processed: {results.embeddings.shape[0]}",
+        f"- Failed decodes: {len(results.failures)}",
+        f"- Mean per-image latency (s): {mean_lat:.4f}",
+        f"- Median per-image latency (s): {med_lat:.4f}",
+        "",
+        "## Sanity Check Statistics",
+        "",
+        f"- Mean of |dimension means|: {stats['mean_abs_mean']:.6f}",
+        f"- Mean of dimension standard deviations: {stats['mean_std']:.6f}",
+        "",
+        "## Nearest Neighbor Spot Check",
+        "",
+        neighbors,
+        "",
+        "## Decode Failures",
+        "",
+        failed,
+        "",
+    ]
+    return "\n".join(lines)
+
+
+def save_artifacts(results: ExtractionResults, stats: Dict[str, float], neighbor_probe: List[Dict[str, object]], data_dir: Path,
+                   device: torch.device) -> None:
+    """embeddings.npy / embeddings.csv / metadata.json / feature_summary.md (src/feature_extraction.py:401-502)."""
+    import pandas as pd
+
+    FEATURE_OUTPUT_DIR.mkdir(parents=True, exist_ok=True)
+    NOTE_OUTPUT_DIR.mkdir(parents=True, exist_ok=True)
+    np.save(EMBEDDING_ARRAY_PATH, results.embeddings.astype(np.float32))
+    frame = pd.DataFrame(
+        {
+            "index": list(range(len(results.records))),
+            "path": [str(r.relative_path) for r in results.records],
+            "bucket": [r.bucket for r in results.records],
+            "label": [r.label for r in results.records],
+        },
+        columns=["index", "path", "bucket", "label"],
+    )
+    frame.to_csv(EMBEDDING_CSV_PATH, index=False)
+    metadata = {
+        "backbone": BACKBONE_NAME,
+        "weights": BACKBONE_WEIGHTS,
+        "layer": BACKBONE_LAYER,
+        "embedding_dimension": int(results.embeddings.shape[1]),
+        "input_resize": TARGET_RESIZE,
+        "input_crop": TARGET_CROP,
+        "normalization_mean": IMAGENET_MEAN,
+        "normalization_std": IMAGENET_STD,
+        "channel_policy": "No conversion (assumes RGB inputs)",
+        "date_utc": datetime.now(timezone.utc).isoformat(),
+        "num_images": int(results.embeddings.shape[0]),
+        "failed_images": len(results.failures),
+        "device": str(device),
+        "dataset_dir": str(data_dir),
+        "dataset_digest": compute_dataset_digest(results.records),
+        "sanity_checks": stats,
+        "neighbor_probe": neighbor_probe,
+    }
+    with METADATA_PATH.open("w", encoding="utf-8") as fh:
+        json.dump(metadata, fh, indent=2)
+    SUMMARY_NOTE_PATH.write_text(_summary_markdown(results, stats, neighbor_probe, device), encoding="utf-8")
+
+
+# --- CLI -----------------------------------------------------------------------------------------
+
+
+def parse_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
+    parser = argparse.ArgumentParser(description="Extract CNN embeddings for the MRI dataset")
+    parser.add_argument("--data-dir", type=Path, default=DEFAULT_DATA_DIR, help="Root directory containing 'avec_labels' and 'sans_label'")
+    parser.add_argument("--device", type=str, default="cuda" if torch.cuda.is_available() else "cpu",
+                        help="Torch device to use (default: cuda if available else cpu)")
+    parser.add_argument("--batch-size", type=int, default=BATCH_SIZE, help="Mini-batch size for inference")
+    parser.add_argument("--verbose", action="store_true", help="Enable verbose logging")
+    return parser.parse_args(argv)
+
+
+def main(argv: Optional[Sequence[str]] = None) -> None:
+    args = parse_args(argv)
+    rank, size, _ = fxdist.env_world()
+    if rank == 0:
+        configure_logging(verbose=args.verbose)
+    else:  # only rank 0 owns the log file and the artifacts
+        logging.basicConfig(level=logging.WARNING)
+    device = torch.device(args.device)
+    logging.info("Starting feature extraction on device %s", device)
+    records = discover_image_records(args.data_dir)
+    t0 = time.perf_counter()
+    results = extract_embeddings(records, device=device, batch_size=args.batch_size)
+    logging.info("Completed embedding extraction in %.2f seconds", time.perf_counter() - t0)
+    if rank == 0:
+        stats = run_sanity_checks(results.embeddings)
+        probe = nearest_neighbor_probe(results.embeddings, results.records)
+        save_artifacts(results, stats, probe, args.data_dir, device)
+        logging.info("Artifacts saved to %s", FEATURE_OUTPUT_DIR)
+    if size > 1 and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,269 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports what include/fx_b200.h
+declares, its host-side integer code (coefficient tables, resize size, crop offsets) equals the
+oracle's, the drop-in module keeps the reference's surface and error behaviour, the N>1 sharding /
+gather logic works on gloo with world_size 2.  No compute call needs a GPU here."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_path as rp
+from ssip_b200 import _native as N
+from ssip_b200 import dist as fxdist
+from ssip_b200 import engine as E
+from ssip_b200 import feature_extraction as fx
+from ssip_b200 import synthetic
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "fx_b200.h").read_text()
+    declared = set(re.findall(r"\b(fx_[a-z0-9_]+)\s*\(", header)) - {"fx_handle"}
+    assert declared == set(N.EXPORTED_SYMBOLS)
+    lib = N.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fx_abi_version() == 1
+    assert b"sm_100a" in lib.fx_version()
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(N.FxError) as err:
+        E.Engine(0, 8)
+    assert err.value.status == N.FX_ERR_UNSUPPORTED and "no CPU path" in err.value.text
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fx.extract_embeddings([], torch.device("cpu"), 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fx.load_model(torch.device("cpu"))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "semi-supervised-image-processing_b200"
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        text = path.read_text()
+        assert not re.search(r"import\s+oracle|from\s+oracle|oracle/|oracle\.|libfx_oracle|fxo_", text), path
+
+
+@pytest.mark.parametrize("sizes", [(512, 256), (224, 256), (300, 256), (500, 426), (1000, 365), (2048, 256), (100, 256), (256, 256), (7, 256)])
+def test_host_coefficients_equal_oracle(sizes):
+    xmin, cnt, taps = E.host_coeffs(*sizes)
+    bounds, kk = rp.c_coeffs(*sizes)
+    np.testing.assert_array_equal(xmin, bounds[:, 0])
+    np.testing.assert_array_equal(cnt, bounds[:, 1])
+    np.testing.assert_array_equal(taps, kk)
+    assert (taps.sum(axis=1) - (1 << 22)).__abs__().max() <= taps.shape[1]  # normalised rows
+
+
+def test_host_resize_and_crop_geometry_equal_torchvision():
+    from torchvision.transforms import functional as F
+
+    for (h, w) in [(224, 224), (512, 512), (300, 500), (500, 300), (514, 512), (777, 333), (1000, 700), (1, 1), (3000, 17)]:
+        want = F._compute_resized_output_size((h, w), [256])
+        assert list(E.host_resized_size(h, w)) == list(want)
+    for size in range(224, 1200):
+        assert E.host_crop_offset(size) == int(round((size - 224) / 2.0))
+
+
+def test_pack_images_layout():
+    imgs = synthetic.ragged_images([(5, 7), (3, 2)], seed=1) + [np.zeros((4, 4), np.uint8)]
+    buf, descs, total = E.pack_images(imgs)
+    assert total % 256 == 0 and descs[0].offset == 0 and descs[1].offset == 256 and descs[2].offset == 512
+    assert (descs[2].channels, descs[1].height, descs[1].width) == (1, 3, 2)
+    np.testing.assert_array_equal(buf[256 : 256 + 18].reshape(3, 2, 3), imgs[1])
+    with pytest.raises(TypeError):
+        E.pack_images([np.zeros((4, 4, 3), np.float32)])
+
+
+def test_layer_table_matches_torchvision_state_dict():
+    state = rp.make_backbone().state_dict()
+    shapes = [tuple(state[k].shape) for k, *_ in E.LAYER_TABLE]
+    assert shapes[0] == (64, 3, 7, 7) and shapes[7] == (128, 64, 1, 1) and shapes[19] == (512, 512, 3, 3)
+    macs = 0
+    hw = [112] + [56] * 4 + [28] * 5 + [14] * 5 + [7] * 5
+    for (co, ci, kh, kw), o in zip(shapes, hw):
+        macs += co * ci * kh * kw * o * o
+    assert macs == 1_813_561_344
+
+
+def _make_dataset(tmp_path, n=6):
+    imgs = list(synthetic.noise_images(n, 32, 40, seed=3))
+    synthetic.write_png_dataset(tmp_path, imgs, n_labeled=4)
+    return imgs
+
+
+def test_discover_image_records_contract(tmp_path, have_reference):
+    _make_dataset(tmp_path)
+    (tmp_path / "sans_label" / "notes.txt").write_text("not an image")
+    recs = fx.discover_image_records(tmp_path)
+    assert [r.bucket for r in recs] == ["labeled"] * 4 + ["unlabeled"] * 3
+    assert [r.label for r in recs] == ["cancer", "cancer", "normal", "normal", None, None, None]
+    assert str(recs[-1].relative_path) == "sans_label/notes.txt"  # every file is a record
+    with pytest.raises(FileNotFoundError):
+        fx.discover_image_records(tmp_path / "missing")
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(RuntimeError, match="No image files"):
+        fx.discover_image_records(empty)
+    if have_reference:
+        sys.path.insert(0, "/root/reference")
+        import src.feature_extraction as fe
+
+        ref = fe.discover_image_records(tmp_path)
+        assert [(r.relative_path, r.bucket, r.label) for r in ref] == [(r.relative_path, r.bucket, r.label) for r in recs]
+
+
+def test_module_surface_matches_reference(have_reference):
+    names = ["discover_image_records", "build_transform", "load_model", "preprocess_image", "batched", "extract_embeddings",
+             "compute_dataset_digest", "run_sanity_checks", "nearest_neighbor_probe", "save_artifacts", "configure_logging",
+             "parse_args", "main", "ImageRecord", "ExtractionResults"]
+    for name in names:
+        assert hasattr(fx, name), name
+    consts = ["IMAGENET_MEAN", "IMAGENET_STD", "TARGET_RESIZE", "TARGET_CROP", "BATCH_SIZE", "NEIGHBOR_SAMPLE", "RNG_SEED",
+              "LABELED_BUCKET", "UNLABELED_BUCKET", "BACKBONE_NAME", "BACKBONE_WEIGHTS", "BACKBONE_LAYER", "EMBEDDING_ARRAY_PATH",
+              "EMBEDDING_CSV_PATH", "METADATA_PATH", "SUMMARY_NOTE_PATH", "LOG_PATH", "DEFAULT_DATA_DIR"]
+    if have_reference:
+        sys.path.insert(0, "/root/reference")
+        import src.feature_extraction as fe
+
+        for c in consts:
+            assert getattr(fx, c) == getattr(fe, c), c
+    args = fx.parse_args(["--data-dir", "d", "--batch-size", "7", "--verbose", "--device", "cuda:3"])
+    assert (str(args.data_dir), args.batch_size, args.verbose, args.device) == ("d", 7, True, "cuda:3")
+    assert list(fx.batched(list(range(7)), 3)) == [[0, 1, 2], [3, 4, 5], [6]]
+
+
+def test_postprocessing_and_artifacts(tmp_path, monkeypatch, have_reference):
+    _make_dataset(tmp_path)
+    recs = fx.discover_image_records(tmp_path)
+    emb = np.random.default_rng(0).random((len(recs), 512), dtype=np.float32)
+    emb[3] = emb[1]  # a duplicate must be its twin's nearest neighbour
+    res = fx.ExtractionResults(emb, recs, [tmp_path / "broken.jpg"], [0.01] * len(recs))
+    stats = fx.run_sanity_checks(emb)
+    probe = fx.nearest_neighbor_probe(emb, recs)
+    assert len(probe) == 5 and all(set(p) == {"query", "neighbor", "similarity"} for p in probe)
+    bad = emb.copy()
+    bad[0, 0] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        fx.run_sanity_checks(bad)
+    bad[0, 0] = np.inf
+    with pytest.raises(ValueError, match="inf"):
+        fx.run_sanity_checks(bad)
+    monkeypatch.chdir(tmp_path)
+    fx.save_artifacts(res, stats, probe, tmp_path, torch.device("cuda:0"))
+    saved = np.load(tmp_path / fx.EMBEDDING_ARRAY_PATH)
+    assert saved.dtype == np.float32 and np.array_equal(saved, emb)
+    import pandas as pd
+
+    frame = pd.read_csv(tmp_path / fx.EMBEDDING_CSV_PATH)
+    assert list(frame.columns) == ["index", "path", "bucket", "label"] and len(frame) == len(recs)
+    assert frame["label"].isna().sum() == 2
+    meta = json.loads((tmp_path / fx.METADATA_PATH).read_text())
+    assert list(meta) == ["backbone", "weights", "layer", "embedding_dimension", "input_resize", "input_crop", "normalization_mean",
+                          "normalization_std", "channel_policy", "date_utc", "num_images", "failed_images", "device", "dataset_dir",
+                          "dataset_digest", "sanity_checks", "neighbor_probe"]
+    assert meta["failed_images"] == 1 and meta["num_images"] == len(recs) and meta["device"] == "cuda:0"
+    note = (tmp_path / fx.SUMMARY_NOTE_PATH).read_text()
+    assert "- Batch size: 32" in note and "- Failed decodes: 1" in note and "| Query | Neighbor | Cosine |" in note
+    if have_reference:
+        # identical numbers / text from the reference's own post-processing on the same inputs
+        sys.path.insert(0, "/root/reference")
+        import src.feature_extraction as fe
+
+        ref_recs = fe.discover_image_records(tmp_path)
+        assert fe.run_sanity_checks(emb) == stats
+        assert fe.nearest_neighbor_probe(emb, ref_recs) == probe
+        assert fe.compute_dataset_digest(ref_recs) == meta["dataset_digest"]
+        ours = {p: (tmp_path / p).read_text() for p in (fx.SUMMARY_NOTE_PATH, fx.EMBEDDING_CSV_PATH)}
+        fe.save_artifacts(fe.ExtractionResults(emb, ref_recs, [tmp_path / "broken.jpg"], [0.01] * len(recs)), stats, probe, tmp_path,
+                          torch.device("cuda:0"))
+        for p, text in ours.items():
+            assert (tmp_path / p).read_text() == text, p
+        ref_meta = json.loads((tmp_path / fx.METADATA_PATH).read_text())
+        ref_meta.pop("date_utc"), meta.pop("date_utc")
+        assert ref_meta == meta
+        # the downstream consumer accepts the files
+        from src.standardize_features import standardize_embeddings
+
+        bundle = tmp_path / "outputs" / "features" / "standardized_features.npz"
+        standardize_embeddings(tmp_path / fx.EMBEDDING_ARRAY_PATH, tmp_path / fx.EMBEDDING_CSV_PATH, bundle)
+        assert bundle.exists()
+
+
+def test_decode_rules_follow_reference_channel_policy(tmp_path):
+    from PIL import Image
+
+    rgb = tmp_path / "a.png"
+    Image.fromarray(synthetic.noise_images(1, 8, 8)[0]).save(rgb)
+    with Image.open(rgb) as im:
+        assert fx._decoded_array(im).shape == (8, 8, 3)
+    gray = tmp_path / "g.png"
+    Image.fromarray(np.zeros((8, 8), np.uint8)).save(gray)
+    with Image.open(gray) as im, pytest.raises(RuntimeError, match="broadcast shape"):
+        fx._decoded_array(im)
+    rgba = tmp_path / "r.png"
+    Image.fromarray(np.zeros((8, 8, 4), np.uint8)).save(rgba)
+    with Image.open(rgba) as im, pytest.raises(RuntimeError):
+        fx._decoded_array(im)
+    deep = tmp_path / "d.png"
+    Image.fromarray(np.zeros((8, 8), np.uint16)).save(deep)
+    with Image.open(deep) as im, pytest.raises(TypeError):
+        fx._decoded_array(im)
+    junk = tmp_path / "junk.jpg"
+    junk.write_bytes(b"not a jpeg")
+    assert isinstance(fx._load_file(junk), Exception)
+
+
+def test_shard_bounds_cover_everything_in_order():
+    for n in (0, 1, 7, 8, 9, 1000, 1506):
+        for size in (1, 2, 3, 4, 8):
+            spans = [fxdist.shard_bounds(n, r, size) for r in range(size)]
+            flat = [i for lo, hi in spans for i in range(lo, hi)]
+            assert flat == list(range(n))
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, numpy as np
+sys.path.insert(0, {root!r})
+from ssip_b200 import dist as fxdist
+assert fxdist.ensure_process_group("gloo")
+rank, size = fxdist.world()
+n = 11
+lo, hi = fxdist.shard_bounds(n, rank, size)
+rows = torch.arange(n * 512, dtype=torch.float32).reshape(n, 512)
+local = rows[lo:hi]
+if rank == 1:
+    local = local[:-2]   # two decode failures on rank 1 -> uneven counts
+full = fxdist.allgather_rows(local.contiguous())
+meta = fxdist.allgather_objects(list(range(lo, hi))[: local.shape[0]])
+kept = fxdist.concat_in_rank_order(meta)
+assert kept == [0, 1, 2, 3, 4, 5, 6, 7, 8], kept
+assert torch.equal(full, rows[kept]), (full.shape,)
+empty = fxdist.allgather_rows(torch.zeros((0, 512)))
+assert empty.shape == (0, 512)
+torch.distributed.barrier()
+torch.distributed.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_allgather_rows_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", "29611", str(script)],
+        capture_output=True, text=True, timeout=240, env=env,
+    )
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
