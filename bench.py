@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the feature-extraction hot path (BASELINE.json metric: ResNet-18 embed images/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (fused preprocess -> ResNet-18 trunk -> [B,512] embeddings) over
+one batch of synthetic 224x224x3 uint8 images.  One JSON line on stdout (rank 0).
+
+  value     images/s, whole job, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the host-buffer C-ABI call fx_embed_host: pinned host uint8 in, host
+            fp32 [B,512] out, both copies inside the timed region
+  roofline  the trunk's implicit-GEMM kernels against the measured dense-bf16 peak
+            (+ roofline_preprocess: the fused preprocess kernel against the measured HBM peak)
+  cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (N=1, rank 0)
+
+--impl reference times that CPU port alone (the reference is pure Python + torchvision and
+/root/reference does not exist on the GPU box; oracle/reference_path.py restates its loop over the
+same third-party calls).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+IMG_H = IMG_W = 224
+IMG_BYTES = IMG_H * IMG_W * 3
+POOL_IMAGES = 50_000  # BASELINE.json configs[1]
+TRUNK_FLOP_PER_IMAGE = 2 * 1_813_561_344  # 1.8136 GMAC, 2 FLOP/MAC
+PRE_BYTES_BF16 = IMG_BYTES + 224 * 224 * 3 * 2  # source read once + bf16 NHWC(3) written once
+WEIGHT_SEED = 1234
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]),
+                "tf_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "src": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_port_rate(images: np.ndarray, batch: int, budget_s: float, threads: int):
+    """Oracle port of the reference loop (preprocess_image per file + stack + model forward,
+    src/feature_extraction.py:272-300) on decoded arrays; returns (images/s, images timed, seconds)."""
+    from oracle import reference_path as rp
+
+    torch.set_num_threads(threads)
+    transform = rp.port_transform()
+    model = rp.port_model(torch.device("cpu"), WEIGHT_SEED, False)
+
+    def one_batch(chunk):
+        x = torch.stack([rp.port_preprocess_array(a, transform) for a in chunk])
+        with torch.no_grad():
+            return torch.flatten(model(x), 1).numpy()
+
+    one_batch(images[:batch])  # warm-up (oneDNN primitive creation)
+    done, t0 = 0, time.perf_counter()
+    while done < len(images):
+        one_batch(images[done : done + batch])
+        done += min(batch, len(images) - done)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def synth_host(n: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (n, IMG_H, IMG_W, 3), dtype=np.uint8)
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the CPU path alone, rank 0 only."""
+    if rank != 0:
+        return
+    cores = host_cores()
+    batch = 32  # the reference's own default batch (src/feature_extraction.py:68)
+    from oracle import reference_path as rp
+
+    torch.set_num_threads(cores)
+    transform = rp.port_transform()
+    model = rp.port_model(torch.device("cpu"), WEIGHT_SEED, False)
+    imgs = synth_host(batch, 0)
+
+    def step(k):
+        x = torch.stack([rp.port_preprocess_array(a, transform) for a in imgs[:k]])
+        with torch.no_grad():
+            return torch.flatten(model(x), 1).numpy()
+
+    t0 = time.perf_counter()
+    step(batch)
+    first = time.perf_counter() - t0
+    # size the per-step sample so that steps+warmup end within ~150 s
+    t0 = time.perf_counter()
+    step(batch)
+    per_img = (time.perf_counter() - t0) / batch
+    total_steps = args.steps + args.warmup
+    k = int(max(4, min(batch, 150.0 / max(total_steps, 1) / per_img)))
+    for _ in range(args.warmup):
+        step(k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(k)
+    dt = time.perf_counter() - t0
+    value = args.steps * k / dt
+    sample = f"{k} synthetic 224x224x3 images per step x {args.steps} steps, fp32, torch threads={cores} (first call {first:.2f}s untimed)"
+    line = {
+        "impl": "reference", "metric": "ResNet-18 embed images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int):
+    if world == 1:
+        name = f"ResNet-18 embedding extraction, 50k synthetic 224x224 images, batch {args.batch}, {args.precision} on 1xB200"
+    else:
+        name = (f"Image-sharded extraction of synthetic 224x224 images at {world}xB200, batch {args.batch}/GPU, "
+                f"NCCL all-gather of [N,512] embeddings")
+    return {"workload": name, "batch_per_gpu": args.batch, "image": "224x224x3 uint8", "precision": args.precision,
+            "weights": f"torchvision resnet18 random-init seed {WEIGHT_SEED}",
+            "l2": "every step reads a different batch of a resident uint8 pool larger than L2",
+            "parallelism": f"image-sharded dp{world}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default 256 at 1 GPU, 512 at N>1)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--pool", type=int, default=0, help="resident images per GPU (default 50000 / enough for L2 rule)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline work (N=1 only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.batch <= 0:
+        args.batch = 256 if world == 1 else 512
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU path (use --impl reference for the CPU arm)")
+
+    from ssip_b200.engine import Engine, uniform_descs
+    from ssip_b200.feature_extraction import _seeded_backbone
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, args.warmup
+    eng = Engine(local_rank, max_batch=B, precision=args.precision)
+    eng.load_state_dict(_seeded_backbone(WEIGHT_SEED, False).state_dict())
+
+    # resident synthetic pool (seeded, generated on the device): C2 keeps 50k images = 7.5 GB in HBM
+    pool_n = args.pool or POOL_IMAGES
+    pool_n = max(B, (pool_n // B) * B)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    pool = torch.empty(pool_n * IMG_BYTES, dtype=torch.uint8, device=dev)
+    chunk = 2048 * IMG_BYTES
+    for off in range(0, pool.numel(), chunk):
+        hi = min(pool.numel(), off + chunk)
+        pool[off:hi] = torch.randint(0, 256, (hi - off,), dtype=torch.uint8, device=dev, generator=gen)
+    n_batches = pool_n // B
+    descs = uniform_descs(B, IMG_H, IMG_W)
+    out_local = torch.empty((K * B, 512), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * K * B, 512), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def batch_view(i):
+        j = i % n_batches
+        return pool[j * B * IMG_BYTES : (j + 1) * B * IMG_BYTES]
+
+    def device_steps(k0, k1, out):
+        for i in range(k0, k1):
+            eng.embed_device(batch_view(i), descs, B, out=out[(i - k0) * B : (i - k0 + 1) * B])
+
+    # ---- value: device-resident inputs -----------------------------------------------------------
+    scratch = torch.empty((W * B, 512), dtype=torch.float32, device=dev)
+    device_steps(0, W, scratch)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    device_steps(W, W + K, out_local)
+    if world > 1:
+        dist.all_gather_into_tensor(gathered, out_local)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * B / (ms_max / 1e3)
+
+    # ---- per-kernel-family timing (separate pass, same stream, CUDA events) ----------------------
+    k_prof = min(K, 30)
+    pre_ms, trunk_ms = [], []
+    emb = scratch[:B]
+    for i in range(k_prof):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        src = batch_view(W + K + i)
+        a.record()
+        eng.preprocess(src, descs, B)
+        b.record()
+        eng.forward(B, emb)
+        c.record()
+        c.synchronize()
+        pre_ms.append(a.elapsed_time(b))
+        trunk_ms.append(b.elapsed_time(c))
+    pre_avg, trunk_avg = statistics.mean(pre_ms), statistics.mean(trunk_ms)
+    peaks = load_peaks()
+    tf = TRUNK_FLOP_PER_IMAGE * B / (trunk_avg / 1e3) / 1e12
+    gbs = PRE_BYTES_BF16 * B / (pre_avg / 1e3) / 1e9
+
+    # ---- e2e: host buffers through fx_embed_host ---------------------------------------------------
+    k_e2e = min(K, 50)
+    n_host = min(8, n_batches)
+    host_in = [torch.from_numpy(synth_host(B, 77 + rank * 100 + j).reshape(-1)).pin_memory() for j in range(n_host)]
+    host_out = torch.empty((B, 512), dtype=torch.float32).pin_memory()
+    for j in range(3):
+        eng.embed_host(host_in[j % n_host], descs, B, B * IMG_BYTES, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(k_e2e):
+        eng.embed_host(host_in[i % n_host], descs, B, B * IMG_BYTES, out=host_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * k_e2e * B / float(t.item())
+    finite = bool(torch.isfinite(out_local).all().item()) and bool(np.isfinite(host_out.numpy()).all())
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        sample = synth_host(512, 5)
+        rate, done, secs = cpu_port_rate(list(sample), 32, args.cpu_budget, cores)
+        cpu_baseline = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"{done} synthetic 224x224x3 images, batch 32, fp32, {secs:.1f}s, oracle port of src/feature_extraction.py:272-300"}
+
+    if rank == 0:
+        line = {
+            "metric": "ResNet-18 embed images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_BYTES, "d2h_bytes_per_step": B * 512 * 4,
+                    "steps": k_e2e, "api": "fx_embed_host (pinned host uint8 in, host fp32 [B,512] out)"},
+            "gpu_launches": int(launches * world),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["tf_sustained"], "traffic": None,
+                         "kernel": "tc_conv_kernel family (20 implicit-GEMM launches + maxpool/avgpool) per batch",
+                         "flop_per_image": TRUNK_FLOP_PER_IMAGE, "avg_ms": trunk_avg, "peak_src": peaks["src"] + " sustained bf16",
+                         "frac_of_burst_peak": tf / peaks["tf_burst"]},
+            "roofline_preprocess": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                    "traffic": None, "kernel": "preprocess_kernel<bf16 staging>", "bytes_per_image": PRE_BYTES_BF16,
+                                    "avg_ms": pre_avg, "peak_src": peaks["src"]},
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "finite": finite,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

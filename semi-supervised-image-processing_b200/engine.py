@@ -149,6 +149,16 @@ class Engine:
         self._check(self._lib.fx_forward(self._h, n, out.data_ptr(), self._stream()))
         return out
 
+    def preprocess(self, packed_dev: torch.Tensor, descs, n: int) -> None:
+        """Fused transform into the engine's conv1 staging tensor (follow with forward())."""
+        self._dev_u8(packed_dev)
+        self._check(self._lib.fx_preprocess(self._h, packed_dev.data_ptr(), descs, n, self._stream()))
+
+    def forward(self, n: int, out: torch.Tensor) -> torch.Tensor:
+        """Trunk on the n staged images -> fp32 [n,512] written at `out` (CUDA, contiguous)."""
+        self._check(self._lib.fx_forward(self._h, n, out.data_ptr(), self._stream()))
+        return out
+
     # -- whole path ---------------------------------------------------------------------------
     def embed_device(self, packed_dev: torch.Tensor, descs, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Preprocess + trunk on device-resident uint8 images -> fp32 [n,512] on the device."""

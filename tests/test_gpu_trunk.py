@@ -1,0 +1,238 @@
+"""GPU parity of the ResNet-18 trunk kernels through the C ABI.
+
+Floating-point work, so the comparison is against a plain PyTorch fp32 evaluation of the same op
+(per layer) and against the oracle port of the reference path (end to end).  Tolerances:
+  * fp32 mode (CUDA-core implicit GEMM, true fp32): relative L2 <= 2e-6 per layer, 1e-5 end to end;
+  * bf16 mode (tcgen05, bf16 operands, fp32 accumulate): per layer the comparison feeds the SAME
+    bf16-rounded inputs/weights to an fp32 conv, so only the output rounding (2^-9 relative) and
+    accumulation order differ; end to end BASELINE.json's bound applies: per-embedding
+    cosine >= 0.999 and relative L2 <= 1e-2.
+Reference lines: src/feature_extraction.py:210-227,289-294; torchvision/models/resnet.py:89-105,266-282.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import reference_path as rp
+from ssip_b200 import synthetic
+from ssip_b200.engine import Engine, pack_images, uniform_descs
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def eng_bf16():
+    e = Engine(0, max_batch=64, precision="bf16")
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_fp32():
+    e = Engine(0, max_batch=64, precision="fp32")
+    yield e
+    e.close()
+
+
+# ---- TMA behaviours the implicit-GEMM kernel relies on ------------------------------------------
+
+
+def test_tma_zero_fill_and_element_strides(eng_bf16):
+    n, h, w, c = 2, 6, 10, 64
+    x = torch.arange(n * h * w * c, dtype=torch.float32).reshape(n, h, w, c).remainder(251).to(torch.bfloat16).cuda()
+    dims = [c, w, h, n]
+    strides = [c * 2, w * c * 2, h * w * c * 2]
+    # box {64 c, 4 w, 2 h, 1 n} at (w=-1, h=-1): first row and first column are out of bounds -> zeros
+    raw = eng_bf16.tma_probe(x, dims, strides, [64, 4, 2, 1], [1, 1, 1, 1], 0, [0, -1, -1, 0], 64 * 4 * 2 * 2)
+    got = raw.view(torch.bfloat16).reshape(2, 4, 64).float().cpu()
+    want = torch.zeros(2, 4, 64)
+    want[1, 1:] = x[0, 0, 0:3].float().cpu()
+    assert torch.equal(got, want)
+    # element stride 2 along w and h: box spans 8 x 4 source elements, loads 4 x 2
+    raw = eng_bf16.tma_probe(x, dims, strides, [64, 8, 4, 1], [1, 2, 2, 1], 0, [0, 1, 1, 1], 64 * 4 * 2 * 2)
+    got = raw.view(torch.bfloat16).reshape(2, 4, 64).float().cpu()
+    assert torch.equal(got, x[1, 1:5:2, 1:9:2].float().cpu())
+
+
+def test_tma_swizzle_128b_layout(eng_bf16):
+    x = torch.arange(16 * 64, dtype=torch.float32).reshape(1, 1, 16, 64).remainder(509).to(torch.bfloat16).cuda()
+    raw = eng_bf16.tma_probe(x, [64, 16, 1, 1], [128, 16 * 128, 16 * 128], [64, 16, 1, 1], [1, 1, 1, 1], 128, [0, 0, 0, 0], 16 * 128)
+    got = raw.view(torch.bfloat16).reshape(16, 8, 8).float().cpu()  # [row][16-byte chunk][8 elems]
+    src = x.reshape(16, 8, 8).float().cpu()
+    for r in range(16):
+        for ch in range(8):
+            assert torch.equal(got[r, ch ^ (r & 7)], src[r, ch])
+
+
+def test_tma_overlapping_windows_for_the_stem(eng_bf16):
+    # rows of 232 px x 4 ch; window of output column ow = 8 px starting at pixel 2*ow (16-byte stride)
+    n, hh, ww = 1, 4, 232
+    x = torch.arange(n * hh * ww * 4, dtype=torch.float32).remainder(241).to(torch.bfloat16).reshape(n, hh, ww, 4).cuda()
+    dims = [32, 112, hh, n]
+    strides = [16, ww * 4 * 2, hh * ww * 4 * 2]
+    raw = eng_bf16.tma_probe(x, dims, strides, [32, 4, 2, 1], [1, 1, 2, 1], 0, [0, 5, 1, 0], 64 * 4)
+    got = raw.view(torch.bfloat16).reshape(4, 32).float().cpu()
+    for j in range(4):
+        ow = 5 + j
+        assert torch.equal(got[j], x[0, 1, 2 * ow : 2 * ow + 8].reshape(-1).float().cpu())
+
+
+# ---- one conv+bn group at a time ------------------------------------------------------------------
+
+LAYER_CASES = [
+    # cin, cout, k, stride, hin, n, residual, relu
+    (64, 64, 3, 1, 56, 3, False, True),
+    (64, 64, 3, 1, 56, 4, True, True),
+    (64, 128, 3, 2, 56, 5, False, True),
+    (64, 128, 1, 2, 56, 5, False, False),
+    (128, 128, 3, 1, 28, 9, True, True),
+    (128, 256, 3, 2, 28, 7, False, True),
+    (128, 256, 1, 2, 28, 7, False, False),
+    (256, 256, 3, 1, 14, 33, True, True),
+    (256, 512, 3, 2, 14, 20, False, True),
+    (256, 512, 1, 2, 14, 20, False, False),
+    (512, 512, 3, 1, 7, 64, True, True),
+    (512, 512, 3, 1, 7, 1, False, True),
+    (3, 64, 7, 2, 224, 3, False, True),
+]
+
+
+def _case_tensors(cin, cout, k, hin, n, residual, seed):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bn = {
+        "weight": 0.8 + 0.4 * torch.rand(cout, generator=g),
+        "bias": 0.1 * torch.randn(cout, generator=g),
+        "running_mean": 0.1 * torch.randn(cout, generator=g),
+        "running_var": 0.6 + 0.8 * torch.rand(cout, generator=g),
+    }
+    x = torch.randn(n, hin, hin, cin, generator=g)
+    return w, bn, x
+
+
+def _torch_conv(w, bn, x_nhwc, stride, pad, res_nhwc, relu, round_bf16):
+    s = (bn["weight"].double() / torch.sqrt(bn["running_var"].double() + 1e-5))
+    wf = (w.double() * s[:, None, None, None]).float()
+    bf = (bn["bias"].double() - bn["running_mean"].double() * s).float()
+    x = x_nhwc
+    if round_bf16:
+        wf, x = _bf16r(wf), _bf16r(x)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), wf.double(), bf.double(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    if res_nhwc is not None:
+        y = y + (_bf16r(res_nhwc) if round_bf16 else res_nhwc).double()
+    if relu:
+        y = y.clamp_min(0)
+    return y.float()
+
+
+@pytest.mark.parametrize("case", LAYER_CASES, ids=lambda c: "c%d-%d_k%d_s%d_h%d_n%d_r%d" % c[:7])
+def test_conv_layer_bf16_tcgen05(eng_bf16, case):
+    cin, cout, k, stride, hin, n, residual, relu = case
+    w, bn, x = _case_tensors(cin, cout, k, hin, n, residual, seed=cin + cout + k + hin)
+    pad = k // 2
+    ho = (hin + 2 * pad - k) // stride + 1
+    res = torch.randn(n, ho, ho, cout, generator=torch.Generator().manual_seed(7)) if residual else None
+    got = eng_bf16.debug_conv(w, bn, stride, pad, x.cuda(), res.cuda() if res is not None else None, relu).cpu()
+    want = _torch_conv(w, bn, x, stride, pad, res, relu, round_bf16=True)
+    # identical operands; only the bf16 rounding of the stored output differs (<= 2^-8 relative per value)
+    err = (got - want).abs()
+    tol = want.abs() * 2.0 ** -7 + 2e-2 * want.abs().mean()
+    assert bool((err <= tol).all()), f"max err {err.max():.4g}, relL2 {_rel(got, want):.3e}"
+    assert _rel(got, want) < 4e-3
+
+
+@pytest.mark.parametrize("case", LAYER_CASES, ids=lambda c: "c%d-%d_k%d_s%d_h%d_n%d_r%d" % c[:7])
+def test_conv_layer_fp32(eng_fp32, case):
+    cin, cout, k, stride, hin, n, residual, relu = case
+    n = min(n, 8)
+    w, bn, x = _case_tensors(cin, cout, k, hin, n, residual, seed=cin + cout + k + hin)
+    pad = k // 2
+    ho = (hin + 2 * pad - k) // stride + 1
+    res = torch.randn(n, ho, ho, cout, generator=torch.Generator().manual_seed(7)) if residual else None
+    got = eng_fp32.debug_conv(w, bn, stride, pad, x.cuda(), res.cuda() if res is not None else None, relu).cpu()
+    want = _torch_conv(w, bn, x, stride, pad, res, relu, round_bf16=False)
+    assert _rel(got, want) < 2e-6
+
+
+# ---- whole path -----------------------------------------------------------------------------------
+
+
+def _embed(eng, images):
+    buf, descs, total = pack_images(images)
+    return eng.embed_host(buf, descs, len(images), total)
+
+
+def _check_rows(got, want, rel_tol, cos_tol):
+    rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+    cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
+    assert rel.max() <= rel_tol, f"max relL2 {rel.max():.3e}"
+    assert cos.min() >= cos_tol, f"min cosine {cos.min():.6f}"
+    return rel.max()
+
+
+@pytest.mark.parametrize("randbn", [False, True])
+def test_embeddings_match_reference_golden_bf16(eng_bf16, golden_dir, randbn):
+    z = np.load(golden_dir / "embeddings_golden.npz")
+    eng_bf16.load_state_dict(rp.make_backbone(randomize_bn=randbn).state_dict())
+    noise = list(synthetic.noise_images(16, 224, 224, seed=0))
+    _check_rows(_embed(eng_bf16, noise), z["noise_randbn" if randbn else "noise_default"], 1e-2, 0.999)
+    if randbn:
+        mri = list(synthetic.mri_like_images(8, 512, seed=7))
+        _check_rows(_embed(eng_bf16, mri), z["mri_randbn"], 1e-2, 0.999)
+        ragged = synthetic.ragged_images([(300, 500), (500, 300), (514, 512), (777, 333), (256, 256), (640, 480)], seed=11)
+        _check_rows(_embed(eng_bf16, ragged), z["ragged_randbn"], 1e-2, 0.999)
+
+
+def test_embeddings_match_reference_golden_fp32(eng_fp32, golden_dir):
+    z = np.load(golden_dir / "embeddings_golden.npz")
+    eng_fp32.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+    noise = list(synthetic.noise_images(16, 224, 224, seed=0))
+    _check_rows(_embed(eng_fp32, noise), z["noise_randbn"], 1e-5, 0.999999)
+    mri = list(synthetic.mri_like_images(8, 512, seed=7))
+    _check_rows(_embed(eng_fp32, mri), z["mri_randbn"], 1e-5, 0.999999)
+
+
+def test_trunk_alone_on_reference_batch_tensor(eng_bf16):
+    # load_model drop-in: the reference's normalised batch tensor in, [B,512] out
+    net = rp.make_backbone(randomize_bn=True)
+    eng_bf16.load_state_dict(net.state_dict())
+    imgs = list(synthetic.mri_like_images(6, 512, seed=1))
+    x = torch.stack([torch.from_numpy(rp.c_preprocess_rgb(a)) for a in imgs])
+    trunk = rp.port_model(torch.device("cpu"), randomize_bn=True)
+    with torch.no_grad():
+        want = torch.flatten(trunk(x), 1).numpy()
+    got = eng_bf16.forward_nchw(x.cuda()).cpu().numpy()
+    _check_rows(got, want, 1e-2, 0.999)
+
+
+def test_batch_composition_does_not_change_rows(eng_bf16):
+    # determinism contract: a row depends on its image only -> byte-identical whatever
+    # the batch size or position (this is what makes 1/2/4/8-GPU results identical)
+    eng_bf16.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+    x = synthetic.noise_images(37, 224, 224, seed=4)
+    full = _embed(eng_bf16, list(x))
+    for lo, hi in [(0, 1), (5, 6), (3, 20), (30, 37)]:
+        part = _embed(eng_bf16, list(x[lo:hi]))
+        assert np.array_equal(part, full[lo:hi])
+
+
+def test_device_resident_path_and_launch_count(eng_bf16):
+    eng_bf16.load_state_dict(rp.make_backbone(randomize_bn=False).state_dict())
+    x = synthetic.noise_images(64, 224, 224, seed=12)
+    dev = torch.from_numpy(x.reshape(-1)).cuda()
+    before = eng_bf16.launch_count
+    out = eng_bf16.embed_device(dev, uniform_descs(64, 224, 224), 64)
+    torch.cuda.synchronize()
+    assert eng_bf16.launch_count - before >= 3
+    host = _embed(eng_bf16, list(x))
+    assert np.array_equal(out.cpu().numpy(), host)
+    assert np.isfinite(host).all()

