@@ -176,6 +176,13 @@ int fx_debug_tma_probe(fx_handle h, const void *base_dev, const uint64_t *dims, 
                        const uint32_t *box, const uint32_t *elem_strides, int swizzle, const int *coords,
                        int bytes, uint8_t *out_dev);
 
+/* One tcgen05.mma chain D[128][64] = A[shift .. shift+128) * B^T (fp32 out) where A is a 256-row,
+ * kb_elems-wide (64/32/16 -> SWIZZLE_128B/64B/32B) K-major bf16 tile loaded by one TMA box and the A
+ * descriptor starts `shift_rows` rows into it.  Pins the shifted-view behaviour the halo-tile conv
+ * kernels rely on.  b_dev is [64][kb_elems] bf16. */
+int fx_debug_umma_shift(fx_handle h, const void *a_dev, const void *b_dev, int kb_elems, int shift_rows,
+                        int base_offset, float *out_dev);
+
 /* Host-side integer pieces of the preprocess (no GPU needed): torchvision's Resize(256) output
  * size, CenterCrop(224)'s round-half-even offset, Pillow's fixed-point coefficient table
  * (returns taps per output sample; with NULL arrays only returns that count). */

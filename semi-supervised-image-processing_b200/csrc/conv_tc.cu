@@ -373,6 +373,65 @@ __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap map, int c0
 }
 
 // ------------------------------------------------------------------------------------------
+// UMMA descriptor probe (test entry point): D[128 x 64] = A[shift .. shift+128) x B^T where A is a
+// [256 rows][KB] K-major swizzled tile written by ONE TMA box and the A descriptor simply starts
+// `shift` rows into it (start address not aligned to the swizzle repeat).  Pins the behaviour the
+// halo-tile convolution kernels rely on: the swizzle XOR is a function of the absolute shared
+// memory address, so a row-shifted view of a TMA-written tile is a valid operand.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_shift_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int kb_elems,
+                        int shift_rows, int base_offset, int layout_code, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int rowbytes = kb_elems * 2;
+    const uint32_t sA = sbase, sB = sbase + 256 * rowbytes;
+    const uint32_t bar0 = sB + 64 * rowbytes, bar1 = bar0 + 8, tslot = bar1 + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tslot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar0, 320 * rowbytes);
+        tma_load_2d(sA, &map_a, bar0, 0, 0);
+        tma_load_2d(sB, &map_b, bar0, 0, 0);
+        mbar_wait(bar0, 0);
+        tc_fence_after();
+        const uint64_t sbo = (uint64_t)((8 * rowbytes) >> 4);
+        const uint64_t hi = (sbo << 32) | (1ull << 46) | ((uint64_t)(base_offset & 7) << 49) | ((uint64_t)layout_code << 61);
+        const uint64_t da = (uint64_t)(((sA + shift_rows * rowbytes) >> 4) & 0x3FFF) | hi;
+        const uint64_t db = (uint64_t)((sB >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | ((uint64_t)layout_code << 61);
+        constexpr uint32_t idesc = make_idesc<64>();
+        for (int k = 0; k < kb_elems / 16; ++k) umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0);
+        umma_commit(bar1);
+    }
+    __syncwarp();
+    mbar_wait(bar1, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 struct TcState {
@@ -539,6 +598,28 @@ int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uin
     FX_CUDA(e, cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     tma_probe_kernel<<<1, 128, smem, stream>>>(m, coords[0], coords[1], coords[2], coords[3], bytes, out_dev);
     FX_LAUNCH_CHECK(e, "tma_probe_kernel");
+    return FX_OK;
+}
+
+// Test hook behind fx_debug_umma_shift (engine.cu).
+int tc_umma_shift_probe(fx_engine* e, const void* a_dev, const void* b_dev, int kb_elems, int shift_rows, int base_offset,
+                        float* out_dev, cudaStream_t stream) {
+    if (kb_elems != 64 && kb_elems != 32 && kb_elems != 16) return set_error(e, FX_ERR_INVALID, "umma probe: K block must be 64, 32 or 16");
+    if (shift_rows < 0 || shift_rows > 128) return set_error(e, FX_ERR_INVALID, "umma probe: shift must be in [0,128]");
+    const CUtensorMapSwizzle sw = kb_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kb_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const int layout_code = kb_elems == 64 ? 2 : kb_elems == 32 ? 4 : 6;
+    CUtensorMap ma, mb;
+    const uint64_t da[2] = {(uint64_t)kb_elems, 256}, db[2] = {(uint64_t)kb_elems, 64};
+    const uint64_t st[1] = {(uint64_t)kb_elems * 2};
+    const uint32_t ba[2] = {(uint32_t)kb_elems, 256}, bb[2] = {(uint32_t)kb_elems, 64}, es[2] = {1, 1};
+    int rc = encode_map(e, &ma, a_dev, 2, da, st, ba, es, sw, "umma probe A");
+    if (rc != FX_OK) return rc;
+    rc = encode_map(e, &mb, b_dev, 2, db, st, bb, es, sw, "umma probe B");
+    if (rc != FX_OK) return rc;
+    const int smem = 1024 + 320 * kb_elems * 2 + 64;
+    FX_CUDA(e, cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    umma_shift_probe_kernel<<<1, 128, smem, stream>>>(ma, mb, kb_elems, shift_rows, base_offset, layout_code, out_dev);
+    FX_LAUNCH_CHECK(e, "umma_shift_probe_kernel");
     return FX_OK;
 }
 

@@ -18,6 +18,9 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
 int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                  const uint32_t* estr, int swizzle, const int* coords, int bytes, uint8_t* out_dev, cudaStream_t stream);
 
+int tc_umma_shift_probe(fx_engine* e, const void* a_dev, const void* b_dev, int kb_elems, int shift_rows, int base_offset,
+                        float* out_dev, cudaStream_t stream);
+
 static std::mutex g_err_mutex;
 static std::string g_create_error;
 
@@ -423,6 +426,17 @@ int fx_debug_tma_probe(fx_handle e, const void* base_dev, const uint64_t* dims, 
     if (!e) return FX_ERR_INVALID;
     FX_CUDA(e, cudaSetDevice(e->device));
     int rc = tc_tma_probe(e, base_dev, dims, strides_bytes, box, elem_strides, swizzle, coords, bytes, out_dev, nullptr);
+    if (rc != FX_OK) return rc;
+    FX_CUDA(e, cudaDeviceSynchronize());
+    return FX_OK;
+}
+
+int fx_debug_umma_shift(fx_handle e, const void* a_dev, const void* b_dev, int kb_elems, int shift_rows, int base_offset,
+                        float* out_dev) {
+    if (!e) return FX_ERR_INVALID;
+    if (!a_dev || !b_dev || !out_dev) return set_error(e, FX_ERR_INVALID, "fx_debug_umma_shift: null pointer");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    int rc = tc_umma_shift_probe(e, a_dev, b_dev, kb_elems, shift_rows, base_offset, out_dev, nullptr);
     if (rc != FX_OK) return rc;
     FX_CUDA(e, cudaDeviceSynchronize());
     return FX_OK;

@@ -231,6 +231,13 @@ class Engine:
         self._check(self._lib.fx_debug_tma_probe(self._h, base.data_ptr(), a, s, b, es, swizzle, c, nbytes, out.data_ptr()))
         return out
 
+    def umma_shift(self, a: torch.Tensor, b: torch.Tensor, shift_rows: int, base_offset: int = 0) -> torch.Tensor:
+        """a: bf16 [256,kb] CUDA, b: bf16 [64,kb] CUDA -> fp32 [128,64] = a[shift:shift+128] @ b.T on the tensor cores."""
+        out = torch.empty((128, 64), dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self._check(self._lib.fx_debug_umma_shift(self._h, a.data_ptr(), b.data_ptr(), int(a.shape[1]), shift_rows, base_offset, out.data_ptr()))
+        return out
+
     def _dev_u8(self, t: torch.Tensor) -> None:
         if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous() or t.device.index != self.device_index:
             raise TypeError(f"expected a contiguous uint8 tensor on cuda:{self.device_index}")
