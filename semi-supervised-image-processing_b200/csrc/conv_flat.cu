@@ -1,0 +1,346 @@
+// Weight-stationary, halo-tile implicit-GEMM convolution on tcgen05 / TMEM ("flat" kernel).
+//
+// Serves the stride-1 3x3 convolutions of layer1 / layer2 and (in space-to-depth form) the 7x7/s2
+// stem of the frozen ResNet-18 the reference runs at src/feature_extraction.py:290-291
+// (torchvision/models/resnet.py:89-105,197-206,266-282).  Why it exists: feeding each filter tap
+// with its own TMA box (conv_tc.cu) re-reads every input pixel kh*kw times from L2 and re-reads the
+// weights for every output tile; for the Cout=64/128 layers that traffic, not the tensor pipe, is
+// the bound (profiles/r01_launches_v0.md).  Here
+//   * a CTA owns one 64-wide slice of output channels for the whole launch and keeps that slice's
+//     folded weights resident in shared memory (one TMA burst at start: 72 KB layer1, 144 KB
+//     layer2, 32 KB stem);
+//   * the input is streamed ONCE per tile: a TMA box brings R+KH-1 input rows, each P = W+KW-1
+//     pixels wide (the conv zero padding is TMA out-of-bounds fill), for one 64-channel chunk.  In
+//     shared memory that box is a flat list of pixels, one swizzled row of ROWB bytes each;
+//   * output pixel (i, x) of the tile gets flat index m = i*P + x; filter tap (r, s) of that pixel
+//     is smem row m + r*P + s.  So the A operand of tap (r, s) for 128 consecutive m is the SAME
+//     tile viewed r*P + s rows further down: one UMMA descriptor whose start address is shifted.
+//     (The swizzle XOR is a function of the absolute smem address, so a row-shifted view of a
+//     TMA-written tile is a valid operand -- pinned by tests via fx_debug_umma_shift.)  No im2col,
+//     no per-tap loads; x >= W positions are junk rows that are never stored (W/P efficiency);
+//   * accumulators are 64-column TMEM slots in a ring of 8, so the epilogue of one 128-pixel
+//     M-tile overlaps the MMAs of the next ones; 8 epilogue warps (+bias, +residual, ReLU, bf16).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue.
+#include <algorithm>
+#include <cstring>
+
+#include "tc_ptx.cuh"
+
+namespace fx {
+
+struct FlatParams {
+    int P, W, H;           // smem row pitch (pixels), valid output width / height
+    int R;                 // output rows per work tile
+    int tiles_per_img, n_work;
+    int chunks;            // 64-channel chunks of the input (1 for the stem)
+    int ns;                // cout / 64 output-channel slices
+    int x0, ypad;          // TMA box origin: x = x0, y = y0 - ypad
+    int cout;
+    int nstages, stage_bytes, box_bytes, w_bytes, slack_bytes;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    int relu;
+};
+
+constexpr int kFlatThreads = 384;
+constexpr int kFlatSlots = 8;  // 8 x 64 fp32 columns = the whole TMEM
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int ROWB, int KH, int KW>
+__global__ void __launch_bounds__(kFlatThreads, 1)
+flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const FlatParams p) {
+    constexpr int TAPS = KH * KW;
+    constexpr int KSTEPS = ROWB / 32;  // K=16 bf16 MMAs per smem row
+    constexpr int WTILE = 64 * ROWB;   // one (tap, chunk) weight tile: 64 cout rows
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sW = sbase;
+    const uint32_t sA = sbase + p.w_bytes;
+    const uint32_t bars = sA + p.nstages * p.stage_bytes + p.slack_bytes;
+    const uint32_t full0 = bars, empty0 = full0 + 8 * p.nstages, tfull0 = empty0 + 8 * p.nstages;
+    const uint32_t tempty0 = tfull0 + 8 * kFlatSlots, wbar = tempty0 + 8 * kFlatSlots, tslot = wbar + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nslice = blockIdx.x % p.ns;
+    const int w_first = blockIdx.x / p.ns, w_step = gridDim.x / p.ns;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.nstages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < kFlatSlots; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 256);
+        }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer: the weight slice once, then one halo box per (tile, chunk) =====
+        if (lane == 0) {
+            mbar_expect_tx(wbar, TAPS * p.chunks * WTILE);
+            for (int kb = 0; kb < TAPS * p.chunks; ++kb) tma_load_2d(sW + kb * WTILE, &map_b, wbar, kb * (ROWB / 2), nslice * 64);
+            uint32_t stage = 0, phase = 0;
+            for (int w = w_first; w < p.n_work; w += w_step) {
+                const int img = w / p.tiles_per_img;
+                const int y0 = (w - img * p.tiles_per_img) * p.R;
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(full0 + 8 * stage, p.box_bytes);
+                    tma_load_4d(sA + stage * p.stage_bytes, &map_a, full0 + 8 * stage, c * 64, p.x0, y0 - p.ypad, img);
+                    if (++stage == (uint32_t)p.nstages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<64>();
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, g_base = 0;
+            for (int w = w_first; w < p.n_work; w += w_step) {
+                const int img = w / p.tiles_per_img;
+                const int y0 = (w - img * p.tiles_per_img) * p.R;
+                const int rows_valid = min(p.R, p.H - y0);
+                const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_stage = sA + stage * p.stage_bytes;
+                    for (int mt = 0; mt < n_mt; ++mt) {
+                        const uint32_t g = g_base + mt, slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+                        if (c == 0) {
+                            mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t d = tmem_base + slot * 64;
+#pragma unroll
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            const int r = tap / KW, s = tap % KW;
+                            const uint64_t da = make_smem_desc_rowb<ROWB>(a_stage + (uint32_t)(mt * 128 + r * p.P + s) * ROWB);
+                            const uint64_t db = make_smem_desc_rowb<ROWB>(sW + (uint32_t)(tap * p.chunks + c) * WTILE);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k)
+                                umma_bf16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | tap | k) != 0);
+                        }
+                        if (c == p.chunks - 1) umma_commit(tfull0 + 8 * slot);
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                    if (++stage == (uint32_t)p.nstages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                g_base += n_mt;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 NHWC =====
+        const int q = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;  // which 32 of the slot's 64 columns
+        const int cbase = nslice * 64 + half * 32;
+        float bias[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + j);
+            bias[4 * j + 0] = b.x;
+            bias[4 * j + 1] = b.y;
+            bias[4 * j + 2] = b.z;
+            bias[4 * j + 3] = b.w;
+        }
+        uint32_t g_base = 0;
+        for (int w = w_first; w < p.n_work; w += w_step) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * p.R;
+            const int rows_valid = min(p.R, p.H - y0);
+            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+            for (int mt = 0; mt < n_mt; ++mt) {
+                const uint32_t g = g_base + mt, slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+                const int m = mt * 128 + q * 32 + lane;
+                const int i = m / p.P, x = m - i * p.P;
+                const bool valid = x < p.W && i < rows_valid;
+                const size_t off = (((size_t)img * p.H + y0 + i) * p.W + x) * p.cout + cbase;
+                uint4 res[4];
+                const bool has_res = valid && p.residual != nullptr;
+                if (has_res) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[j] = __ldg(rp + j);
+                }
+                mbar_wait(tfull0 + 8 * slot, use & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + slot * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back
+                if (valid) {
+                    uint4 o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float f[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * j + k]) + bias[8 * j + k];
+                        if (has_res) {
+                            const unsigned u[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                f[2 * k] += __uint_as_float(u[k] << 16);
+                                f[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        unsigned* ou = &o[j].x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                            ou[k] = *reinterpret_cast<const unsigned*>(&h2);
+                        }
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = o[j];
+                }
+            }
+            g_base += n_mt;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+constexpr int kSmemMax = 227 * 1024;
+
+template <int ROWB, int KH, int KW>
+static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, FlatParams& p, cudaStream_t stream) {
+    // shared-memory plan
+    const int stage_rows = (p.R + KH - 1) * p.P;
+    p.box_bytes = stage_rows * ROWB;
+    p.stage_bytes = (p.box_bytes + 1023) & ~1023;
+    p.w_bytes = (KH * KW * p.chunks * 64 * ROWB + 1023) & ~1023;
+    const int n_mt_max = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
+    if (n_mt_max > kFlatSlots) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: tile needs more than 8 accumulator slots");
+    const int reach_rows = n_mt_max * 128 + (KH - 1) * p.P + (KW - 1);  // rows a (junk) view may touch
+    p.slack_bytes = std::max(0, reach_rows * ROWB - p.stage_bytes);
+    p.slack_bytes = (p.slack_bytes + 15) & ~15;
+    const int fixed = 1024 + p.w_bytes + p.slack_bytes + 8 * (2 * 8 + 2 * kFlatSlots + 2) + 64;
+    p.nstages = std::min(6, (kSmemMax - fixed) / p.stage_bytes);
+    if (p.nstages < 2) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: weights + two input stages do not fit in shared memory");
+    const int smem = 1024 + p.w_bytes + p.nstages * p.stage_bytes + p.slack_bytes + 8 * (2 * p.nstages + 2 * kFlatSlots + 2) + 64;
+    static bool attr_done[16] = {};
+    if (!attr_done[e->device & 15]) {
+        FX_CUDA(e, cudaFuncSetAttribute(flat_conv_kernel<ROWB, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_done[e->device & 15] = true;
+    }
+    int grid = std::min(e->sm_count, p.n_work * p.ns);
+    grid -= grid % p.ns;
+    if (grid < p.ns) grid = p.ns;
+    flat_conv_kernel<ROWB, KH, KW><<<grid, kFlatThreads, smem, stream>>>(ma, mb, p);
+    FX_LAUNCH_CHECK(e, "flat_conv_kernel");
+    return FX_OK;
+}
+
+// Can this conv+bn group run on the flat kernel?
+bool flat_supported(const LayerGeom& g) {
+    if (g.cin == 3) return g.kh == 7 && g.kw == 7 && g.stride == 2 && g.pad == 3 && g.hin == kCrop && g.win == kCrop && g.cout == 64;
+    return g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin % 64 == 0 && g.cin <= 128 && g.cout % 64 == 0 &&
+           g.win + 2 <= 128 && g.win >= 8;
+}
+
+int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, int n,
+              int relu, cudaStream_t stream) {
+    const LayerGeom& g = L.g;
+    FlatParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.bias = L.bias;
+    p.residual = residual;
+    p.out = out;
+    p.relu = relu;
+    p.cout = g.cout;
+    p.ns = g.cout / 64;
+    p.W = g.wout;
+    p.H = g.hout;
+    CUtensorMap ma, mb;
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    if (g.cin == 3) {
+        // stem in space-to-depth form: a 4x4 stride-1 conv over [115][116][16] (see engine.cu pack)
+        p.P = kS2dW;
+        p.R = 8;
+        p.chunks = 1;
+        p.x0 = 0;
+        p.ypad = 0;
+        const uint64_t dims[4] = {(uint64_t)kS2dC, (uint64_t)kS2dW, (uint64_t)kS2dH, (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)kS2dC * 2, (uint64_t)kS2dW * kS2dC * 2, (uint64_t)kS2dH * kS2dW * kS2dC * 2};
+        const uint32_t box[4] = {(uint32_t)kS2dC, (uint32_t)p.P, (uint32_t)(p.R + 3), 1};
+        int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stem A");
+        if (rc != FX_OK) return rc;
+        const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+        const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+        const uint32_t bbox[2] = {16, 64};
+        rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stem B");
+        if (rc != FX_OK) return rc;
+        p.tiles_per_img = (p.H + p.R - 1) / p.R;
+        p.n_work = n * p.tiles_per_img;
+        return launch_flat<32, 4, 4>(e, ma, mb, p, stream);
+    }
+    p.P = g.win + 2;
+    p.R = std::max(1, std::min(g.hout, 256 / p.P));
+    p.chunks = g.cin / 64;
+    p.x0 = -1;
+    p.ypad = 1;
+    const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.P, (uint32_t)(p.R + 2), 1};
+    int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat A");
+    if (rc != FX_OK) return rc;
+    const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+    const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+    const uint32_t bbox[2] = {64, 64};
+    rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat B");
+    if (rc != FX_OK) return rc;
+    p.tiles_per_img = (p.H + p.R - 1) / p.R;
+    p.n_work = n * p.tiles_per_img;
+    return launch_flat<128, 3, 3>(e, ma, mb, p, stream);
+}
+
+}  // namespace fx

@@ -25,115 +25,9 @@
 #include <algorithm>
 #include <cstring>
 
-#include <cudaTypedefs.h>
-
-#include "fx_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace fx {
-
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Parity wait with a watchdog: a protocol bug must end in a trap (the launch fails with an
-// error) rather than in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    unsigned long long t0 = 0;
-    for (uint32_t spin = 0;; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (spin == 64) t0 = global_ns();
-        if (spin > 64 && (spin & 63) == 0 && global_ns() - t0 > 2000000000ull) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        :
-        : "r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        :
-        : "r"(dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread for the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, K-major operand whose K extent is exactly one swizzle atom
-// (BK*2 bytes = 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).  8-row groups are `8*BK*2` bytes apart.
-template <int BK>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    constexpr uint64_t sbo = (8 * BK * 2) >> 4;
-    constexpr uint64_t layout = BK == 64 ? 2 : 4;  // SWIZZLE_128B : SWIZZLE_64B
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-// Instruction descriptor: c=f32, a=b=bf16, both K-major, M=128, N=BN.
-template <int BN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------
 // Kernel
@@ -438,7 +332,7 @@ struct TcState {
     PFN_cuTensorMapEncodeTiled encode = nullptr;
 };
 
-static int encode_map(fx_engine* e, CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+int tc_encode_map(fx_engine* e, CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr, CUtensorMapSwizzle sw,
                       const char* what) {
     TcState* st = static_cast<TcState*>(e->tc_state);
@@ -522,47 +416,19 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_g * p.n_tiles_n;
 
     CUtensorMap ma, mb;
-    const bool is_conv1 = g.cin == 3;
-    if (is_conv1) {
-        if (!(g.kh == 7 && g.kw == 7 && g.stride == 2 && g.pad == 3 && g.hin == kCrop && g.win == kCrop))
-            return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: a 3-channel input is only supported for the 7x7/s2/p3 stem on 224x224");
-        // A: the staging tensor [n][230][232][4] seen as {32 elems (8 px x 4 ch), ow, ih, n}: the window of
-        // output column ow starts at pixel 2*ow, i.e. 16 bytes further for each ow.
-        const uint64_t dims[4] = {32, (uint64_t)g.wout, (uint64_t)kIn0H, (uint64_t)n};
-        const uint64_t strides[3] = {16, (uint64_t)kIn0W * kIn0C * 2, (uint64_t)kIn0H * kIn0W * kIn0C * 2};
-        const uint32_t box[4] = {32, 1u << p.wt_log2, 2u << p.ht_log2, 1u << p.nt_log2};
-        const uint32_t estr[4] = {1, 1, 2, 1};
-        int rc = encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B, "conv1 A");
-        if (rc != FX_OK) return rc;
-        const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
-        const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
-        const uint32_t bbox[2] = {32, (uint32_t)bn};
-        const uint32_t be[2] = {1, 1};
-        rc = encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_64B, "conv1 B");
-        if (rc != FX_OK) return rc;
-        p.kh = 7;
-        p.kw = 1;
-        p.cchunks = 1;
-        p.cw_mul = 1;
-        p.ch_mul = 2;
-        p.pad_w = 0;
-        p.pad_h = 0;
-        if (bn != 64) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: stem must have 64 output channels");
-        return launch_tc<64, 32, 7>(e, ma, mb, p, stream);
-    }
-    if (g.cin % 64 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: cin must be 3 or a multiple of 64");
+    if (g.cin % 64 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: cin must be a multiple of 64 (the stem runs on the flat kernel)");
     {
         const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
         const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
         const uint32_t box[4] = {64, (uint32_t)g.stride << p.wt_log2, (uint32_t)g.stride << p.ht_log2, 1u << p.nt_log2};
         const uint32_t estr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
-        int rc = encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A");
+        int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A");
         if (rc != FX_OK) return rc;
         const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
         const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
         const uint32_t bbox[2] = {64, (uint32_t)bn};
         const uint32_t be[2] = {1, 1};
-        rc = encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B");
+        rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B");
         if (rc != FX_OK) return rc;
     }
     p.kh = g.kh;
@@ -592,7 +458,7 @@ int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uin
                             : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                             : swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                             : CU_TENSOR_MAP_SWIZZLE_NONE;
-    int rc = encode_map(e, &m, base, 4, dims, strides, box, estr, sw, "probe");
+    int rc = tc_encode_map(e, &m, base, 4, dims, strides, box, estr, sw, "probe");
     if (rc != FX_OK) return rc;
     const int smem = 1024 + ((bytes + 15) & ~15) + 16;
     FX_CUDA(e, cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -612,9 +478,9 @@ int tc_umma_shift_probe(fx_engine* e, const void* a_dev, const void* b_dev, int 
     const uint64_t da[2] = {(uint64_t)kb_elems, 256}, db[2] = {(uint64_t)kb_elems, 64};
     const uint64_t st[1] = {(uint64_t)kb_elems * 2};
     const uint32_t ba[2] = {(uint32_t)kb_elems, 256}, bb[2] = {(uint32_t)kb_elems, 64}, es[2] = {1, 1};
-    int rc = encode_map(e, &ma, a_dev, 2, da, st, ba, es, sw, "umma probe A");
+    int rc = tc_encode_map(e, &ma, a_dev, 2, da, st, ba, es, sw, "umma probe A");
     if (rc != FX_OK) return rc;
-    rc = encode_map(e, &mb, b_dev, 2, db, st, bb, es, sw, "umma probe B");
+    rc = tc_encode_map(e, &mb, b_dev, 2, db, st, bb, es, sw, "umma probe B");
     if (rc != FX_OK) return rc;
     const int smem = 1024 + 320 * kb_elems * 2 + 64;
     FX_CUDA(e, cudaFuncSetAttribute(umma_shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

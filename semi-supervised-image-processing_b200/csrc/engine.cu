@@ -98,16 +98,17 @@ static int pack_layer(fx_engine* e, const fx_conv_bn& src, int hin, int win, Pac
     // bf16 GEMM-B pack [cout][K]
     std::vector<__nv_bfloat16> w;
     if (stem) {
-        // K = kh rows x (8 pixels x 4 channels); pixel 7 and channel 3 are zero
-        if (g.kw > 8) return set_error(e, FX_ERR_UNSUPPORTED, "stem kernel wider than 8");
-        L.k_bf16 = g.kh * 32;
+        // space-to-depth form (fx_common.cuh): K = (R, S, dy, dx, c) with filter row 2R+dy, column 2S+dx;
+        // the 8th row / column and channels 12..15 are zero
+        if (g.kh != 7 || g.kw != 7) return set_error(e, FX_ERR_UNSUPPORTED, "stem must be 7x7");
+        L.k_bf16 = 16 * kS2dC;
         w.assign((size_t)g.cout * L.k_bf16, __float2bfloat16_rn(0.f));
         for (int o = 0; o < g.cout; ++o)
-            for (int r = 0; r < g.kh; ++r)
-                for (int s = 0; s < g.kw; ++s)
-                    for (int i = 0; i < g.cin; ++i)
-                        w[(size_t)o * L.k_bf16 + r * 32 + s * 4 + i] =
-                            __float2bfloat16_rn(L.host_w[((size_t)o * taps + r * g.kw + s) * g.cin + i]);
+            for (int r = 0; r < 7; ++r)
+                for (int s = 0; s < 7; ++s)
+                    for (int i = 0; i < 3; ++i)
+                        w[(size_t)o * L.k_bf16 + ((r >> 1) * 4 + (s >> 1)) * kS2dC + ((r & 1) * 2 + (s & 1)) * 3 + i] =
+                            __float2bfloat16_rn(L.host_w[((size_t)o * taps + r * 7 + s) * 3 + i]);
     } else {
         L.k_bf16 = taps * g.cin;
         w.resize((size_t)g.cout * L.k_bf16);
@@ -122,9 +123,13 @@ static int pack_layer(fx_engine* e, const fx_conv_bn& src, int hin, int win, Pac
 static int run_conv(fx_engine* e, int li, const void* in, const void* residual, void* out, float* out_f32, int n, int relu,
                     cudaStream_t stream) {
     const PackedLayer& L = e->layers[li];
-    if (e->precision == FX_PRECISION_BF16)
+    if (e->precision == FX_PRECISION_BF16) {
+        if (!out_f32 && flat_supported(L.g))
+            return flat_conv(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
+                             static_cast<__nv_bfloat16*>(out), n, relu, stream);
         return tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
                               static_cast<__nv_bfloat16*>(out), out_f32, n, relu, stream);
+    }
     float* o = out_f32 ? out_f32 : static_cast<float*>(out);
     if (li == 0)
         return simt_conv(e, L, static_cast<const float*>(in), kIn0H, kIn0W, kIn0C, 0, static_cast<const float*>(residual), o, n,
@@ -229,7 +234,8 @@ int fx_create(fx_handle* out, int device, int max_batch, int precision) {
         return rc;
     };
     const size_t esz = precision == FX_PRECISION_BF16 ? 2 : 4;
-    const size_t in0_bytes = (size_t)max_batch * kIn0H * kIn0W * kIn0C * esz;
+    const size_t in0_bytes = precision == FX_PRECISION_BF16 ? (size_t)max_batch * kS2dH * kS2dW * kS2dC * 2
+                                                            : (size_t)max_batch * kIn0H * kIn0W * kIn0C * 4;
     e->act_bytes = (size_t)max_batch * 112 * 112 * 64 * esz;  // largest activation: conv1 output
     int rc = FX_OK;
     auto alloc = [&](void** p, size_t bytes) {
@@ -401,9 +407,12 @@ int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const 
             in_act = bin;
         }
         if (residual_dev && (rc = f32_to_bf16(e, residual_dev, bres, out_count, stream)) != FX_OK) break;
-        if ((rc = tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, nullptr, n,
-                                 relu, stream)) != FX_OK)
-            break;
+        if (flat_supported(L.g))
+            rc = flat_conv(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, n, relu, stream);
+        else
+            rc = tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, nullptr, n, relu,
+                                stream);
+        if (rc != FX_OK) break;
         rc = bf16_to_f32(e, bout, out_dev, out_count, stream);
     } while (0);
     cudaError_t serr = cudaStreamSynchronize(stream);  // the packed weights are freed below

@@ -31,6 +31,15 @@ constexpr int kIn0H = kCrop + 6;  // 230
 constexpr int kIn0W = kCrop + 8;  // 232: 8-pixel windows starting at 2*ow stay inside the row
 constexpr int kIn0C = 4;
 
+// bf16 path: the stem reads the normalised crop in SPACE-TO-DEPTH form so that the 7x7/s2 conv is a
+// 4x4/s1 conv the flat kernel can run (conv_flat.cu).  With the crop zero-padded by 3 on every side
+// (230 x 230, conv padding of the NORMALISED tensor), s2d pixel (Y, X) holds padded pixels
+// (2Y+dy, 2X+dx), dy, dx in {0,1}, as channel (dy*2+dx)*3 + c; channels 12..15 and column 115 are
+// zero.  [n][115][116][16] bf16 = 426,880 B per image (same bytes as the fp32 path's layout / 2).
+constexpr int kS2dH = 115;
+constexpr int kS2dW = 116;
+constexpr int kS2dC = 16;
+
 struct LayerGeom {
     int cin, cout, kh, kw, stride, pad;
     int hin, win, hout, wout;  // logical activation sizes
@@ -66,7 +75,7 @@ struct PackedLayer {
     LayerGeom g{};
     // fp32 pack: [cout][kh][kw][cin_pad]  (cin_pad = 4 for conv1, else cin)
     float* w_f32 = nullptr;
-    // bf16 pack: GEMM B matrix [cout][K], K ordered (kh, kw, cin) -- conv1: (kh, 8 px, 4 ch)
+    // bf16 pack: GEMM B matrix [cout][K], K ordered (kh, kw, cin) -- conv1: s2d form (4, 4, 16)
     __nv_bfloat16* w_bf16 = nullptr;
     float* bias = nullptr;
     int k_bf16 = 0;
@@ -96,7 +105,7 @@ struct fx_engine {
 
     // trunk
     fx::PackedLayer layers[fx::kNumLayers];
-    void* in0 = nullptr;       // [max_batch][230][232][4], bf16 or fp32
+    void* in0 = nullptr;       // conv1 staging: fp32 [max_batch][230][232][4] or bf16 s2d [max_batch][115][116][16]
     void* act[3] = {nullptr, nullptr, nullptr};  // ping-pong activations (NHWC)
     float* final_f32 = nullptr;  // [max_batch][49][512]
     size_t act_bytes = 0;
@@ -160,5 +169,10 @@ void tc_free(fx_engine* e);
 // Runs layer `li` on NHWC bf16 activations.  out_f32 != nullptr: write fp32 instead of bf16.
 int tc_conv(fx_engine* e, int li, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
             float* out_f32, int n, int relu, cudaStream_t stream);
+
+// conv_flat.cu (bf16 tcgen05 weight-stationary halo-tile path: stem, layer1, layer2 3x3/s1)
+bool flat_supported(const LayerGeom& g);
+int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, int n,
+              int relu, cudaStream_t stream);
 
 }  // namespace fx

@@ -271,16 +271,11 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
     __syncthreads();
 
     // ---- vertical pass + table lookup + store -------------------------------------------------
-    const int nout = (y1 - y0) * kCrop;
     const size_t img_idx = blockIdx.y;
-    for (int idx = tid; idx < nout; idx += kPreThreads) {
-        const int yy = idx / kCrop;
-        const int x = idx - yy * kCrop;
-        const int y = y0 + yy;
+    auto vertical = [&](int y, int x, int& v0, int& v1, int& v2) {
         const int ym = __ldg(vy_min + y) - rlo;
         const int n = __ldg(vy_cnt + y);
         const int32_t* k = vk + y * img.ksv;
-        int v0, v1, v2;
         if (C == 3) {
             int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
             const uint8_t* p = s_tmp + ym * rowpix + 3 * x;
@@ -303,6 +298,47 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
             }
             v0 = v1 = v2 = clip8(a0);  // gray carriage: one plane, three normalisations
         }
+    };
+    if (MODE == 1) {
+        // bf16 space-to-depth staging (fx_common.cuh): a thread owns the two crop pixels (y, 2j-1), (y, 2j)
+        // that share s2d pixel X = j+1 -> 6 consecutive bf16 at channel (dy*2)*3, written as 3 words.
+        constexpr int kPairs = kCrop / 2 + 1;  // 113
+        const int npair = (y1 - y0) * kPairs;
+        for (int idx = tid; idx < npair; idx += kPreThreads) {
+            const int yy = idx / kPairs;
+            const int j = idx - yy * kPairs;
+            const int y = y0 + yy;
+            const int xa = 2 * j - 1, xb = 2 * j;
+            unsigned short h[6] = {0, 0, 0, 0, 0, 0};
+            int v0, v1, v2;
+            if (xa >= 0) {
+                vertical(y, xa, v0, v1, v2);
+                h[0] = __bfloat16_as_ushort(s_lutb[v0]);
+                h[1] = __bfloat16_as_ushort(s_lutb[256 + v1]);
+                h[2] = __bfloat16_as_ushort(s_lutb[512 + v2]);
+            }
+            if (xb < kCrop) {
+                vertical(y, xb, v0, v1, v2);
+                h[3] = __bfloat16_as_ushort(s_lutb[v0]);
+                h[4] = __bfloat16_as_ushort(s_lutb[256 + v1]);
+                h[5] = __bfloat16_as_ushort(s_lutb[512 + v2]);
+            }
+            const int py = y + kIn0Pad;
+            const size_t elem = ((img_idx * kS2dH + (py >> 1)) * kS2dW + (j + 1)) * kS2dC + (py & 1) * 6;
+            unsigned* o = reinterpret_cast<unsigned*>(reinterpret_cast<__nv_bfloat16*>(out) + elem);
+            o[0] = (unsigned)h[0] | ((unsigned)h[1] << 16);
+            o[1] = (unsigned)h[2] | ((unsigned)h[3] << 16);
+            o[2] = (unsigned)h[4] | ((unsigned)h[5] << 16);
+        }
+        return;
+    }
+    const int nout = (y1 - y0) * kCrop;
+    for (int idx = tid; idx < nout; idx += kPreThreads) {
+        const int yy = idx / kCrop;
+        const int x = idx - yy * kCrop;
+        const int y = y0 + yy;
+        int v0, v1, v2;
+        vertical(y, x, v0, v1, v2);
         if (MODE == 0) {
             float* o = reinterpret_cast<float*>(out) + img_idx * 3 * kCrop * kCrop + (size_t)y * kCrop + x;
             o[0] = s_lut[v0];
@@ -310,19 +346,15 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
             o[2 * kCrop * kCrop] = s_lut[512 + v2];
         } else {
             const size_t pix = (img_idx * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
-            if (MODE == 1) {
-                const unsigned short b0 = __bfloat16_as_ushort(s_lutb[v0]);
-                const unsigned short b1 = __bfloat16_as_ushort(s_lutb[256 + v1]);
-                const unsigned short b2 = __bfloat16_as_ushort(s_lutb[512 + v2]);
-                uint2 pk;
-                pk.x = (unsigned)b0 | ((unsigned)b1 << 16);
-                pk.y = (unsigned)b2;
-                reinterpret_cast<uint2*>(out)[pix] = pk;
-            } else {
-                reinterpret_cast<float4*>(out)[pix] = make_float4(s_lut[v0], s_lut[256 + v1], s_lut[512 + v2], 0.f);
-            }
+            reinterpret_cast<float4*>(out)[pix] = make_float4(s_lut[v0], s_lut[256 + v1], s_lut[512 + v2], 0.f);
         }
     }
+}
+
+// Element offset of crop pixel (y, x), channel 0, in the bf16 space-to-depth staging tensor.
+__device__ __forceinline__ size_t s2d_elem(size_t img, int y, int x) {
+    const int py = y + kIn0Pad, px = x + kIn0Pad;
+    return ((img * kS2dH + (py >> 1)) * kS2dW + (px >> 1)) * kS2dC + ((py & 1) * 2 + (px & 1)) * 3;
 }
 
 // fp32 NCHW [n][3][224][224] (the reference's batch tensor) -> conv1 staging layout.
@@ -335,14 +367,13 @@ __global__ void stage_nchw_kernel(const float* __restrict__ in, void* __restrict
         const int y = rem / kCrop, x = rem - y * kCrop;
         const float* p = in + img * 3 * kCrop * kCrop + rem;
         const float c0 = p[0], c1 = p[kCrop * kCrop], c2 = p[2 * kCrop * kCrop];
-        const size_t pix = (img * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
         if (BF16) {
-            uint2 pk;
-            pk.x = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c0)) |
-                   ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c1)) << 16);
-            pk.y = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c2));
-            reinterpret_cast<uint2*>(out)[pix] = pk;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + s2d_elem(img, y, x);
+            o[0] = __float2bfloat16_rn(c0);
+            o[1] = __float2bfloat16_rn(c1);
+            o[2] = __float2bfloat16_rn(c2);
         } else {
+            const size_t pix = (img * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
             reinterpret_cast<float4*>(out)[pix] = make_float4(c0, c1, c2, 0.f);
         }
     }

@@ -278,14 +278,15 @@ __global__ void pad_in0_kernel(const float* __restrict__ in, void* __restrict__ 
         const int rem = (int)(i - img * kCrop * kCrop);
         const int y = rem / kCrop, x = rem - y * kCrop;
         const float c0 = in[3 * i], c1 = in[3 * i + 1], c2 = in[3 * i + 2];
-        const size_t pix = (img * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
         if (BF16) {
-            uint2 pk;
-            pk.x = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c0)) |
-                   ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c1)) << 16);
-            pk.y = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(c2));
-            reinterpret_cast<uint2*>(out)[pix] = pk;
+            const int py = y + kIn0Pad, px = x + kIn0Pad;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) +
+                               ((img * kS2dH + (py >> 1)) * kS2dW + (px >> 1)) * kS2dC + ((py & 1) * 2 + (px & 1)) * 3;
+            o[0] = __float2bfloat16_rn(c0);
+            o[1] = __float2bfloat16_rn(c1);
+            o[2] = __float2bfloat16_rn(c2);
         } else {
+            const size_t pix = (img * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
             reinterpret_cast<float4*>(out)[pix] = make_float4(c0, c1, c2, 0.f);
         }
     }

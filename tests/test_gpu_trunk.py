@@ -86,6 +86,19 @@ def test_tma_overlapping_windows_for_the_stem(eng_bf16):
         assert torch.equal(got[j], x[0, 1, 2 * ow : 2 * ow + 8].reshape(-1).float().cpu())
 
 
+@pytest.mark.parametrize("kb", [64, 32, 16])
+def test_umma_row_shifted_descriptor_views(eng_bf16, kb):
+    # the halo-tile ("flat") conv kernels feed every filter tap as a row-shifted view of one TMA-written
+    # swizzled tile; exact integer data so the comparison is bit-exact
+    g = torch.Generator().manual_seed(kb)
+    a = torch.randint(-4, 5, (256, kb), generator=g).float()
+    b = torch.randint(-4, 5, (64, kb), generator=g).float()
+    ad, bd = a.to(torch.bfloat16).cuda(), b.to(torch.bfloat16).cuda()
+    for shift in (0, 1, 3, 7, 8, 30, 58, 59, 117, 128):
+        got = eng_bf16.umma_shift(ad, bd, shift).cpu()
+        assert torch.equal(got, a[shift : shift + 128] @ b.T), f"shift {shift}"
+
+
 # ---- one conv+bn group at a time ------------------------------------------------------------------
 
 LAYER_CASES = [
@@ -103,6 +116,10 @@ LAYER_CASES = [
     (512, 512, 3, 1, 7, 64, True, True),
     (512, 512, 3, 1, 7, 1, False, True),
     (3, 64, 7, 2, 224, 3, False, True),
+    (3, 64, 7, 2, 224, 40, False, True),
+    (64, 64, 3, 1, 56, 37, True, True),
+    (128, 128, 3, 1, 28, 41, True, False),
+    (128, 128, 3, 1, 28, 1, False, True),
 ]
 
 
