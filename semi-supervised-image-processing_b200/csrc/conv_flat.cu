@@ -102,7 +102,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     if (warp == 0) {
         // ===== TMA producer: the weight slice once, then one halo box per (tile, chunk) =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(wbar, TAPS * p.chunks * WTILE);
             for (int kb = 0; kb < TAPS * p.chunks; ++kb) tma_load_2d(sW + kb * WTILE, &map_b, wbar, kb * (ROWB / 2), nslice * 64);
             uint32_t stage = 0, phase = 0;
@@ -121,47 +121,55 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<64>();
-            mbar_wait(wbar, 0);
-            tc_fence_after();
-            uint32_t stage = 0, phase = 0, g_base = 0;
-            for (int w = w_first; w < p.n_work; w += w_step) {
-                const int img = w / p.tiles_per_img;
-                const int y0 = (w - img * p.tiles_per_img) * p.R;
-                const int rows_valid = min(p.R, p.H - y0);
-                const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
-                for (int c = 0; c < p.chunks; ++c) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t a_stage = sA + stage * p.stage_bytes;
-                    for (int mt = 0; mt < n_mt; ++mt) {
-                        const uint32_t g = g_base + mt, slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
-                        if (c == 0) {
-                            mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
-                            tc_fence_after();
-                        }
+        // ===== MMA issuer: the whole warp walks the (uniform) schedule, one elected lane issues =====
+        constexpr uint32_t idesc = make_idesc<64>();
+        constexpr uint64_t desc_hi = make_smem_desc_rowb<ROWB>(0) & 0xFFFFFFFF00000000ull;
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0, g_base = 0;
+        const uint32_t w_lo = sW >> 4;
+        const uint32_t row_units = ROWB / 16;  // descriptor address units (16 B) per smem row
+        for (int w = w_first; w < p.n_work; w += w_step) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * p.R;
+            const int rows_valid = min(p.R, p.H - y0);
+            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_lo_stage = (sA + stage * p.stage_bytes) >> 4;
+                for (int mt = 0; mt < n_mt; ++mt) {
+                    const uint32_t g = g_base + mt, slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+                    if (c == 0) {
+                        mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
+                        tc_fence_after();
+                    }
+                    if (elect_one_sync()) {
                         const uint32_t d = tmem_base + slot * 64;
+                        const uint32_t a_lo_mt = a_lo_stage + (uint32_t)(mt * 128) * row_units;
+                        const uint32_t b_lo_c = w_lo + (uint32_t)c * (WTILE / 16);
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap) {
                             const int r = tap / KW, s = tap % KW;
-                            const uint64_t da = make_smem_desc_rowb<ROWB>(a_stage + (uint32_t)(mt * 128 + r * p.P + s) * ROWB);
-                            const uint64_t db = make_smem_desc_rowb<ROWB>(sW + (uint32_t)(tap * p.chunks + c) * WTILE);
+                            const uint32_t a_lo = a_lo_mt + (uint32_t)(r * p.P + s) * row_units;
+                            const uint32_t b_lo = b_lo_c + (uint32_t)(tap * p.chunks) * (WTILE / 16);
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k)
-                                umma_bf16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (c | tap | k) != 0);
+                                umma_bf16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                                          (c | tap | k) != 0);
                         }
                         if (c == p.chunks - 1) umma_commit(tfull0 + 8 * slot);
                     }
-                    umma_commit(empty0 + 8 * stage);
-                    if (++stage == (uint32_t)p.nstages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    __syncwarp();
                 }
-                g_base += n_mt;
+                if (elect_one_sync()) umma_commit(empty0 + 8 * stage);
+                __syncwarp();
+                if (++stage == (uint32_t)p.nstages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
             }
+            g_base += n_mt;
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 NHWC =====

@@ -97,7 +97,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int n_tile = t % p.n_tiles_n;
@@ -125,30 +125,31 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<BN>();
-            uint32_t stage = 0, phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-                mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+        // ===== MMA issuer: warp-uniform schedule, one elected lane issues =====
+        constexpr uint32_t idesc = make_idesc<BN>();
+        constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
+        uint32_t stage = 0, phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint64_t da = make_smem_desc<BK>(sA + stage * L::kA);
-                    const uint64_t db = make_smem_desc<BK>(sB + stage * L::kB);
+                if (elect_one_sync()) {
+                    const uint32_t a_lo = (sA + stage * L::kA) >> 4, b_lo = (sB + stage * L::kB) >> 4;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (kb | k) != 0);
                     umma_commit(empty0 + 8 * stage);  // frees the smem slot once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }

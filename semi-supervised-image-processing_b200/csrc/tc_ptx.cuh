@@ -13,6 +13,17 @@ namespace fx {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (ptxas then knows the guarded region is single-threaded and feeds
+// UTCHMMA / UTMALDG from uniform registers directly instead of a per-instruction broadcast loop).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -101,7 +112,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor, K-major operand whose K extent is exactly one swizzle atom
 // (BK*2 bytes = 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).  8-row groups are `8*BK*2` bytes apart.
 template <int BK>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__host__ __device__ constexpr uint64_t make_smem_desc(uint32_t saddr) {
     constexpr uint64_t sbo = (8 * BK * 2) >> 4;
     constexpr uint64_t layout = BK == 64 ? 2 : 4;  // SWIZZLE_128B : SWIZZLE_64B
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | (layout << 61);
@@ -118,7 +129,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 // The start address may sit any whole number of rows into a TMA-written tile: the swizzle XOR is
 // a function of the absolute shared-memory address (pinned by fx_debug_umma_shift).
 template <int ROWB>
-__device__ __forceinline__ uint64_t make_smem_desc_rowb(uint32_t saddr) {
+__host__ __device__ constexpr uint64_t make_smem_desc_rowb(uint32_t saddr) {
     constexpr uint64_t sbo = (8 * ROWB) >> 4;
     constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | (layout << 61);
