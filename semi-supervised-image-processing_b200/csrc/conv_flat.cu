@@ -59,6 +59,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <int ROWB, int KH, int KW>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const FlatParams p) {
@@ -69,7 +83,9 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sW = sbase;
     const uint32_t sA = sbase + p.w_bytes;
-    const uint32_t bars = sA + p.nstages * p.stage_bytes + p.slack_bytes;
+    const uint32_t stage0 = sA + p.nstages * p.stage_bytes + p.slack_bytes;  // 8 epilogue warps x 4 KB staging
+    const uint32_t bias0 = stage0 + 8 * 4096;                                // 64 fp32 bias values of this slice
+    const uint32_t bars = bias0 + 256;
     const uint32_t full0 = bars, empty0 = full0 + 8 * p.nstages, tfull0 = empty0 + 8 * p.nstages;
     const uint32_t tempty0 = tfull0 + 8 * kFlatSlots, wbar = tempty0 + 8 * kFlatSlots, tslot = wbar + 8;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
@@ -89,12 +105,17 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int i = 0; i < kFlatSlots; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 256);
+            mbar_init(tempty0 + 8 * i, 128);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tslot, 512);
+    if (warp == 3) {
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        bs[lane] = __ldg(p.bias + nslice * 64 + lane);
+        bs[lane + 32] = __ldg(p.bias + nslice * 64 + lane + 32);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -172,78 +193,132 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             g_base += n_mt;
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 NHWC =====
-        const int q = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = (warp - 4) >> 2;  // which 32 of the slot's 64 columns
-        const int cbase = nslice * 64 + half * 32;
-        float bias[32];
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 -> smem -> coalesced NHWC =====
+        // Two groups of four warps take alternate M-tiles (g even / odd).  A warp owns 32 accumulator
+        // rows x 64 channels = 4 KB, staged in a private swizzled smem block so that global traffic is
+        // whole 128-byte pixel rows (8 lanes x 16 B) instead of one 16-byte piece per lane per line.
+        // The residual of the warp's NEXT tile is prefetched into the same block with cp.async.
+        const int q = warp & 3;           // TMEM lane quarter this warp may read
+        const int grp = (warp - 4) >> 2;  // which M-tiles (g & 1) this warp handles
+        const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        const int cbase = nslice * 64;
+        const int rr0 = lane >> 3, ch = lane & 7;  // store-out role: row (it*4 + rr0), 16-byte chunk ch
+        const bool has_res = p.residual != nullptr;
+
+        // this group's M-tile sequence
+        int w = w_first, mt = 0, n_mt = 0, img = 0, y0 = 0, rows_valid = 0;
+        uint32_t g = 0;
+        auto tile_setup = [&]() {
+            img = w / p.tiles_per_img;
+            y0 = (w - img * p.tiles_per_img) * p.R;
+            rows_valid = min(p.R, p.H - y0);
+            n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+        };
+        auto advance = [&]() {  // next M-tile in schedule order; returns false at the end
+            ++g;
+            if (++mt == n_mt) {
+                mt = 0;
+                w += w_step;
+                if (w >= p.n_work) return false;
+                tile_setup();
+            }
+            return true;
+        };
+        auto my_pix = [&]() {  // output pixel index of this lane's accumulator row, or -1
+            const int m = mt * 128 + q * 32 + lane;
+            const int i = m / p.P, x = m - i * p.P;
+            return (x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+        };
+        auto prefetch_res = [&](int pix) {
+            if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + j);
-            bias[4 * j + 0] = b.x;
-            bias[4 * j + 1] = b.y;
-            bias[4 * j + 2] = b.z;
-            bias[4 * j + 3] = b.w;
-        }
-        uint32_t g_base = 0;
-        for (int w = w_first; w < p.n_work; w += w_step) {
-            const int img = w / p.tiles_per_img;
-            const int y0 = (w - img * p.tiles_per_img) * p.R;
-            const int rows_valid = min(p.R, p.H - y0);
-            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
-            for (int mt = 0; mt < n_mt; ++mt) {
-                const uint32_t g = g_base + mt, slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
-                const int m = mt * 128 + q * 32 + lane;
-                const int i = m / p.P, x = m - i * p.P;
-                const bool valid = x < p.W && i < rows_valid;
-                const size_t off = (((size_t)img * p.H + y0 + i) * p.W + x) * p.cout + cbase;
-                uint4 res[4];
-                const bool has_res = valid && p.residual != nullptr;
-                if (has_res) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) res[j] = __ldg(rp + j);
-                }
-                mbar_wait(tfull0 + 8 * slot, use & 1);
-                tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem_base + slot * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back
-                if (valid) {
-                    uint4 o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float f[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * j + k]) + bias[8 * j + k];
-                        if (has_res) {
-                            const unsigned u[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                f[2 * k] += __uint_as_float(u[k] << 16);
-                                f[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
-                            }
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
-                        }
-                        unsigned* ou = &o[j].x;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-                            ou[k] = *reinterpret_cast<const unsigned*>(&h2);
-                        }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) op[j] = o[j];
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rr0;
+                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                    if (pr >= 0)
+                        cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + ch * 8);
                 }
             }
-            g_base += n_mt;
+            cp_async_commit();
+        };
+
+        bool live = w < p.n_work;
+        if (live) {
+            tile_setup();
+            if (grp == 1) live = advance();
         }
+        int pix = live ? my_pix() : -1;
+        if (live) prefetch_res(pix);
+        while (live) {
+            const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+            cp_async_wait_all();
+            __syncwarp();
+            mbar_wait(tfull0 + 8 * slot, use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + slot * 64 + ((uint32_t)(q * 32) << 16);
+            const uint32_t srow = stg + lane * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
+                tmem_ld_wait();
+                if (h == 1) {
+                    tc_fence_before();
+                    mbar_arrive(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
+                    float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                  __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                  __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                  __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                    if (has_res && pix >= 0) {
+                        const uint4 rv = lds128(sa);
+                        const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            f[2 * k] += __uint_as_float(u[k] << 16);
+                            f[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                    }
+                    uint4 o;
+                    unsigned* ou = &o.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                        ou[k] = *reinterpret_cast<const unsigned*>(&h2);
+                    }
+                    sts128(sa, o);
+                }
+            }
+            __syncwarp();
+            // store-out: 4 pixel rows (512 contiguous bytes when the pixels are neighbours) per instruction
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rr0;
+                const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                if (pr >= 0) {
+                    const uint4 val = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    *reinterpret_cast<uint4*>(p.out + (size_t)pr * p.cout + cbase + ch * 8) = val;
+                }
+            }
+            __syncwarp();
+            live = advance();
+            if (live) live = advance();
+            if (live) {
+                pix = my_pix();
+                prefetch_res(pix);
+            }
+        }
+        cp_async_wait_all();
     }
 
     tc_fence_before();
@@ -259,27 +334,34 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemMax = 227 * 1024;
 
+constexpr int kEpiBytes = 8 * 4096 + 256;  // epilogue staging + bias
+
+// Shared-memory plan for a given R; returns the total dynamic smem bytes, or 0 if it cannot work.
 template <int ROWB, int KH, int KW>
-static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, FlatParams& p, cudaStream_t stream) {
-    // shared-memory plan
+static int plan_flat(FlatParams& p) {
     const int stage_rows = (p.R + KH - 1) * p.P;
     p.box_bytes = stage_rows * ROWB;
     p.stage_bytes = (p.box_bytes + 1023) & ~1023;
     p.w_bytes = (KH * KW * p.chunks * 64 * ROWB + 1023) & ~1023;
     const int n_mt_max = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
-    if (n_mt_max > kFlatSlots) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: tile needs more than 8 accumulator slots");
+    if (n_mt_max > kFlatSlots) return 0;
     const int reach_rows = n_mt_max * 128 + (KH - 1) * p.P + (KW - 1);  // rows a (junk) view may touch
-    p.slack_bytes = std::max(0, reach_rows * ROWB - p.stage_bytes);
-    p.slack_bytes = (p.slack_bytes + 15) & ~15;
-    const int fixed = 1024 + p.w_bytes + p.slack_bytes + 8 * (2 * 8 + 2 * kFlatSlots + 2) + 64;
-    p.nstages = std::min(6, (kSmemMax - fixed) / p.stage_bytes);
-    if (p.nstages < 2) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: weights + two input stages do not fit in shared memory");
-    const int smem = 1024 + p.w_bytes + p.nstages * p.stage_bytes + p.slack_bytes + 8 * (2 * p.nstages + 2 * kFlatSlots + 2) + 64;
+    p.slack_bytes = (std::max(0, reach_rows * ROWB - p.stage_bytes) + 1023) & ~1023;
+    const int bar_bytes = 8 * (2 * 8 + 2 * kFlatSlots + 2) + 64;
+    const int fixed = 1024 + p.w_bytes + p.slack_bytes + kEpiBytes + bar_bytes;
+    p.nstages = std::min(p.chunks > 1 ? 4 : 6, (kSmemMax - fixed) / p.stage_bytes);
+    if (p.nstages < 2) return 0;
+    return fixed + p.nstages * p.stage_bytes;
+}
+
+template <int ROWB, int KH, int KW>
+static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, FlatParams& p, int smem, cudaStream_t stream) {
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
         FX_CUDA(e, cudaFuncSetAttribute(flat_conv_kernel<ROWB, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_done[e->device & 15] = true;
     }
+    p.tiles_per_img = (p.H + p.R - 1) / p.R;
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
     if (grid < p.ns) grid = p.ns;
@@ -315,6 +397,8 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
         p.P = kS2dW;
         p.R = 8;
         p.chunks = 1;
+        const int smem = plan_flat<32, 4, 4>(p);
+        if (!smem) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: stem tile does not fit in shared memory");
         p.x0 = 0;
         p.ypad = 0;
         const uint64_t dims[4] = {(uint64_t)kS2dC, (uint64_t)kS2dW, (uint64_t)kS2dH, (uint64_t)n};
@@ -329,11 +413,15 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
         if (rc != FX_OK) return rc;
         p.tiles_per_img = (p.H + p.R - 1) / p.R;
         p.n_work = n * p.tiles_per_img;
-        return launch_flat<32, 4, 4>(e, ma, mb, p, stream);
+        return launch_flat<32, 4, 4>(e, ma, mb, p, smem, stream);
     }
     p.P = g.win + 2;
-    p.R = std::max(1, std::min(g.hout, 256 / p.P));
     p.chunks = g.cin / 64;
+    // tallest tile (fewest halo re-reads) of at most two 128-pixel M-tiles that fits next to the weights
+    int smem = 0;
+    for (p.R = std::max(1, std::min(g.hout, 256 / p.P)); p.R >= 1; --p.R)
+        if ((smem = plan_flat<128, 3, 3>(p)) != 0) break;
+    if (!smem) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: layer does not fit in shared memory");
     p.x0 = -1;
     p.ypad = 1;
     const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
@@ -348,7 +436,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     if (rc != FX_OK) return rc;
     p.tiles_per_img = (p.H + p.R - 1) / p.R;
     p.n_work = n * p.tiles_per_img;
-    return launch_flat<128, 3, 3>(e, ma, mb, p, stream);
+    return launch_flat<128, 3, 3>(e, ma, mb, p, smem, stream);
 }
 
 }  // namespace fx
