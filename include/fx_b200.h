@@ -165,6 +165,11 @@ uint64_t fx_launch_count(fx_handle h);
 int fx_debug_conv(fx_handle h, const fx_conv_bn *layer, int hin, int win, const float *in_dev,
                   const float *residual_dev, int n, int relu, float *out_dev, void *stream);
 
+/* The fused stem: conv1 7x7/s2 + folded bn1 + ReLU + 3x3/s2/p1 max-pool in ONE tcgen05 kernel
+ * (torchvision/models/resnet.py:197-200,268-271).  in_dev fp32 NHWC [n][224][224][3] (normalised),
+ * out_dev fp32 NHWC [n][56][56][64].  BF16 engines only.  Synchronises `stream`. */
+int fx_debug_stem_pool(fx_handle h, const fx_conv_bn *layer, const float *in_dev, int n, float *out_dev, void *stream);
+
 /* Copy out the folded parameters of loaded layer `layer` as the kernels see them (fp32,
  * [cout][kh][kw][cin] order, bf16-rounded in BF16 precision) -- host pointers, either may be NULL. */
 int fx_debug_folded(fx_handle h, int layer, float *weight_host, float *bias_host);

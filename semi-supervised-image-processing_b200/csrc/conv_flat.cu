@@ -30,7 +30,8 @@ namespace fx {
 
 struct FlatParams {
     int P, W, H;           // smem row pitch (pixels), valid output width / height
-    int R;                 // output rows per work tile
+    int R;                 // output rows computed per work tile
+    int rstep, yfirst;     // tile t covers output rows [t*rstep + yfirst, +R)  (pooled stem: rstep 8, yfirst -1)
     int tiles_per_img, n_work;
     int chunks;            // 64-channel chunks of the input (1 for the stem)
     int ns;                // cout / 64 output-channel slices
@@ -45,6 +46,8 @@ struct FlatParams {
 
 constexpr int kFlatThreads = 384;
 constexpr int kFlatSlots = 8;  // 8 x 64 fp32 columns = the whole TMEM
+constexpr int kEpiBytes = 8 * 4096 + 256;      // epilogue staging (8 warps x 4 KB) + bias
+constexpr int kPoolRingBytes = 6 * 112 * 128;  // pooled stem: six conv rows of 112 px x 64 ch bf16
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -73,7 +76,10 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int ROWB, int KH, int KW>
+// POOL (stem only): the epilogue keeps the ReLU'd conv rows of the tile in a shared-memory ring and
+// writes the 3x3 / stride-2 / pad-1 max-pooled rows (torchvision/models/resnet.py:200) instead of the
+// conv output: work tile = 4 pooled rows = 9 conv rows (one recomputed), `out` is [n][H/2][W/2][64].
+template <int ROWB, int KH, int KW, bool POOL>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const FlatParams p) {
     constexpr int TAPS = KH * KW;
@@ -83,8 +89,8 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sW = sbase;
     const uint32_t sA = sbase + p.w_bytes;
-    const uint32_t stage0 = sA + p.nstages * p.stage_bytes + p.slack_bytes;  // 8 epilogue warps x 4 KB staging
-    const uint32_t bias0 = stage0 + 8 * 4096;                                // 64 fp32 bias values of this slice
+    const uint32_t stage0 = sA + p.nstages * p.stage_bytes + p.slack_bytes;  // epilogue staging / pooled-stem conv-row ring
+    const uint32_t bias0 = stage0 + (POOL ? kPoolRingBytes : 8 * 4096);      // 64 fp32 bias values of this slice
     const uint32_t bars = bias0 + 256;
     const uint32_t full0 = bars, empty0 = full0 + 8 * p.nstages, tfull0 = empty0 + 8 * p.nstages;
     const uint32_t tempty0 = tfull0 + 8 * kFlatSlots, wbar = tempty0 + 8 * kFlatSlots, tslot = wbar + 8;
@@ -105,7 +111,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int i = 0; i < kFlatSlots; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 128);
+            mbar_init(tempty0 + 8 * i, POOL ? 256 : 128);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
@@ -129,7 +135,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t stage = 0, phase = 0;
             for (int w = w_first; w < p.n_work; w += w_step) {
                 const int img = w / p.tiles_per_img;
-                const int y0 = (w - img * p.tiles_per_img) * p.R;
+                const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
                 for (int c = 0; c < p.chunks; ++c) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     mbar_expect_tx(full0 + 8 * stage, p.box_bytes);
@@ -152,7 +158,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t row_units = ROWB / 16;  // descriptor address units (16 B) per smem row
         for (int w = w_first; w < p.n_work; w += w_step) {
             const int img = w / p.tiles_per_img;
-            const int y0 = (w - img * p.tiles_per_img) * p.R;
+            const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             const int rows_valid = min(p.R, p.H - y0);
             const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
             for (int c = 0; c < p.chunks; ++c) {
@@ -192,6 +198,92 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             g_base += n_mt;
         }
+    } else if (warp >= 4 && POOL) {
+        // ===== pooled-stem epilogue: TMEM -> (+bias, ReLU) -> bf16 conv rows in a smem ring -> 3x3/s2 max -> NHWC =====
+        // All eight warps work on the same M-tile (two warps per TMEM lane quarter, 32 channels each).
+        // Conv row i of the tile lives in ring slot i % 6 as [x][64 ch] with the 16-byte chunk index
+        // XOR-swizzled by x.  Pooled row j of the tile needs conv rows 2j, 2j+1, 2j+2; it is emitted right
+        // after the M-tile that completes row 2j+2.  Conv row -1 (first band) is stored as zeros, which is
+        // neutral for a max over post-ReLU values (the reference pads with -inf).
+        constexpr int kRing = 6;
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int te = threadIdx.x - 128;  // 0..255
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        const int Wc = p.W, Wp = p.W >> 1, Hp = p.H >> 1;
+        const uint32_t row_bytes = (uint32_t)Wc * 128;
+        uint32_t g = 0;
+        for (int w = w_first; w < p.n_work; w += w_step) {
+            const int img = w / p.tiles_per_img;
+            const int t = w - img * p.tiles_per_img;
+            const int y0 = t * p.rstep + p.yfirst;
+            const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
+            for (int mt = 0; mt < n_mt; ++mt, ++g) {
+                const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+                mbar_wait(tfull0 + 8 * slot, use & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + slot * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * slot);
+                const int m = mt * 128 + q * 32 + lane;
+                const int i = m / p.P, x = m - i * p.P;
+                if (x < Wc && i < p.R) {
+                    const bool keep = y0 + i >= 0;
+                    const uint32_t srow = stage0 + (uint32_t)(i % kRing) * row_bytes + (uint32_t)x * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8 + 4);
+                        const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                            __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                            __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                            __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                        uint4 o;
+                        unsigned* ou = &o.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
+                            ou[k] = keep ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
+                        }
+                        sts128(srow + (((half * 4 + j) ^ (x & 7)) << 4), o);
+                    }
+                }
+                // which pooled row (if any) does this M-tile complete?  row 2j+2 ends at flat index (2j+2)*P + W - 1
+                int jdone = -1;
+                for (int j = 0; 2 * j + 2 < p.R; ++j)
+                    if (((2 * j + 2) * p.P + Wc - 1) / 128 == mt) jdone = j;
+                if (jdone >= 0) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    const int prow = (y0 + 1) / 2 + jdone;  // pooled row index in the image
+                    for (int item = te; item < Wp * 8; item += 256) {
+                        const int pw = item >> 3, c = item & 7;
+                        __nv_bfloat162 acc[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                        for (int di = 0; di < 3; ++di) {
+                            const uint32_t rbase = stage0 + (uint32_t)((2 * jdone + di) % kRing) * row_bytes;
+#pragma unroll
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const int xx = 2 * pw + dx;
+                                if (xx >= 0) {
+                                    const uint4 val = lds128(rbase + (uint32_t)xx * 128 + ((c ^ (xx & 7)) << 4));
+                                    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], hv[k]);
+                                }
+                            }
+                        }
+                        if (prow < Hp)
+                            *reinterpret_cast<uint4*>(p.out + (((size_t)img * Hp + prow) * Wp + pw) * 64 + c * 8) =
+                                *reinterpret_cast<const uint4*>(acc);
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 -> smem -> coalesced NHWC =====
         // Two groups of four warps take alternate M-tiles (g even / odd).  A warp owns 32 accumulator
@@ -211,7 +303,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t g = 0;
         auto tile_setup = [&]() {
             img = w / p.tiles_per_img;
-            y0 = (w - img * p.tiles_per_img) * p.R;
+            y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             rows_valid = min(p.R, p.H - y0);
             n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
         };
@@ -334,38 +426,36 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemMax = 227 * 1024;
 
-constexpr int kEpiBytes = 8 * 4096 + 256;  // epilogue staging + bias
 
 // Shared-memory plan for a given R; returns the total dynamic smem bytes, or 0 if it cannot work.
 template <int ROWB, int KH, int KW>
-static int plan_flat(FlatParams& p) {
+static int plan_flat(FlatParams& p, bool pool = false) {
     const int stage_rows = (p.R + KH - 1) * p.P;
     p.box_bytes = stage_rows * ROWB;
     p.stage_bytes = (p.box_bytes + 1023) & ~1023;
     p.w_bytes = (KH * KW * p.chunks * 64 * ROWB + 1023) & ~1023;
     const int n_mt_max = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
-    if (n_mt_max > kFlatSlots) return 0;
+    if (n_mt_max > kFlatSlots && p.chunks > 1) return 0;  // multi-chunk tiles keep all their accumulators live
     const int reach_rows = n_mt_max * 128 + (KH - 1) * p.P + (KW - 1);  // rows a (junk) view may touch
     p.slack_bytes = (std::max(0, reach_rows * ROWB - p.stage_bytes) + 1023) & ~1023;
     const int bar_bytes = 8 * (2 * 8 + 2 * kFlatSlots + 2) + 64;
-    const int fixed = 1024 + p.w_bytes + p.slack_bytes + kEpiBytes + bar_bytes;
+    const int fixed = 1024 + p.w_bytes + p.slack_bytes + (pool ? kPoolRingBytes + 256 : kEpiBytes) + bar_bytes;
     p.nstages = std::min(p.chunks > 1 ? 4 : 6, (kSmemMax - fixed) / p.stage_bytes);
     if (p.nstages < 2) return 0;
     return fixed + p.nstages * p.stage_bytes;
 }
 
-template <int ROWB, int KH, int KW>
+template <int ROWB, int KH, int KW, bool POOL>
 static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, FlatParams& p, int smem, cudaStream_t stream) {
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
-        FX_CUDA(e, cudaFuncSetAttribute(flat_conv_kernel<ROWB, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        FX_CUDA(e, cudaFuncSetAttribute(flat_conv_kernel<ROWB, KH, KW, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_done[e->device & 15] = true;
     }
-    p.tiles_per_img = (p.H + p.R - 1) / p.R;
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
     if (grid < p.ns) grid = p.ns;
-    flat_conv_kernel<ROWB, KH, KW><<<grid, kFlatThreads, smem, stream>>>(ma, mb, p);
+    flat_conv_kernel<ROWB, KH, KW, POOL><<<grid, kFlatThreads, smem, stream>>>(ma, mb, p);
     FX_LAUNCH_CHECK(e, "flat_conv_kernel");
     return FX_OK;
 }
@@ -378,7 +468,7 @@ bool flat_supported(const LayerGeom& g) {
 }
 
 int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, int n,
-              int relu, cudaStream_t stream) {
+              int relu, bool pool, cudaStream_t stream) {
     const LayerGeom& g = L.g;
     FlatParams p;
     std::memset(&p, 0, sizeof(p));
@@ -395,12 +485,23 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     if (g.cin == 3) {
         // stem in space-to-depth form: a 4x4 stride-1 conv over [115][116][16] (see engine.cu pack)
         p.P = kS2dW;
-        p.R = 8;
         p.chunks = 1;
-        const int smem = plan_flat<32, 4, 4>(p);
-        if (!smem) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: stem tile does not fit in shared memory");
         p.x0 = 0;
         p.ypad = 0;
+        if (pool) {
+            if (!relu || residual) return set_error(e, FX_ERR_INVALID, "flat_conv: the pooled stem is conv+bn+relu+maxpool");
+            p.R = 9;  // 4 pooled rows need conv rows 8t-1 .. 8t+7
+            p.rstep = 8;
+            p.yfirst = -1;
+            p.tiles_per_img = p.H / 8;
+        } else {
+            p.R = 8;
+            p.rstep = 8;
+            p.yfirst = 0;
+            p.tiles_per_img = (p.H + p.R - 1) / p.R;
+        }
+        const int smem = plan_flat<32, 4, 4>(p, pool);
+        if (!smem) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: stem tile does not fit in shared memory");
         const uint64_t dims[4] = {(uint64_t)kS2dC, (uint64_t)kS2dW, (uint64_t)kS2dH, (uint64_t)n};
         const uint64_t strides[3] = {(uint64_t)kS2dC * 2, (uint64_t)kS2dW * kS2dC * 2, (uint64_t)kS2dH * kS2dW * kS2dC * 2};
         const uint32_t box[4] = {(uint32_t)kS2dC, (uint32_t)p.P, (uint32_t)(p.R + 3), 1};
@@ -411,19 +512,23 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
         const uint32_t bbox[2] = {16, 64};
         rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stem B");
         if (rc != FX_OK) return rc;
-        p.tiles_per_img = (p.H + p.R - 1) / p.R;
         p.n_work = n * p.tiles_per_img;
-        return launch_flat<32, 4, 4>(e, ma, mb, p, smem, stream);
+        return pool ? launch_flat<32, 4, 4, true>(e, ma, mb, p, smem, stream) : launch_flat<32, 4, 4, false>(e, ma, mb, p, smem, stream);
     }
+    if (pool) return set_error(e, FX_ERR_INVALID, "flat_conv: only the stem has a fused max-pool");
     p.P = g.win + 2;
     p.chunks = g.cin / 64;
+    p.x0 = -1;
+    p.ypad = 1;
     // tallest tile (fewest halo re-reads) of at most two 128-pixel M-tiles that fits next to the weights
     int smem = 0;
     for (p.R = std::max(1, std::min(g.hout, 256 / p.P)); p.R >= 1; --p.R)
         if ((smem = plan_flat<128, 3, 3>(p)) != 0) break;
     if (!smem) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: layer does not fit in shared memory");
-    p.x0 = -1;
-    p.ypad = 1;
+    p.rstep = p.R;
+    p.yfirst = 0;
+    p.tiles_per_img = (p.H + p.R - 1) / p.R;
+    p.n_work = n * p.tiles_per_img;
     const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
     const uint32_t box[4] = {64, (uint32_t)p.P, (uint32_t)(p.R + 2), 1};
@@ -434,9 +539,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     const uint32_t bbox[2] = {64, 64};
     rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat B");
     if (rc != FX_OK) return rc;
-    p.tiles_per_img = (p.H + p.R - 1) / p.R;
-    p.n_work = n * p.tiles_per_img;
-    return launch_flat<128, 3, 3>(e, ma, mb, p, smem, stream);
+    return launch_flat<128, 3, 3, false>(e, ma, mb, p, smem, stream);
 }
 
 }  // namespace fx

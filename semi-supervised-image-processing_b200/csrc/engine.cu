@@ -126,7 +126,7 @@ static int run_conv(fx_engine* e, int li, const void* in, const void* residual, 
     if (e->precision == FX_PRECISION_BF16) {
         if (!out_f32 && flat_supported(L.g))
             return flat_conv(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
-                             static_cast<__nv_bfloat16*>(out), n, relu, stream);
+                             static_cast<__nv_bfloat16*>(out), n, relu, false, stream);
         return tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
                               static_cast<__nv_bfloat16*>(out), out_f32, n, relu, stream);
     }
@@ -144,8 +144,14 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
     void *A = e->act[0], *B = e->act[1], *C = e->act[2];
     int rc;
     // stem: conv1+bn1+relu -> maxpool            (resnet.py:268-271)
-    if ((rc = run_conv(e, 0, e->in0, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
-    if ((rc = maxpool_3x3s2(e, B, A, n, 112, 112, 64, bf16, stream)) != FX_OK) return rc;
+    if (bf16) {  // one kernel: the max-pool runs in the conv epilogue
+        if ((rc = flat_conv(e, e->layers[0], static_cast<const __nv_bfloat16*>(e->in0), nullptr, static_cast<__nv_bfloat16*>(A), n, 1,
+                            true, stream)) != FX_OK)
+            return rc;
+    } else {
+        if ((rc = run_conv(e, 0, e->in0, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
+        if ((rc = maxpool_3x3s2(e, B, A, n, 112, 112, 64, bf16, stream)) != FX_OK) return rc;
+    }
     // four stages of two BasicBlocks            (resnet.py:89-105, 273-276)
     int li = 1;
     for (int stage = 0; stage < 4; ++stage)
@@ -408,7 +414,7 @@ int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const 
         }
         if (residual_dev && (rc = f32_to_bf16(e, residual_dev, bres, out_count, stream)) != FX_OK) break;
         if (flat_supported(L.g))
-            rc = flat_conv(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, n, relu, stream);
+            rc = flat_conv(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, n, relu, false, stream);
         else
             rc = tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, nullptr, n, relu,
                                 stream);
@@ -418,6 +424,25 @@ int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const 
     cudaError_t serr = cudaStreamSynchronize(stream);  // the packed weights are freed below
     free_layer(L);
     if (rc == FX_OK && serr != cudaSuccess) rc = set_error(e, FX_ERR_CUDA, std::string("fx_debug_conv: ") + cudaGetErrorString(serr));
+    return rc;
+}
+
+int fx_debug_stem_pool(fx_handle e, const fx_conv_bn* layer, const float* in_dev, int n, float* out_dev, void* stream_) {
+    if (!e) return FX_ERR_INVALID;
+    if (!layer || !in_dev || !out_dev || n < 1 || n > e->max_batch) return set_error(e, FX_ERR_INVALID, "fx_debug_stem_pool: bad arguments");
+    if (e->precision != FX_PRECISION_BF16) return set_error(e, FX_ERR_UNSUPPORTED, "fx_debug_stem_pool: bf16 engines only");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PackedLayer L;
+    int rc = pack_layer(e, *layer, kCrop, kCrop, L);
+    if (rc == FX_OK && !flat_supported(L.g)) rc = set_error(e, FX_ERR_UNSUPPORTED, "fx_debug_stem_pool: not the 7x7/s2 stem");
+    if (rc == FX_OK) rc = pad_nhwc3_to_in0(e, in_dev, e->in0, true, n, stream);
+    __nv_bfloat16* bout = static_cast<__nv_bfloat16*>(e->act[0]);
+    if (rc == FX_OK) rc = flat_conv(e, L, static_cast<const __nv_bfloat16*>(e->in0), nullptr, bout, n, 1, true, stream);
+    if (rc == FX_OK) rc = bf16_to_f32(e, bout, out_dev, (size_t)n * 56 * 56 * 64, stream);
+    cudaError_t serr = cudaStreamSynchronize(stream);
+    free_layer(L);
+    if (rc == FX_OK && serr != cudaSuccess) rc = set_error(e, FX_ERR_CUDA, std::string("fx_debug_stem_pool: ") + cudaGetErrorString(serr));
     return rc;
 }
 

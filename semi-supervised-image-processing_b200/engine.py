@@ -220,6 +220,26 @@ class Engine:
                                             n, int(relu), out.data_ptr(), self._stream()))
         return out
 
+    def debug_stem_pool(self, weight: torch.Tensor, bn: Dict[str, torch.Tensor], x_nhwc: torch.Tensor) -> torch.Tensor:
+        """conv1+bn1+relu+maxpool through the fused stem kernel: fp32 NHWC [n,224,224,3] -> [n,56,56,64]."""
+        n = int(x_nhwc.shape[0])
+        keep = []
+
+        def fptr(t):
+            a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+        e = N.ConvBn()
+        e.weight = fptr(weight)
+        e.gamma, e.beta, e.mean, e.var = fptr(bn["weight"]), fptr(bn["bias"]), fptr(bn["running_mean"]), fptr(bn["running_var"])
+        e.eps = 1e-5
+        e.cout, e.cin, e.kh, e.kw, e.stride, e.pad = 64, 3, 7, 7, 2, 3
+        out = torch.empty((n, 56, 56, 64), dtype=torch.float32, device=self.device)
+        x = x_nhwc.contiguous()
+        self._check(self._lib.fx_debug_stem_pool(self._h, ctypes.byref(e), x.data_ptr(), n, out.data_ptr(), self._stream()))
+        return out
+
     def tma_probe(self, base: torch.Tensor, dims, strides_bytes, box, elem_strides, swizzle: int, coords, nbytes: int) -> torch.Tensor:
         out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         a = (ctypes.c_uint64 * 4)(*dims)

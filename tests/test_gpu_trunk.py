@@ -167,6 +167,19 @@ def test_conv_layer_bf16_tcgen05(eng_bf16, case):
     assert _rel(got, want) < 4e-3
 
 
+@pytest.mark.parametrize("n", [1, 5, 33])
+def test_fused_stem_conv_bn_relu_maxpool(eng_bf16, n):
+    w, bn, x = _case_tensors(3, 64, 7, 224, n, False, seed=99 + n)
+    got = eng_bf16.debug_stem_pool(w, bn, x.cuda()).cpu()
+    conv = _torch_conv(w, bn, x, 2, 3, None, True, round_bf16=True)
+    conv = _bf16r(conv)  # the kernel pools the bf16-rounded conv rows
+    want = F.max_pool2d(conv.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    err = (got - want).abs()
+    tol = want.abs() * 2.0 ** -7 + 2e-2 * want.abs().mean()
+    assert bool((err <= tol).all()), f"max err {err.max():.4g}, relL2 {_rel(got, want):.3e}"
+    assert _rel(got, want) < 4e-3
+
+
 @pytest.mark.parametrize("case", LAYER_CASES, ids=lambda c: "c%d-%d_k%d_s%d_h%d_n%d_r%d" % c[:7])
 def test_conv_layer_fp32(eng_fp32, case):
     cin, cout, k, stride, hin, n, residual, relu = case
