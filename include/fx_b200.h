@@ -188,6 +188,11 @@ int fx_debug_tma_probe(fx_handle h, const void *base_dev, const uint64_t *dims, 
 int fx_debug_umma_shift(fx_handle h, const void *a_dev, const void *b_dev, int kb_elems, int shift_rows,
                         int base_offset, float *out_dev);
 
+/* tcgen05.mma issue-rate microbenchmark: every SM issues iters x (rowb/32) MMAs M128 x n_cols x K16 from
+ * zeroed shared-memory tiles, the A view starting shift_rows (+ k*tap_stride_rows, k = 0..8) rows into
+ * the tile.  out_dev[sm_count] <- SM cycles per MMA.  Evidence for DESIGN.md's operand-fetch floors. */
+int fx_debug_mma_rate(fx_handle h, int n_cols, int rowb, int shift_rows, int tap_stride_rows, int iters, float *out_dev);
+
 /* Host-side integer pieces of the preprocess (no GPU needed): torchvision's Resize(256) output
  * size, CenterCrop(224)'s round-half-even offset, Pillow's fixed-point coefficient table
  * (returns taps per output sample; with NULL arrays only returns that count). */

@@ -24,7 +24,7 @@ RESIZE = 256
 EXPORTED_SYMBOLS = (
     "fx_version", "fx_abi_version", "fx_last_error", "fx_create", "fx_destroy", "fx_load_weights",
     "fx_preprocess_nchw_f32", "fx_preprocess", "fx_forward", "fx_stage_nchw_f32", "fx_embed", "fx_embed_host",
-    "fx_launch_count", "fx_debug_conv", "fx_debug_folded", "fx_debug_tma_probe", "fx_debug_umma_shift", "fx_debug_stem_pool",
+    "fx_launch_count", "fx_debug_conv", "fx_debug_folded", "fx_debug_tma_probe", "fx_debug_umma_shift", "fx_debug_stem_pool", "fx_debug_mma_rate",
     "fx_host_resized_size", "fx_host_crop_offset", "fx_host_coeffs",
 )
 
@@ -85,6 +85,7 @@ def lib() -> ctypes.CDLL:
     L.fx_debug_tma_probe.argtypes = [c_void_p, c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint32),
                                      POINTER(c_uint32), c_int, POINTER(c_int), c_int, c_void_p]
     L.fx_debug_stem_pool.argtypes = [c_void_p, POINTER(ConvBn), c_void_p, c_int, c_void_p, c_void_p]
+    L.fx_debug_mma_rate.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     L.fx_debug_umma_shift.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.fx_host_resized_size.argtypes = [c_int, c_int, POINTER(c_int), POINTER(c_int)]
     L.fx_host_crop_offset.argtypes = [c_int]

@@ -468,6 +468,101 @@ int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uin
     return FX_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark (inspection entry point): every CTA issues `iters` rounds of
+// (rowb/32) back-to-back tcgen05.mma M128 x N x K16 from fixed shared-memory tiles whose A view starts
+// `shift_rows` rows into the tile and moves by `tap_stride_rows` between rounds (9 positions, like
+// filter taps).  Reports SM cycles per MMA -> the operand-fetch floor for each (N, swizzle, shift).
+// ------------------------------------------------------------------------------------------
+template <int ROWB, int NACC>
+__global__ void __launch_bounds__(128, 1)
+mma_rate_kernel(int n_cols, int shift_rows, int tap_stride_rows, int iters, float* cycles_per_mma) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = sbase, sB = sbase + 96 * 1024;
+    const uint32_t bar = sB + 64 * 1024, tslot = bar + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x * 16; i < 160 * 1024; i += blockDim.x * 16)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(sbase + i), "r"(0u) : "memory");
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tslot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+    if (warp == 0) {
+        constexpr int KSTEPS = ROWB / 32;
+        constexpr uint64_t hi = make_smem_desc_rowb<ROWB>(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a0 = (sA >> 4) + (uint32_t)shift_rows * (ROWB / 16);
+        const uint32_t astep = (uint32_t)tap_stride_rows * (ROWB / 16);
+        const uint32_t b0 = sB >> 4;
+        const uint32_t bstep = (uint32_t)((n_cols * ROWB) >> 4) * (n_cols * ROWB * 8 <= 64 * 1024 ? 1u : 0u);
+        long long t0 = 0, t1 = 0;
+        const int rounds = iters / 8;
+        if (elect_one_sync()) {
+            t0 = clock64();
+            for (int it = 0; it < rounds; ++it) {
+#pragma unroll
+                for (int tap = 0; tap < 8; ++tap) {
+                    const uint32_t d = tmem_base + (uint32_t)(tap % NACC) * (uint32_t)n_cols;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k)
+                        umma_bf16(d, hi | (uint64_t)(a0 + tap * astep + 2 * k), hi | (uint64_t)(b0 + tap * bstep + 2 * k), idesc, 1);
+                }
+            }
+            umma_commit(bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+        t1 = clock64();
+        if (elect_one_sync()) cycles_per_mma[blockIdx.x] = (float)(t1 - t0) / (float)(rounds * 8 * KSTEPS);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int ROWB>
+static void launch_mma_rate(int nacc, int grid, int smem, cudaStream_t stream, int n_cols, int shift_rows, int ts, int iters, float* out) {
+    cudaFuncSetAttribute(mma_rate_kernel<ROWB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mma_rate_kernel<ROWB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mma_rate_kernel<ROWB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (nacc >= 4)
+        mma_rate_kernel<ROWB, 4><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, out);
+    else if (nacc >= 2)
+        mma_rate_kernel<ROWB, 2><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, out);
+    else
+        mma_rate_kernel<ROWB, 1><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, out);
+}
+
+// tap_stride_rows >= 1000 encodes "round-robin over (tap_stride_rows / 1000) accumulators".
+int tc_mma_rate(fx_engine* e, int n_cols, int rowb, int shift_rows, int tap_stride_rows, int iters, float* out_dev, cudaStream_t stream) {
+    const int nacc = std::max(1, tap_stride_rows / 1000);
+    tap_stride_rows %= 1000;
+    if ((n_cols != 64 && n_cols != 128 && n_cols != 256) || (rowb != 128 && rowb != 64 && rowb != 32))
+        return set_error(e, FX_ERR_INVALID, "mma_rate: N must be 64/128/256 and rowb 128/64/32");
+    if (shift_rows < 0 || tap_stride_rows < 0 || (shift_rows + 7 * tap_stride_rows + 128) * rowb > 96 * 1024 || nacc * n_cols > 512)
+        return set_error(e, FX_ERR_INVALID, "mma_rate: views leave the shared-memory tile");
+    const int smem = 1024 + 160 * 1024 + 64;
+    if (rowb == 128)
+        launch_mma_rate<128>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, out_dev);
+    else if (rowb == 64)
+        launch_mma_rate<64>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, out_dev);
+    else
+        launch_mma_rate<32>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, out_dev);
+    FX_LAUNCH_CHECK(e, "mma_rate_kernel");
+    return FX_OK;
+}
+
 // Test hook behind fx_debug_umma_shift (engine.cu).
 int tc_umma_shift_probe(fx_engine* e, const void* a_dev, const void* b_dev, int kb_elems, int shift_rows, int base_offset,
                         float* out_dev, cudaStream_t stream) {

@@ -21,6 +21,8 @@ int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uin
 int tc_umma_shift_probe(fx_engine* e, const void* a_dev, const void* b_dev, int kb_elems, int shift_rows, int base_offset,
                         float* out_dev, cudaStream_t stream);
 
+int tc_mma_rate(fx_engine* e, int n_cols, int rowb, int shift_rows, int tap_stride_rows, int iters, float* out_dev, cudaStream_t stream);
+
 static std::mutex g_err_mutex;
 static std::string g_create_error;
 
@@ -471,6 +473,16 @@ int fx_debug_umma_shift(fx_handle e, const void* a_dev, const void* b_dev, int k
     if (!a_dev || !b_dev || !out_dev) return set_error(e, FX_ERR_INVALID, "fx_debug_umma_shift: null pointer");
     FX_CUDA(e, cudaSetDevice(e->device));
     int rc = tc_umma_shift_probe(e, a_dev, b_dev, kb_elems, shift_rows, base_offset, out_dev, nullptr);
+    if (rc != FX_OK) return rc;
+    FX_CUDA(e, cudaDeviceSynchronize());
+    return FX_OK;
+}
+
+int fx_debug_mma_rate(fx_handle e, int n_cols, int rowb, int shift_rows, int tap_stride_rows, int iters, float* out_dev) {
+    if (!e) return FX_ERR_INVALID;
+    if (!out_dev || iters < 1) return set_error(e, FX_ERR_INVALID, "fx_debug_mma_rate: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    int rc = tc_mma_rate(e, n_cols, rowb, shift_rows, tap_stride_rows, iters, out_dev, nullptr);
     if (rc != FX_OK) return rc;
     FX_CUDA(e, cudaDeviceSynchronize());
     return FX_OK;

@@ -240,6 +240,13 @@ class Engine:
         self._check(self._lib.fx_debug_stem_pool(self._h, ctypes.byref(e), x.data_ptr(), n, out.data_ptr(), self._stream()))
         return out
 
+    def mma_rate(self, n_cols: int, rowb: int, shift_rows: int = 0, tap_stride_rows: int = 0, iters: int = 2000) -> torch.Tensor:
+        """SM cycles per tcgen05.mma (M128 x n_cols x K16) on every SM; see fx_debug_mma_rate."""
+        out = torch.zeros(256, dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self._check(self._lib.fx_debug_mma_rate(self._h, n_cols, rowb, shift_rows, tap_stride_rows, iters, out.data_ptr()))
+        return out
+
     def tma_probe(self, base: torch.Tensor, dims, strides_bytes, box, elem_strides, swizzle: int, coords, nbytes: int) -> torch.Tensor:
         out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         a = (ctypes.c_uint64 * 4)(*dims)
