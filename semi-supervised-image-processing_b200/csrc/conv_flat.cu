@@ -47,7 +47,7 @@ struct FlatParams {
 constexpr int kFlatThreads = 384;
 constexpr int kFlatSlots = 8;  // 8 x 64 fp32 columns = the whole TMEM
 constexpr int kEpiBytes = 8 * 4096 + 256;      // epilogue staging (8 warps x 4 KB) + bias
-constexpr int kPoolRingBytes = 6 * 112 * 128;  // pooled stem: six conv rows of 112 px x 64 ch bf16
+constexpr int kPoolRingBytes = 6 * 56 * 128 + 2048;  // pooled stem: six half-width conv rows (56 px x 64 ch bf16) + mailboxes
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -199,19 +199,24 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             g_base += n_mt;
         }
     } else if (warp >= 4 && POOL) {
-        // ===== pooled-stem epilogue: TMEM -> (+bias, ReLU) -> bf16 conv rows in a smem ring -> 3x3/s2 max -> NHWC =====
-        // All eight warps work on the same M-tile (two warps per TMEM lane quarter, 32 channels each).
-        // Conv row i of the tile lives in ring slot i % 6 as [x][64 ch] with the 16-byte chunk index
-        // XOR-swizzled by x.  Pooled row j of the tile needs conv rows 2j, 2j+1, 2j+2; it is emitted right
-        // after the M-tile that completes row 2j+2.  Conv row -1 (first band) is stored as zeros, which is
-        // neutral for a max over post-ReLU values (the reference pads with -inf).
+        // ===== pooled-stem epilogue: TMEM -> (+bias, ReLU) -> bf16 -> horizontal 3-max in registers ->
+        //       half-width rows in a smem ring -> vertical 3-max -> NHWC [n][56][56][64] =====
+        // All eight warps work on the same M-tile (two warps per TMEM lane quarter, 32 channels each);
+        // a lane owns conv pixel x of conv row i (m = i*P + x, lanes are consecutive x).  The horizontal
+        // max over x-1, x, x+1 (kept for even x = 2*pw) comes from the neighbouring lanes by shuffle; the
+        // neighbour of lane 0 lives in the previous warp / M-tile and arrives through a 64-byte mailbox.
+        // Ring slot i % 6 holds the horizontally pooled conv row i as [pw][64 ch] (16-byte chunk index
+        // XOR-swizzled by pw).  Pooled row j of the tile = max over ring rows 2j, 2j+1, 2j+2, emitted
+        // right after the M-tile that completes row 2j+2.  Conv row -1 (first band) and the junk columns
+        // x >= W are zeros: neutral for a max over post-ReLU values (the reference pads with -inf).
         constexpr int kRing = 6;
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int te = threadIdx.x - 128;  // 0..255
         const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         const int Wc = p.W, Wp = p.W >> 1, Hp = p.H >> 1;
-        const uint32_t row_bytes = (uint32_t)Wc * 128;
+        const uint32_t row_bytes = (uint32_t)Wp * 128;
+        const uint32_t mbox0 = stage0 + kRing * row_bytes;  // [3][4 quarters][2 halves][64 B]
         uint32_t g = 0;
         for (int w = w_first; w < p.n_work; w += w_step) {
             const int img = w / p.tiles_per_img;
@@ -229,58 +234,82 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_arrive(tempty0 + 8 * slot);
                 const int m = mt * 128 + q * 32 + lane;
                 const int i = m / p.P, x = m - i * p.P;
-                if (x < Wc && i < p.R) {
-                    const bool keep = y0 + i >= 0;
-                    const uint32_t srow = stage0 + (uint32_t)(i % kRing) * row_bytes + (uint32_t)x * 128;
+                const bool live = x < Wc && i < p.R && y0 + i >= 0;
+                unsigned c[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8 + 4);
-                        const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
-                                            __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
-                                            __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
-                                            __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
-                        uint4 o;
-                        unsigned* ou = &o.x;
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8 + 4);
+                    const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                        __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                        __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                        __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
-                            ou[k] = keep ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
-                        }
-                        sts128(srow + (((half * 4 + j) ^ (x & 7)) << 4), o);
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
+                        c[4 * j + k] = live ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
                     }
+                }
+                // hand the last lane's pixel to the next warp / M-tile
+                const uint32_t mb_mine = mbox0 + (((g % 3) * 4 + q) * 2 + half) * 64;
+                if (lane == 31) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sts128(mb_mine + j * 16, make_uint4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]));
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                unsigned hm[16];
+                {
+                    const uint32_t mb_left = q > 0 ? mb_mine - 128 : mbox0 + ((((g + 2) % 3) * 4 + 3) * 2 + half) * 64;
+                    uint4 lv[4];
+                    const bool need_box = lane == 0 && x > 0 && (q > 0 || mt > 0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) lv[j] = need_box ? lds128(mb_left + j * 16) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        unsigned l = __shfl_up_sync(0xffffffffu, c[k], 1);
+                        const unsigned r = __shfl_down_sync(0xffffffffu, c[k], 1);
+                        if (lane == 0) l = (&lv[k >> 2].x)[k & 3];
+                        if (x == 0) l = 0u;  // no pixel to the left of the row start (the junk column of the previous row is zero anyway)
+                        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&l), *reinterpret_cast<const __nv_bfloat162*>(&c[k]));
+                        const __nv_bfloat162 bb = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&r));
+                        hm[k] = *reinterpret_cast<const unsigned*>(&bb);
+                    }
+                }
+                if (x < Wc && i < p.R && (x & 1) == 0) {
+                    const int pw = x >> 1;
+                    const uint32_t srow = stage0 + (uint32_t)(i % kRing) * row_bytes + (uint32_t)pw * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        sts128(srow + (((half * 4 + j) ^ (pw & 7)) << 4), make_uint4(hm[4 * j], hm[4 * j + 1], hm[4 * j + 2], hm[4 * j + 3]));
                 }
                 // which pooled row (if any) does this M-tile complete?  row 2j+2 ends at flat index (2j+2)*P + W - 1
                 int jdone = -1;
                 for (int j = 0; 2 * j + 2 < p.R; ++j)
                     if (((2 * j + 2) * p.P + Wc - 1) / 128 == mt) jdone = j;
                 if (jdone >= 0) {
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
                     const int prow = (y0 + 1) / 2 + jdone;  // pooled row index in the image
+                    const uint32_t r0 = stage0 + (uint32_t)((2 * jdone) % kRing) * row_bytes;
+                    const uint32_t r1 = stage0 + (uint32_t)((2 * jdone + 1) % kRing) * row_bytes;
+                    const uint32_t r2 = stage0 + (uint32_t)((2 * jdone + 2) % kRing) * row_bytes;
                     for (int item = te; item < Wp * 8; item += 256) {
-                        const int pw = item >> 3, c = item & 7;
-                        __nv_bfloat162 acc[4];
+                        const int pw = item >> 3, ch = item & 7;
+                        const uint32_t off = (uint32_t)pw * 128 + ((ch ^ (pw & 7)) << 4);
+                        const uint4 a = lds128(r0 + off), bq = lds128(r1 + off), cq = lds128(r2 + off);
+                        uint4 o;
+                        const unsigned* au = &a.x;
+                        const unsigned* bu = &bq.x;
+                        const unsigned* cu = &cq.x;
+                        unsigned* ou = &o.x;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[k] = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-                        for (int di = 0; di < 3; ++di) {
-                            const uint32_t rbase = stage0 + (uint32_t)((2 * jdone + di) % kRing) * row_bytes;
-#pragma unroll
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const int xx = 2 * pw + dx;
-                                if (xx >= 0) {
-                                    const uint4 val = lds128(rbase + (uint32_t)xx * 128 + ((c ^ (xx & 7)) << 4));
-                                    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], hv[k]);
-                                }
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 mx = __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&au[k]),
+                                                                      *reinterpret_cast<const __nv_bfloat162*>(&bu[k])),
+                                                              *reinterpret_cast<const __nv_bfloat162*>(&cu[k]));
+                            ou[k] = *reinterpret_cast<const unsigned*>(&mx);
                         }
-                        if (prow < Hp)
-                            *reinterpret_cast<uint4*>(p.out + (((size_t)img * Hp + prow) * Wp + pw) * 64 + c * 8) =
-                                *reinterpret_cast<const uint4*>(acc);
+                        if (prow < Hp) *reinterpret_cast<uint4*>(p.out + (((size_t)img * Hp + prow) * Wp + pw) * 64 + ch * 8) = o;
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             }
         }
