@@ -150,6 +150,17 @@ int fx_embed(fx_handle h, const uint8_t *src_dev, const fx_image_desc *descs_hos
 int fx_embed_host(fx_handle h, const uint8_t *src_host, size_t total_bytes, const fx_image_desc *descs_host,
                   int n, float *emb_host);
 
+/*
+ * The same, pipelined: two slots (0, 1).  fx_embed_host_async queues the H2D copy of the batch on the
+ * library's copy stream, the kernels and the D2H of the embeddings on its compute stream, and returns;
+ * fx_embed_host_wait(slot) blocks until that slot's embeddings are in emb_host.  Alternating the slots
+ * overlaps the copy of batch i+1 with the kernels of batch i.  src_host / emb_host must stay valid (and
+ * should be pinned) until the wait returns.  fx_embed_host == async on slot 0 + wait.
+ */
+int fx_embed_host_async(fx_handle h, int slot, const uint8_t *src_host, size_t total_bytes,
+                        const fx_image_desc *descs_host, int n, float *emb_host);
+int fx_embed_host_wait(fx_handle h, int slot);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 uint64_t fx_launch_count(fx_handle h);
 

@@ -203,9 +203,15 @@ void fx_destroy(fx_handle e) {
     cudaFree(e->in0);
     for (auto& a : e->act) cudaFree(a);
     cudaFree(e->final_f32);
-    cudaFree(e->h2d_dev);
+    for (auto& hs : e->slots) {
+        cudaFree(hs.src_dev);
+        cudaFree(hs.emb_dev);
+        if (hs.copied) cudaEventDestroy(hs.copied);
+        if (hs.done) cudaEventDestroy(hs.done);
+    }
     cudaFree(e->emb_dev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
 }
 
@@ -262,6 +268,8 @@ int fx_create(fx_handle* out, int device, int max_batch, int precision) {
     // the pad region of the staging tensor is conv zero padding and is never written again
     if ((err = cudaMemset(e->in0, 0, in0_bytes)) != cudaSuccess) return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
     if ((err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
+    if ((err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
     if ((rc = preprocess_init(e)) != FX_OK) return fail(rc);
     if ((rc = tc_init(e)) != FX_OK) return fail(rc);
@@ -335,34 +343,66 @@ int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, in
     return fx_forward(e, n, emb_dev, stream);
 }
 
-int fx_embed_host(fx_handle e, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n, float* emb_host) {
+// Host-buffer path, pipelined over two slots: the H2D copy of one batch (copy stream) overlaps the
+// kernels of the previous one (compute stream); the D2H of the embeddings follows the kernels.
+int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
+                        float* emb_host) {
     if (!e) return FX_ERR_INVALID;
-    if (n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || !emb_host)))
-        return set_error(e, FX_ERR_INVALID, "fx_embed_host: bad arguments");
-    if (n == 0) return FX_OK;
+    if (slot < 0 || slot > 1 || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || !emb_host)))
+        return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: bad arguments");
     for (int i = 0; i < n; ++i) {
         const size_t need = descs[i].offset + (size_t)descs[i].height * descs[i].width * descs[i].channels;
         if (descs[i].height < 1 || descs[i].width < 1 || need > total_bytes)
-            return set_error(e, FX_ERR_INVALID, "fx_embed_host: image " + std::to_string(i) + " lies outside the buffer");
+            return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: image " + std::to_string(i) + " lies outside the buffer");
     }
     FX_CUDA(e, cudaSetDevice(e->device));
-    if (total_bytes > e->h2d_cap) {
-        FX_CUDA(e, cudaStreamSynchronize(e->own_stream));
-        cudaFree(e->h2d_dev);
-        e->h2d_dev = nullptr;
-        e->h2d_cap = 0;
-        const size_t cap = total_bytes + total_bytes / 4 + 256;
-        cudaError_t a = cudaMalloc(&e->h2d_dev, cap);
-        if (a != cudaSuccess) return set_error(e, FX_ERR_NOMEM, std::string("cudaMalloc(h2d staging): ") + cudaGetErrorString(a));
-        e->h2d_cap = cap;
+    fx_engine::HostSlot& hs = e->slots[slot];
+    if (!hs.copied) {
+        FX_CUDA(e, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
+        FX_CUDA(e, cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
+        FX_CUDA(e, cudaMalloc(&hs.emb_dev, sizeof(float) * kEmbed * e->max_batch));
     }
+    if (hs.busy) {  // the caller reuses a slot it never waited on: finish it first
+        FX_CUDA(e, cudaEventSynchronize(hs.done));
+        hs.busy = false;
+    }
+    if (n == 0) return FX_OK;
+    if (total_bytes > hs.cap) {
+        cudaFree(hs.src_dev);
+        hs.src_dev = nullptr;
+        hs.cap = 0;
+        const size_t cap = total_bytes + total_bytes / 4 + 256;
+        cudaError_t a = cudaMalloc(&hs.src_dev, cap);
+        if (a != cudaSuccess) return set_error(e, FX_ERR_NOMEM, std::string("cudaMalloc(h2d staging): ") + cudaGetErrorString(a));
+        hs.cap = cap;
+    }
+    FX_CUDA(e, cudaMemcpyAsync(hs.src_dev, src_host, total_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
     cudaStream_t s = e->own_stream;
-    FX_CUDA(e, cudaMemcpyAsync(e->h2d_dev, src_host, total_bytes, cudaMemcpyHostToDevice, s));
-    int rc = fx_embed(e, e->h2d_dev, descs, n, e->emb_dev, s);
+    FX_CUDA(e, cudaStreamWaitEvent(s, hs.copied, 0));
+    int rc = fx_embed(e, hs.src_dev, descs, n, hs.emb_dev, s);
     if (rc != FX_OK) return rc;
-    FX_CUDA(e, cudaMemcpyAsync(emb_host, e->emb_dev, sizeof(float) * kEmbed * n, cudaMemcpyDeviceToHost, s));
-    FX_CUDA(e, cudaStreamSynchronize(s));
+    FX_CUDA(e, cudaMemcpyAsync(emb_host, hs.emb_dev, sizeof(float) * kEmbed * n, cudaMemcpyDeviceToHost, s));
+    FX_CUDA(e, cudaEventRecord(hs.done, s));
+    hs.busy = true;
     return FX_OK;
+}
+
+int fx_embed_host_wait(fx_handle e, int slot) {
+    if (!e) return FX_ERR_INVALID;
+    if (slot < 0 || slot > 1) return set_error(e, FX_ERR_INVALID, "fx_embed_host_wait: bad slot");
+    fx_engine::HostSlot& hs = e->slots[slot];
+    if (!hs.busy) return FX_OK;
+    FX_CUDA(e, cudaSetDevice(e->device));
+    FX_CUDA(e, cudaEventSynchronize(hs.done));
+    hs.busy = false;
+    return FX_OK;
+}
+
+int fx_embed_host(fx_handle e, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n, float* emb_host) {
+    int rc = fx_embed_host_async(e, 0, src_host, total_bytes, descs, n, emb_host);
+    if (rc != FX_OK) return rc;
+    return fx_embed_host_wait(e, 0);
 }
 
 uint64_t fx_launch_count(fx_handle e) { return e ? e->launches : 0; }

@@ -111,11 +111,17 @@ struct fx_engine {
     size_t act_bytes = 0;
     void* tc_state = nullptr;  // tcgen05 path: tensor maps etc. (conv_tc.cu)
 
-    // host staging for fx_embed_host
-    uint8_t* h2d_dev = nullptr;
-    size_t h2d_cap = 0;
+    // host-buffer path (fx_embed_host*): two pipelined slots
+    struct HostSlot {
+        uint8_t* src_dev = nullptr;
+        size_t cap = 0;
+        float* emb_dev = nullptr;
+        cudaEvent_t copied = nullptr, done = nullptr;
+        bool busy = false;
+    } slots[2];
     float* emb_dev = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr;   // kernels + D2H of the host-buffer path
+    cudaStream_t copy_stream = nullptr;  // H2D of the host-buffer path
 };
 
 namespace fx {

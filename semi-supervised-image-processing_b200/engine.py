@@ -76,7 +76,7 @@ class Engine:
         self._h = ctypes.c_void_p()
         N.check(self._lib.fx_create(ctypes.byref(self._h), self.device_index, self.max_batch, _PRECISIONS[precision]))
         self.device = torch.device("cuda", self.device_index)
-        self._keep = None
+        self._slot_keep = {}
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self) -> None:
@@ -181,6 +181,17 @@ class Engine:
         dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
         self._check(self._lib.fx_embed_host(self._h, src_ptr, total_bytes, descs, n, dst_ptr))
         return out
+
+    def embed_host_async(self, slot: int, packed_host, descs, n: int, total_bytes: int, out) -> None:
+        """Queue one host batch on pipeline slot 0/1 (H2D overlaps the previous batch's kernels); pair with embed_host_wait."""
+        src_ptr = packed_host.data_ptr() if isinstance(packed_host, torch.Tensor) else packed_host.ctypes.data
+        dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        self._slot_keep[slot] = (packed_host, descs, out)  # the library reads/writes them until the wait
+        self._check(self._lib.fx_embed_host_async(self._h, slot, src_ptr, total_bytes, descs, n, dst_ptr))
+
+    def embed_host_wait(self, slot: int) -> None:
+        self._check(self._lib.fx_embed_host_wait(self._h, slot))
+        self._slot_keep.pop(slot, None)
 
     def embed_images(self, images: Sequence[np.ndarray]) -> np.ndarray:
         """Convenience: list of decoded HWC uint8 arrays -> [n,512] (chunks of max_batch)."""

@@ -308,17 +308,38 @@ def _load_file(path: Path):
 
 
 def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int):
-    """Single-GPU pass over `records`: device embeddings + bookkeeping."""
+    """Single-GPU pass over `records`: embeddings + bookkeeping.
+
+    Two pipeline slots (fx_embed_host_async): while the GPU works on batch i, the host decodes batch i+1
+    into the other pinned staging buffer and its H2D copy overlaps the kernels of batch i.
+    """
     kept: List[int] = []
     failures: List[Path] = []
     times: List[float] = []
-    blocks: List[torch.Tensor] = []
+    blocks: List[np.ndarray] = []
     threads = int(os.environ.get(DECODE_THREADS_ENV, "0")) or min(32, (os.cpu_count() or 8))
-    staging: Optional[torch.Tensor] = None
+    staging: List[Optional[torch.Tensor]] = [None, None]
+    outs = [torch.empty((batch_size, 512), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending: List[Optional[Tuple[List[int], int]]] = [None, None]  # per slot: (record indices, n)
+    t_last = time.perf_counter()
+
+    def finish(slot: int) -> None:
+        nonlocal t_last
+        if pending[slot] is None:
+            return
+        ok, n = pending[slot]
+        eng.embed_host_wait(slot)
+        blocks.append(outs[slot][:n].numpy().copy())
+        kept.extend(ok)
+        now = time.perf_counter()
+        times.extend([(now - t_last) / n] * n)  # batch wall time / successes, as src/feature_extraction.py:297-300
+        t_last = now
+        pending[slot] = None
+
     with ThreadPoolExecutor(max_workers=threads) as pool, torch.cuda.device(eng.device):
+        slot = 0
         for lo in range(0, len(records), batch_size):
             chunk = records[lo : lo + batch_size]
-            t0 = time.perf_counter()
             decoded = list(pool.map(_load_file, [r.absolute_path for r in chunk]))
             arrays, ok = [], []
             for off, (rec, item) in enumerate(zip(chunk, decoded)):
@@ -330,19 +351,21 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
                     ok.append(lo + off)
             if not arrays:
                 continue
+            finish(slot)  # the slot's buffers are free again once its previous batch is out
             need = sum((a.size + 255) // 256 * 256 for a in arrays)
-            if staging is None or staging.numel() < need:
-                staging = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8).pin_memory()
-            buf, descs, total = pack_images(arrays, out=staging.numpy())
-            dev = staging[:total].to(eng.device, non_blocking=True)
-            emb = eng.embed_device(dev, descs, len(arrays))
-            blocks.append(emb)
-            torch.cuda.current_stream().synchronize()  # per-batch latency, like the reference's .cpu()
-            kept.extend(ok)
-            dt = time.perf_counter() - t0
-            times.extend([dt / len(ok)] * len(ok))
-    local = torch.cat(blocks, dim=0) if blocks else torch.empty((0, 512), dtype=torch.float32, device=eng.device)
-    return local, kept, failures, times
+            if staging[slot] is None or staging[slot].numel() < need:
+                staging[slot] = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8).pin_memory()
+            _, descs, total = pack_images(arrays, out=staging[slot].numpy())
+            eng.embed_host_async(slot, staging[slot], descs, len(arrays), total, outs[slot])
+            pending[slot] = (ok, len(arrays))
+            slot ^= 1
+        finish(slot)
+        finish(slot ^ 1)
+    order = np.argsort(np.asarray(kept, dtype=np.int64), kind="stable") if kept else np.zeros(0, np.int64)
+    local = np.concatenate(blocks, axis=0)[order] if blocks else np.empty((0, 512), np.float32)
+    kept = [kept[i] for i in order]
+    times = [times[i] for i in order]
+    return torch.from_numpy(local), kept, failures, times
 
 
 def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_size: int = BATCH_SIZE) -> ExtractionResults:
@@ -360,7 +383,7 @@ def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_s
     local, kept, failures, times = _extract_local(records[lo:hi], eng, batch_size)
     kept = [lo + k for k in kept]
     if distributed:
-        full = fxdist.allgather_rows(local)
+        full = fxdist.allgather_rows(local.to(eng.device))
         meta = fxdist.allgather_objects((kept, failures, times))
         kept = fxdist.concat_in_rank_order([m[0] for m in meta])
         failures = fxdist.concat_in_rank_order([m[1] for m in meta])

@@ -1,0 +1,132 @@
+"""The drop-in module (ssip_b200.feature_extraction) on a GPU: same entry points, bookkeeping, error
+behaviour and artifacts as src/feature_extraction.py (reference lines cited per test), results within
+BASELINE.json's tolerance of the oracle port run on the same files."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import reference_path as rp
+from ssip_b200 import feature_extraction as fx
+from ssip_b200 import synthetic
+from ssip_b200.engine import pack_images
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dataset(tmp_path_factory):
+    root = tmp_path_factory.mktemp("data")
+    imgs = synthetic.ragged_images([(224, 224)] * 10 + [(300, 500), (512, 512), (640, 480)], seed=31)
+    imgs += list(synthetic.mri_like_images(3, 512, seed=5))
+    synthetic.write_png_dataset(root, imgs, n_labeled=6)
+    (root / "sans_label" / "zz_broken.png").write_bytes(b"this is not an image")  # decode failure (:281-284)
+    return root, imgs
+
+
+@pytest.fixture(scope="module", autouse=True)
+def weights_env():
+    old = os.environ.get(fx.WEIGHTS_ENV)
+    os.environ[fx.WEIGHTS_ENV] = "random-bn:1234"
+    yield
+    if old is None:
+        os.environ.pop(fx.WEIGHTS_ENV, None)
+    else:
+        os.environ[fx.WEIGHTS_ENV] = old
+
+
+def _oracle(records, batch_size):
+    port = [rp.PortRecord(r.absolute_path, r.relative_path, r.bucket, r.label) for r in records]
+    # fx._seeded_backbone(1234, True) uses BN seed 1235 == rp.BN_SEED
+    return rp.port_extract_embeddings(port, torch.device("cpu"), batch_size=batch_size, seed=1234, randomize_bn=True)
+
+
+def test_extract_embeddings_matches_oracle_and_keeps_bookkeeping(dataset):
+    root, imgs = dataset
+    records = fx.discover_image_records(root)  # :125-181
+    assert len(records) == len(imgs) + 1
+    res = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=5)  # ragged last batch, 2 slots in flight
+    ref = _oracle(records, 5)
+    assert [r.relative_path for r in res.records] == [r.relative_path for r in ref.records]  # order, failures removed (:295)
+    assert [p.name for p in res.failures] == ["zz_broken.png"] == [p.name for p in ref.failures]
+    assert res.embeddings.dtype == np.float32 and res.embeddings.shape == (len(imgs), 512)
+    assert len(res.per_file_times) == len(imgs) and all(t > 0 for t in res.per_file_times)  # :297-300
+    rel = np.linalg.norm(res.embeddings - ref.embeddings, axis=1) / np.linalg.norm(ref.embeddings, axis=1)
+    cos = (res.embeddings * ref.embeddings).sum(1) / (np.linalg.norm(res.embeddings, axis=1) * np.linalg.norm(ref.embeddings, axis=1))
+    assert rel.max() <= 1e-2 and cos.min() >= 0.999, (rel.max(), cos.min())
+    # batch size must not change a single bit (determinism contract)
+    res2 = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=16)
+    assert np.array_equal(res.embeddings, res2.embeddings)
+
+
+def test_main_writes_the_five_artifacts(dataset, tmp_path, monkeypatch):
+    root, imgs = dataset
+    monkeypatch.chdir(tmp_path)  # output paths are CWD-relative constants (:53-62)
+    fx.main(["--data-dir", str(root), "--device", "cuda:0", "--batch-size", "8"])
+    emb = np.load(tmp_path / "outputs/features/embeddings.npy")
+    assert emb.shape == (len(imgs), 512) and emb.dtype == np.float32
+    import pandas as pd
+
+    frame = pd.read_csv(tmp_path / "outputs/features/embeddings.csv")
+    assert list(frame.columns) == ["index", "path", "bucket", "label"] and len(frame) == len(imgs)  # :418-431
+    assert list(frame["index"]) == list(range(len(imgs)))
+    assert set(frame["bucket"]) == {"labeled", "unlabeled"}
+    meta = json.loads((tmp_path / "outputs/features/metadata.json").read_text())
+    for key in ("backbone", "weights", "layer", "embedding_dimension", "input_resize", "input_crop", "normalization_mean",
+                "normalization_std", "channel_policy", "date_utc", "num_images", "failed_images", "device", "dataset_dir",
+                "dataset_digest", "sanity_checks", "neighbor_probe"):  # :433-451
+        assert key in meta, key
+    assert meta["num_images"] == len(imgs) and meta["failed_images"] == 1 and meta["embedding_dimension"] == 512
+    assert set(meta["sanity_checks"]) == {"num_vectors", "dimension", "mean_abs_mean", "mean_std"}
+    note = (tmp_path / "outputs/notes/feature_summary.md").read_text()
+    assert "# Feature Extraction Summary" in note and "zz_broken.png" in note
+    assert (tmp_path / "outputs/logs/feature_extraction.log").stat().st_size > 0
+
+
+def test_build_transform_and_load_model_are_drop_ins(dataset):
+    root, imgs = dataset
+    transform = fx.build_transform()  # :184-207
+    want_t = rp.port_transform()
+    for arr in (imgs[0], imgs[10], imgs[11]):
+        pil = Image.fromarray(arr)
+        assert torch.equal(transform(pil), want_t(pil))  # bit-exact
+    model = fx.load_model(torch.device("cuda:0"))  # :210-227
+    x = torch.stack([want_t(Image.fromarray(a)) for a in imgs[:4]])
+    with torch.no_grad():
+        got = model(x)
+        want = rp.port_model(torch.device("cpu"), 1234, True)(x)
+    assert tuple(got.shape) == (4, 512, 1, 1)
+    g, w = got.flatten(1).cpu().numpy(), want.flatten(1).numpy()
+    assert (np.linalg.norm(g - w, axis=1) / np.linalg.norm(w, axis=1)).max() <= 1e-2
+
+
+def test_channel_policy_errors_propagate_like_the_reference(tmp_path):
+    gray = tmp_path / "avec_labels" / "a"
+    gray.mkdir(parents=True)
+    Image.fromarray(np.zeros((64, 64), np.uint8)).save(gray / "g.png")  # true mode "L": Normalize raises
+    records = fx.discover_image_records(tmp_path)
+    with pytest.raises(RuntimeError, match="broadcast shape"):
+        fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=2)
+
+
+def test_pipelined_slots_equal_the_synchronous_call():
+    eng = fx.get_engine(torch.device("cuda:0"), min_batch=16)
+    batches = [list(synthetic.noise_images(16, 224, 224, seed=s)) for s in range(4)]
+    sync = []
+    packed = []
+    for b in batches:
+        buf, descs, total = pack_images(b)
+        pinned = torch.from_numpy(buf.copy()).pin_memory()
+        packed.append((pinned, descs, total))
+        sync.append(eng.embed_host(pinned, descs, 16, total))
+    outs = [torch.empty((16, 512)).pin_memory() for _ in range(4)]
+    for i, (pinned, descs, total) in enumerate(packed):
+        eng.embed_host_wait(i & 1)
+        eng.embed_host_async(i & 1, pinned, descs, 16, total, outs[i])
+    eng.embed_host_wait(0)
+    eng.embed_host_wait(1)
+    for i in range(4):
+        assert np.array_equal(outs[i].numpy(), sync[i])
