@@ -69,6 +69,7 @@ struct ImgDev {
     const int32_t* geom;
     int h, w, c;
     int ksh, ksv, band, col_lo, col_hi;
+    int fast;  // 1: RGB image whose taps fit the register-resident fast path (ksh, ksv <= 5, band fits in smem)
 };
 
 struct PackedLayer {

@@ -181,6 +181,132 @@ __device__ __forceinline__ int clip8(int acc) {
     return min(max(v, 0), 255);
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast path (RGB, <= 5 taps per axis -- every down-scale factor up to 2, all up-scales): the whole
+// band's source rows are staged in shared memory by block-wide 16-byte loads, then every thread owns
+// up to three BYTE COLUMNS (x, channel) of the 224-pixel-wide band and keeps their horizontal taps in
+// registers for all rows; the vertical pass reads its per-row taps from a small shared table.  About
+// 3x fewer instructions per value than the generic path below.  Same integer arithmetic, bit for bit.
+// ------------------------------------------------------------------------------------------
+constexpr int kFastTaps = 5;
+constexpr int kRowBytes = kCrop * 3;  // 672 byte columns
+
+template <int MODE>
+__device__ __forceinline__ void preprocess_fast(const uint8_t* __restrict__ base, const ImgDev& img, void* __restrict__ out,
+                                                const float* s_lut, const __nv_bfloat16* s_lutb, uint8_t* s_dyn, int y0, int y1,
+                                                size_t img_idx) {
+    const int tid = threadIdx.x;
+    const int32_t* __restrict__ g = img.geom;
+    const int32_t* hx_min = g;
+    const int32_t* hx_cnt = g + kCrop;
+    const int32_t* vy_min = g + 2 * kCrop;
+    const int32_t* vy_cnt = g + 3 * kCrop;
+    const int32_t* hk = g + kGeomHdr;
+    const int32_t* vk = hk + kCrop * img.ksh;
+
+    const int rlo = __ldg(vy_min + y0);
+    const int rhi = __ldg(vy_min + y1 - 1) + __ldg(vy_cnt + y1 - 1);
+    const int nrows = rhi - rlo;
+    const int span_bytes = (img.col_hi - img.col_lo) * 3;
+    const int src_pitch = (span_bytes + 15 + 16) & ~15;  // room for the alignment shift of any row
+    const size_t pitch = (size_t)img.w * 3;
+
+    // shared-memory carve-up (after the 3 KB LUT): vertical table, row shifts, source rows, band
+    int32_t* s_vt = reinterpret_cast<int32_t*>(s_dyn);               // [16 rows][8]: ym, n, k0..k4
+    int32_t* s_shift = s_vt + 16 * 8;                                // [kMaxTmpRows] alignment shift per staged row
+    uint8_t* s_src = reinterpret_cast<uint8_t*>(s_shift + kMaxTmpRows);
+    uint8_t* s_tmp = s_src + (size_t)nrows * src_pitch;              // [nrows][672]
+
+    // ---- stage the source rows (only the byte range the crop touches) ----
+    const int nvec_max = src_pitch >> 4;
+    for (int idx = tid; idx < nrows * nvec_max; idx += kPreThreads) {
+        const int r = idx / nvec_max, j = idx - r * nvec_max;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(base + (size_t)(rlo + r) * pitch + (size_t)img.col_lo * 3);
+        const uintptr_t a0 = ga & ~(uintptr_t)15;
+        const int shift = (int)(ga - a0);
+        if (j == 0) s_shift[r] = shift;
+        // every 16-byte chunk read holds at least one byte of this row (see the generic path)
+        if (j * 16 < shift + span_bytes)
+            reinterpret_cast<uint4*>(s_src + (size_t)r * src_pitch)[j] = ldg_stream16(reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)j));
+    }
+    for (int i = tid; i < (y1 - y0) * 8; i += kPreThreads) {
+        const int yy = i >> 3, f = i & 7, y = y0 + yy;
+        int v = 0;
+        if (f == 0) v = __ldg(vy_min + y) - rlo;
+        else if (f == 1) v = __ldg(vy_cnt + y);
+        else if (f - 2 < img.ksv) v = __ldg(vk + y * img.ksv + (f - 2));
+        s_vt[i] = v;
+    }
+    // ---- per-thread horizontal taps for its byte columns b = tid, tid + 256, tid + 512 ----
+    int off[3], cnt[3], kx[3][kFastTaps];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int b = tid + q * kPreThreads;
+        off[q] = 0;
+        cnt[q] = 0;
+#pragma unroll
+        for (int i = 0; i < kFastTaps; ++i) kx[q][i] = 0;
+        if (b < kRowBytes) {
+            const int x = b / 3, c = b - 3 * x;
+            off[q] = (__ldg(hx_min + x) - img.col_lo) * 3 + c;
+            cnt[q] = __ldg(hx_cnt + x);
+#pragma unroll
+            for (int i = 0; i < kFastTaps; ++i)
+                if (i < img.ksh) kx[q][i] = __ldg(hk + x * img.ksh + i);  // taps past cnt are zero in the table
+        }
+    }
+    __syncthreads();
+    // ---- horizontal pass: staged source rows -> uint8 band ----
+    for (int r = 0; r < nrows; ++r) {
+        const uint8_t* rowp = s_src + (size_t)r * src_pitch + s_shift[r];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int b = tid + q * kPreThreads;
+            if (b < kRowBytes) {
+                int acc = 1 << 21;
+                const uint8_t* pp = rowp + off[q];
+#pragma unroll
+                for (int i = 0; i < kFastTaps; ++i)
+                    if (i < cnt[q]) acc += kx[q][i] * (int)pp[3 * i];
+                s_tmp[r * kRowBytes + b] = (uint8_t)clip8(acc);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass + table lookup + store ----
+    for (int yy = 0; yy < y1 - y0; ++yy) {
+        const int y = y0 + yy;
+        const int ym = s_vt[yy * 8], n = s_vt[yy * 8 + 1];
+        int kv[kFastTaps];
+#pragma unroll
+        for (int i = 0; i < kFastTaps; ++i) kv[i] = s_vt[yy * 8 + 2 + i];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int b = tid + q * kPreThreads;
+            if (b < kRowBytes) {
+                int acc = 1 << 21;
+                const uint8_t* pp = s_tmp + ym * kRowBytes + b;
+#pragma unroll
+                for (int i = 0; i < kFastTaps; ++i)
+                    if (i < n) acc += kv[i] * (int)pp[i * kRowBytes];
+                const int v = clip8(acc);
+                const int x = b / 3, c = b - 3 * x;
+                if (MODE == 0) {
+                    reinterpret_cast<float*>(out)[img_idx * 3 * kCrop * kCrop + (size_t)c * kCrop * kCrop + (size_t)y * kCrop + x] =
+                        s_lut[c * 256 + v];
+                } else if (MODE == 1) {
+                    const int py = y + kIn0Pad, px = x + kIn0Pad;
+                    const size_t elem = ((img_idx * kS2dH + (py >> 1)) * kS2dW + (px >> 1)) * kS2dC + ((py & 1) * 2 + (px & 1)) * 3 + c;
+                    reinterpret_cast<__nv_bfloat16*>(out)[elem] = s_lutb[c * 256 + v];
+                } else {
+                    const size_t pix = (img_idx * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
+                    reinterpret_cast<float*>(out)[pix * 4 + c] = s_lut[c * 256 + v];
+                }
+            }
+        }
+    }
+}
+
 // MODE: 0 = fp32 NCHW [n][3][224][224]; 1 = bf16 conv1 staging; 2 = fp32 conv1 staging.
 template <int MODE>
 __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ src,
@@ -208,6 +334,10 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
         for (int i = tid; i < 768; i += kPreThreads) s_lut[i] = lut_f32[i];
     }
 
+    if (img.fast) {  // block-uniform
+        preprocess_fast<MODE>(src + img.src_off, img, out, s_lut, s_lutb, smem + 3072, y0, y1, blockIdx.y);
+        return;
+    }
     const int32_t* __restrict__ g = img.geom;
     const int32_t* hx_min = g;
     const int32_t* hx_cnt = g + kCrop;
@@ -405,7 +535,7 @@ int preprocess_init(fx_engine* e) {
     FX_CUDA(e, cudaMalloc(&e->img_dev, sizeof(ImgDev) * e->max_batch));
     FX_CUDA(e, cudaMallocHost(&e->img_host, sizeof(ImgDev) * e->max_batch));
     FX_CUDA(e, cudaEventCreateWithFlags(&e->img_host_free, cudaEventDisableTiming));
-    const int max_smem = 3072 + kMaxTmpRows * kCrop * 3 + kPreWarps * kRowBufCap;
+    const int max_smem = 3072 + std::max(kMaxTmpRows * kCrop * 3 + kPreWarps * kRowBufCap, 97 * 1024);
     FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -450,7 +580,7 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
                    cudaStream_t stream) {
     if (n == 0) return FX_OK;
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
-    int min_band = 16, max_tmp = 0, max_span = 0;
+    int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0;
     for (int i = 0; i < n; ++i) {
         const fx_image_desc& d = descs[i];
         if (d.channels != 3 && d.channels != 1)
@@ -472,14 +602,22 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
         im.col_lo = ge->col_lo;
         im.col_hi = ge->col_hi;
         min_band = std::min(min_band, ge->band);
-        max_tmp = std::max(max_tmp, ge->max_rows * kCrop * d.channels);
-        max_span = std::max(max_span, (ge->col_hi - ge->col_lo) * d.channels + 32);
+        // fast path: RGB, few taps, and the band's source rows + uint8 band fit in 96 KB (2 blocks / SM)
+        const int src_pitch = ((ge->col_hi - ge->col_lo) * 3 + 15 + 16) & ~15;
+        const int need = 16 * 8 * 4 + kMaxTmpRows * 4 + ge->max_rows * (src_pitch + kRowBytes) + 16;
+        im.fast = d.channels == 3 && ge->ksh <= kFastTaps && ge->ksv <= kFastTaps && ge->band <= 16 && need <= 96 * 1024;
+        if (im.fast) {
+            fast_smem = std::max(fast_smem, need);
+        } else {
+            max_tmp = std::max(max_tmp, ge->max_rows * kCrop * d.channels);
+            max_span = std::max(max_span, (ge->col_hi - ge->col_lo) * d.channels + 32);
+        }
     }
     FX_CUDA(e, cudaMemcpyAsync(e->img_dev, e->img_host, sizeof(ImgDev) * n, cudaMemcpyHostToDevice, stream));
     FX_CUDA(e, cudaEventRecord(e->img_host_free, stream));
     const int tmp_bytes = (max_tmp + 15) & ~15;
     const int rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
-    const int smem = 3072 + tmp_bytes + kPreWarps * rowbuf;
+    const int smem = 3072 + std::max(max_tmp ? tmp_bytes + kPreWarps * rowbuf : 0, fast_smem);
     dim3 grid((kCrop + min_band - 1) / min_band, n);
     switch (mode) {
         case PreOut::NCHW_F32:
