@@ -55,12 +55,13 @@ struct GeomTableHost {
     int band;                // output rows per thread block
     int max_rows;            // source rows a band touches (upper bound)
     int col_lo, col_hi;      // source pixel columns touched by the crop [lo, hi)
+    int cnt_h, cnt_v;        // largest tap count actually used inside the crop, per axis
     std::vector<int32_t> blob;  // packed device image, layout in preprocess.cu
 };
 
 struct GeomEntry {
     int32_t* dev = nullptr;  // device copy of blob
-    int ksh = 0, ksv = 0, band = 0, max_rows = 0, col_lo = 0, col_hi = 0;
+    int ksh = 0, ksv = 0, band = 0, max_rows = 0, col_lo = 0, col_hi = 0, cnt_h = 0, cnt_v = 0;
 };
 
 // Per-image record consumed by the preprocess kernel.

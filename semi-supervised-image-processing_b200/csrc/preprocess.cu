@@ -136,6 +136,8 @@ static bool build_geom(int h, int w, GeomTableHost& g) {
     g.w = w;
     g.col_lo = hmn[0];
     g.col_hi = hmn[kCrop - 1] + hct[kCrop - 1];
+    g.cnt_h = *std::max_element(hct.begin(), hct.end());
+    g.cnt_v = *std::max_element(vct.begin(), vct.end());
     g.band = 0;
     for (int band = 16; band >= 1; band >>= 1) {
         int worst = 0;
@@ -191,14 +193,13 @@ __device__ __forceinline__ int clip8(int acc) {
 constexpr int kFastTaps = 5;
 constexpr int kRowBytes = kCrop * 3;  // 672 byte columns
 
-template <int MODE>
+template <int MODE, int NTH, int NTV>
 __device__ __forceinline__ void preprocess_fast(const uint8_t* __restrict__ base, const ImgDev& img, void* __restrict__ out,
                                                 const float* s_lut, const __nv_bfloat16* s_lutb, uint8_t* s_dyn, int y0, int y1,
                                                 size_t img_idx) {
     const int tid = threadIdx.x;
     const int32_t* __restrict__ g = img.geom;
     const int32_t* hx_min = g;
-    const int32_t* hx_cnt = g + kCrop;
     const int32_t* vy_min = g + 2 * kCrop;
     const int32_t* vy_cnt = g + 3 * kCrop;
     const int32_t* hk = g + kGeomHdr;
@@ -208,14 +209,14 @@ __device__ __forceinline__ void preprocess_fast(const uint8_t* __restrict__ base
     const int rhi = __ldg(vy_min + y1 - 1) + __ldg(vy_cnt + y1 - 1);
     const int nrows = rhi - rlo;
     const int span_bytes = (img.col_hi - img.col_lo) * 3;
-    const int src_pitch = (span_bytes + 15 + 16) & ~15;  // room for the alignment shift of any row
+    const int src_pitch = (span_bytes + 15 + 16 + 3 * kFastTaps) & ~15;  // + alignment shift + zero-weight tap overreach
     const size_t pitch = (size_t)img.w * 3;
 
     // shared-memory carve-up (after the 3 KB LUT): vertical table, row shifts, source rows, band
-    int32_t* s_vt = reinterpret_cast<int32_t*>(s_dyn);               // [16 rows][8]: ym, n, k0..k4
-    int32_t* s_shift = s_vt + 16 * 8;                                // [kMaxTmpRows] alignment shift per staged row
-    uint8_t* s_src = reinterpret_cast<uint8_t*>(s_shift + kMaxTmpRows);
-    uint8_t* s_tmp = s_src + (size_t)nrows * src_pitch;              // [nrows][672]
+    int32_t* s_vt = reinterpret_cast<int32_t*>(s_dyn);               // [16 rows][8]: ym, k0..k4
+    int32_t* s_shift = s_vt + 16 * 8;                                // [kMaxTmpRows + kFastTaps] alignment shift per staged row
+    uint8_t* s_src = reinterpret_cast<uint8_t*>(s_shift + kMaxTmpRows + 8);
+    uint8_t* s_tmp = s_src + (size_t)nrows * src_pitch;              // [nrows + NTV][672] (rows past nrows: zero-weight reads)
 
     // ---- stage the source rows (only the byte range the crop touches) ----
     const int nvec_max = src_pitch >> 4;
@@ -233,82 +234,82 @@ __device__ __forceinline__ void preprocess_fast(const uint8_t* __restrict__ base
         const int yy = i >> 3, f = i & 7, y = y0 + yy;
         int v = 0;
         if (f == 0) v = __ldg(vy_min + y) - rlo;
-        else if (f == 1) v = __ldg(vy_cnt + y);
-        else if (f - 2 < img.ksv) v = __ldg(vk + y * img.ksv + (f - 2));
+        else if (f - 1 < img.ksv && f - 1 < NTV) v = __ldg(vk + y * img.ksv + (f - 1));  // taps past the count are zero in the table
         s_vt[i] = v;
     }
     // ---- per-thread horizontal taps for its byte columns b = tid, tid + 256, tid + 512 ----
-    int off[3], cnt[3], kx[3][kFastTaps];
+    int off[3], kx[3][NTH], ocol[3], lutc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        const int b = tid + q * kPreThreads;
-        off[q] = 0;
-        cnt[q] = 0;
+        const int b = min(tid + q * kPreThreads, kRowBytes - 1);
+        const int x = b / 3, c = b - 3 * x;
+        off[q] = (__ldg(hx_min + x) - img.col_lo) * 3 + c;
 #pragma unroll
-        for (int i = 0; i < kFastTaps; ++i) kx[q][i] = 0;
-        if (b < kRowBytes) {
-            const int x = b / 3, c = b - 3 * x;
-            off[q] = (__ldg(hx_min + x) - img.col_lo) * 3 + c;
-            cnt[q] = __ldg(hx_cnt + x);
-#pragma unroll
-            for (int i = 0; i < kFastTaps; ++i)
-                if (i < img.ksh) kx[q][i] = __ldg(hk + x * img.ksh + i);  // taps past cnt are zero in the table
+        for (int i = 0; i < NTH; ++i) kx[q][i] = i < img.ksh ? __ldg(hk + x * img.ksh + i) : 0;
+        lutc[q] = c * 256;
+        if (MODE == 0) {
+            ocol[q] = c * kCrop * kCrop + x;
+        } else if (MODE == 1) {
+            const int px = x + kIn0Pad;
+            ocol[q] = (px >> 1) * kS2dC + (px & 1) * 3 + c;
+        } else {
+            ocol[q] = (x + kIn0Pad) * 4 + c;
         }
     }
+    const bool has2 = tid + 2 * kPreThreads < kRowBytes;  // 672 = 2 * 256 + 160
     __syncthreads();
-    // ---- horizontal pass: staged source rows -> uint8 band ----
+    // ---- horizontal pass: staged source rows -> uint8 band (zero-weight taps read valid smem, contribute 0) ----
+#pragma unroll 2
     for (int r = 0; r < nrows; ++r) {
         const uint8_t* rowp = s_src + (size_t)r * src_pitch + s_shift[r];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const int b = tid + q * kPreThreads;
-            if (b < kRowBytes) {
+            if (q < 2 || has2) {
                 int acc = 1 << 21;
                 const uint8_t* pp = rowp + off[q];
 #pragma unroll
-                for (int i = 0; i < kFastTaps; ++i)
-                    if (i < cnt[q]) acc += kx[q][i] * (int)pp[3 * i];
-                s_tmp[r * kRowBytes + b] = (uint8_t)clip8(acc);
+                for (int i = 0; i < NTH; ++i) acc += kx[q][i] * (int)pp[3 * i];
+                s_tmp[r * kRowBytes + tid + q * kPreThreads] = (uint8_t)clip8(acc);
             }
         }
     }
     __syncthreads();
     // ---- vertical pass + table lookup + store ----
+#pragma unroll 2
     for (int yy = 0; yy < y1 - y0; ++yy) {
         const int y = y0 + yy;
-        const int ym = s_vt[yy * 8], n = s_vt[yy * 8 + 1];
-        int kv[kFastTaps];
+        const int ym = s_vt[yy * 8];
+        int kv[NTV];
 #pragma unroll
-        for (int i = 0; i < kFastTaps; ++i) kv[i] = s_vt[yy * 8 + 2 + i];
+        for (int i = 0; i < NTV; ++i) kv[i] = s_vt[yy * 8 + 1 + i];
+        size_t orow;
+        if (MODE == 0) {
+            orow = img_idx * 3 * kCrop * kCrop + (size_t)y * kCrop;
+        } else if (MODE == 1) {
+            const int py = y + kIn0Pad;
+            orow = ((img_idx * kS2dH + (py >> 1)) * kS2dW) * kS2dC + (py & 1) * 6;
+        } else {
+            orow = ((img_idx * kIn0H + (y + kIn0Pad)) * kIn0W) * 4;
+        }
+        const uint8_t* colp = s_tmp + ym * kRowBytes + tid;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const int b = tid + q * kPreThreads;
-            if (b < kRowBytes) {
+            if (q < 2 || has2) {
                 int acc = 1 << 21;
-                const uint8_t* pp = s_tmp + ym * kRowBytes + b;
 #pragma unroll
-                for (int i = 0; i < kFastTaps; ++i)
-                    if (i < n) acc += kv[i] * (int)pp[i * kRowBytes];
+                for (int i = 0; i < NTV; ++i) acc += kv[i] * (int)colp[q * kPreThreads + i * kRowBytes];
                 const int v = clip8(acc);
-                const int x = b / 3, c = b - 3 * x;
-                if (MODE == 0) {
-                    reinterpret_cast<float*>(out)[img_idx * 3 * kCrop * kCrop + (size_t)c * kCrop * kCrop + (size_t)y * kCrop + x] =
-                        s_lut[c * 256 + v];
-                } else if (MODE == 1) {
-                    const int py = y + kIn0Pad, px = x + kIn0Pad;
-                    const size_t elem = ((img_idx * kS2dH + (py >> 1)) * kS2dW + (px >> 1)) * kS2dC + ((py & 1) * 2 + (px & 1)) * 3 + c;
-                    reinterpret_cast<__nv_bfloat16*>(out)[elem] = s_lutb[c * 256 + v];
-                } else {
-                    const size_t pix = (img_idx * kIn0H + (y + kIn0Pad)) * kIn0W + (x + kIn0Pad);
-                    reinterpret_cast<float*>(out)[pix * 4 + c] = s_lut[c * 256 + v];
-                }
+                if (MODE == 1)
+                    reinterpret_cast<__nv_bfloat16*>(out)[orow + ocol[q]] = s_lutb[lutc[q] + v];
+                else
+                    reinterpret_cast<float*>(out)[orow + ocol[q]] = s_lut[lutc[q] + v];
             }
         }
     }
 }
 
 // MODE: 0 = fp32 NCHW [n][3][224][224]; 1 = bf16 conv1 staging; 2 = fp32 conv1 staging.
-template <int MODE>
+template <int MODE, int NTH, int NTV>
 __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* __restrict__ src,
                                                                  const ImgDev* __restrict__ imgs,
                                                                  void* __restrict__ out,
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
     }
 
     if (img.fast) {  // block-uniform
-        preprocess_fast<MODE>(src + img.src_off, img, out, s_lut, s_lutb, smem + 3072, y0, y1, blockIdx.y);
+        preprocess_fast<MODE, NTH, NTV>(src + img.src_off, img, out, s_lut, s_lutb, smem + 3072, y0, y1, blockIdx.y);
         return;
     }
     const int32_t* __restrict__ g = img.geom;
@@ -513,6 +514,21 @@ __global__ void stage_nchw_kernel(const float* __restrict__ in, void* __restrict
 // Host driver
 // ------------------------------------------------------------------------------------------
 
+using PreKernel = void (*)(const uint8_t*, const ImgDev*, void*, const float*, const __nv_bfloat16*, int, int);
+
+// [mode 0..2][NTH class 2/4/5][NTV class 2/4/5]
+static PreKernel* pre_kernels() {
+    static PreKernel table[27] = {
+#define FX_PRE_ROW(M) \
+    preprocess_kernel<M, 2, 2>, preprocess_kernel<M, 2, 4>, preprocess_kernel<M, 2, 5>, preprocess_kernel<M, 4, 2>, \
+        preprocess_kernel<M, 4, 4>, preprocess_kernel<M, 4, 5>, preprocess_kernel<M, 5, 2>, preprocess_kernel<M, 5, 4>, \
+        preprocess_kernel<M, 5, 5>
+        FX_PRE_ROW(0), FX_PRE_ROW(1), FX_PRE_ROW(2)
+#undef FX_PRE_ROW
+    };
+    return table;
+}
+
 int preprocess_init(fx_engine* e) {
     // ToTensor + Normalize as torch computes them (fp32 division by 255, fp32 subtract, fp32
     // true division): torchvision/transforms/functional.py:166-178, _functional_tensor.py:916-928.
@@ -536,9 +552,8 @@ int preprocess_init(fx_engine* e) {
     FX_CUDA(e, cudaMallocHost(&e->img_host, sizeof(ImgDev) * e->max_batch));
     FX_CUDA(e, cudaEventCreateWithFlags(&e->img_host_free, cudaEventDisableTiming));
     const int max_smem = 3072 + std::max(kMaxTmpRows * kCrop * 3 + kPreWarps * kRowBufCap, 97 * 1024);
-    FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    FX_CUDA(e, cudaFuncSetAttribute(preprocess_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    for (int i = 0; i < 27; ++i)
+        FX_CUDA(e, cudaFuncSetAttribute(pre_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     return FX_OK;
 }
 
@@ -568,6 +583,8 @@ static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
         ent.max_rows = g.max_rows;
         ent.col_lo = g.col_lo;
         ent.col_hi = g.col_hi;
+        ent.cnt_h = g.cnt_h;
+        ent.cnt_v = g.cnt_v;
         FX_CUDA(e, cudaMalloc(&ent.dev, sizeof(int32_t) * g.blob.size()));
         FX_CUDA(e, cudaMemcpy(ent.dev, g.blob.data(), sizeof(int32_t) * g.blob.size(), cudaMemcpyHostToDevice));
         it = e->geoms.emplace(key, ent).first;
@@ -580,7 +597,7 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
                    cudaStream_t stream) {
     if (n == 0) return FX_OK;
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
-    int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0;
+    int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
     for (int i = 0; i < n; ++i) {
         const fx_image_desc& d = descs[i];
         if (d.channels != 3 && d.channels != 1)
@@ -603,9 +620,13 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
         im.col_hi = ge->col_hi;
         min_band = std::min(min_band, ge->band);
         // fast path: RGB, few taps, and the band's source rows + uint8 band fit in 96 KB (2 blocks / SM)
-        const int src_pitch = ((ge->col_hi - ge->col_lo) * 3 + 15 + 16) & ~15;
-        const int need = 16 * 8 * 4 + kMaxTmpRows * 4 + ge->max_rows * (src_pitch + kRowBytes) + 16;
-        im.fast = d.channels == 3 && ge->ksh <= kFastTaps && ge->ksv <= kFastTaps && ge->band <= 16 && need <= 96 * 1024;
+        const int src_pitch = ((ge->col_hi - ge->col_lo) * 3 + 15 + 16 + 3 * kFastTaps) & ~15;
+        const int need = 16 * 8 * 4 + (kMaxTmpRows + 8) * 4 + ge->max_rows * src_pitch + (ge->max_rows + kFastTaps) * kRowBytes + 16;
+        im.fast = d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->band <= 16 && need <= 96 * 1024;
+        if (im.fast) {
+            nth = std::max(nth, ge->cnt_h);
+            ntv = std::max(ntv, ge->cnt_v);
+        }
         if (im.fast) {
             fast_smem = std::max(fast_smem, need);
         } else {
@@ -619,20 +640,9 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     const int rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
     const int smem = 3072 + std::max(max_tmp ? tmp_bytes + kPreWarps * rowbuf : 0, fast_smem);
     dim3 grid((kCrop + min_band - 1) / min_band, n);
-    switch (mode) {
-        case PreOut::NCHW_F32:
-            preprocess_kernel<0><<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32,
-                                                                       e->lut_bf16, tmp_bytes, rowbuf);
-            break;
-        case PreOut::IN0_BF16:
-            preprocess_kernel<1><<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32,
-                                                                       e->lut_bf16, tmp_bytes, rowbuf);
-            break;
-        case PreOut::IN0_F32:
-            preprocess_kernel<2><<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32,
-                                                                       e->lut_bf16, tmp_bytes, rowbuf);
-            break;
-    }
+    const int ih = nth <= 2 ? 0 : (nth <= 4 ? 1 : 2), iv = ntv <= 2 ? 0 : (ntv <= 4 ? 1 : 2);
+    pre_kernels()[((int)mode * 3 + ih) * 3 + iv]<<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32, e->lut_bf16,
+                                                                                   tmp_bytes, rowbuf);
     FX_LAUNCH_CHECK(e, "preprocess_kernel");
     return FX_OK;
 }
