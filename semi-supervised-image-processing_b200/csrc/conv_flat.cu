@@ -451,6 +451,264 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// flat128: the same halo-tile / shifted-view A operand, but 128 output channels per MMA (N=128 issues at
+// the tensor floor, 64 cycles, where two N=64 MMAs cost 96) and the weights STREAMED per (tap, chunk)
+// K-block through a ring, because a 128-channel slice of a 3x3x128 filter bank (288 KB) does not fit in
+// shared memory.  A work tile is R rows = two 128-pixel M-tiles that share every weight K-block; the two
+// accumulators (2 x 128 TMEM columns) are double-buffered across tiles.  Used for layer2's 3x3/s1 convs.
+// Warp roles: 0 = A (activation) producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = B (weight) producer,
+// 4..11 = epilogue (four warps per M-tile, two 64-column passes each through the 4 KB staging block).
+// ------------------------------------------------------------------------------------------
+struct Flat128Params {
+    int P, W, H, R, tiles_per_img, n_work, chunks, ns, cout;
+    int a_stages, a_stage_bytes, a_box_bytes, b_stages, slack_bytes;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    int relu;
+};
+
+__global__ void __launch_bounds__(kFlatThreads, 1)
+flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Flat128Params p) {
+    constexpr int TAPS = 9, KW = 3, ROWB = 128, KSTEPS = 4;
+    constexpr int BTILE = 128 * ROWB;  // one weight K-block: 128 cout rows x 64 k
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sB = sbase;
+    const uint32_t sA = sB + p.b_stages * BTILE;
+    const uint32_t stage0 = sA + p.a_stages * p.a_stage_bytes + p.slack_bytes;  // 8 epilogue warps x 4 KB
+    const uint32_t bias0 = stage0 + 8 * 4096;                                  // 128 fp32
+    const uint32_t bars = bias0 + 512;
+    const uint32_t afull0 = bars, aempty0 = afull0 + 8 * p.a_stages;
+    const uint32_t bfull0 = aempty0 + 8 * p.a_stages, bempty0 = bfull0 + 8 * p.b_stages;
+    const uint32_t tfull0 = bempty0 + 8 * p.b_stages, tempty0 = tfull0 + 16, tslot = tempty0 + 16;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nslice = blockIdx.x % p.ns;
+    const int w_first = blockIdx.x / p.ns, w_step = gridDim.x / p.ns;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.a_stages; ++i) {
+            mbar_init(afull0 + 8 * i, 1);
+            mbar_init(aempty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < p.b_stages; ++i) {
+            mbar_init(bfull0 + 8 * i, 1);
+            mbar_init(bempty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 256);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tslot, 512);
+    if (warp == 3) {
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        for (int i = lane; i < 128; i += 32) bs[i] = __ldg(p.bias + nslice * 128 + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    if (warp == 0) {
+        // ===== A producer: one halo box per (tile, chunk) =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int w = w_first; w < p.n_work; w += w_step) {
+                const int img = w / p.tiles_per_img;
+                const int y0 = (w - img * p.tiles_per_img) * p.R;
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(aempty0 + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(afull0 + 8 * stage, p.a_box_bytes);
+                    tma_load_4d(sA + stage * p.a_stage_bytes, &map_a, afull0 + 8 * stage, c * 64, -1, y0 - 1, img);
+                    if (++stage == (uint32_t)p.a_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== B producer: the weight K-blocks in the order the MMA warp consumes them =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int w = w_first; w < p.n_work; w += w_step)
+                for (int c = 0; c < p.chunks; ++c)
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        mbar_wait(bempty0 + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bfull0 + 8 * stage, BTILE);
+                        tma_load_2d(sB + stage * BTILE, &map_b, bfull0 + 8 * stage, (tap * p.chunks + c) * 64, nslice * 128);
+                        if (++stage == (uint32_t)p.b_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc<128>();
+        constexpr uint64_t desc_hi = make_smem_desc_rowb<ROWB>(0) & 0xFFFFFFFF00000000ull;
+        uint32_t astage = 0, aphase = 0, bstage = 0, bphase = 0;
+        int it = 0;
+        for (int w = w_first; w < p.n_work; w += w_step, ++it) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * p.R;
+            const int rows_valid = min(p.R, p.H - y0);
+            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+            const uint32_t set = it & 1, sphase = (it >> 1) & 1;
+            mbar_wait(tempty0 + 8 * set, sphase ^ 1);
+            tc_fence_after();
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(afull0 + 8 * astage, aphase);
+                tc_fence_after();
+                const uint32_t a_lo_stage = (sA + astage * p.a_stage_bytes) >> 4;
+#pragma unroll 1
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(bfull0 + 8 * bstage, bphase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const int r = tap / KW, sx = tap - r * KW;
+                        const uint32_t b_lo = (sB + bstage * BTILE) >> 4;
+                        for (int mt = 0; mt < n_mt; ++mt) {
+                            const uint32_t d = tmem_base + set * 256 + mt * 128;
+                            const uint32_t a_lo = a_lo_stage + (uint32_t)(mt * 128 + r * p.P + sx) * (ROWB / 16);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k)
+                                umma_bf16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (c | tap | k) != 0);
+                        }
+                        umma_commit(bempty0 + 8 * bstage);
+                    }
+                    __syncwarp();
+                    if (++bstage == (uint32_t)p.b_stages) {
+                        bstage = 0;
+                        bphase ^= 1;
+                    }
+                }
+                if (elect_one_sync()) {
+                    umma_commit(aempty0 + 8 * astage);
+                    if (c == p.chunks - 1) umma_commit(tfull0 + 8 * set);
+                }
+                __syncwarp();
+                if (++astage == (uint32_t)p.a_stages) {
+                    astage = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;
+        const int mt = (warp - 4) >> 2;  // which M-tile of the work tile this warp handles
+        const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        const int cbase = nslice * 128;
+        const int rr0 = lane >> 3, ch = lane & 7;
+        const bool has_res = p.residual != nullptr;
+        int it = 0;
+        for (int w = w_first; w < p.n_work; w += w_step, ++it) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * p.R;
+            const int rows_valid = min(p.R, p.H - y0);
+            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+            const uint32_t set = it & 1, sphase = (it >> 1) & 1;
+            const int m = mt * 128 + q * 32 + lane;
+            const int i = m / p.P, x = m - i * p.P;
+            const int pix = (mt < n_mt && x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+            mbar_wait(tfull0 + 8 * set, sphase);
+            tc_fence_after();
+            if (mt >= n_mt) {  // nothing of ours in this (short) tile
+                tc_fence_before();
+                mbar_arrive(tempty0 + 8 * set);
+                continue;
+            }
+            const uint32_t taddr = tmem_base + set * 256 + mt * 128 + ((uint32_t)(q * 32) << 16);
+            const uint32_t srow = stg + lane * 128;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {  // 64 output channels per pass
+                if (has_res) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int rr = t * 4 + rr0;
+                        const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                        if (pr >= 0)
+                            cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
+                    }
+                    cp_async_commit();
+                    cp_async_wait_all();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + pass * 64 + h * 32, v);
+                    tmem_ld_wait();
+                    if (pass == 1 && h == 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty0 + 8 * set);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + pass * 64 + h * 32 + j * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + pass * 64 + h * 32 + j * 8 + 4);
+                        float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                      __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                      __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                      __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                        if (has_res && pix >= 0) {
+                            const uint4 rv = lds128(sa);
+                            const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                f[2 * k] += __uint_as_float(u[k] << 16);
+                                f[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        uint4 o;
+                        unsigned* ou = &o.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                            ou[k] = *reinterpret_cast<const unsigned*>(&h2);
+                        }
+                        sts128(sa, o);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = t * 4 + rr0;
+                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                    if (pr >= 0) {
+                        const uint4 val = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                        *reinterpret_cast<uint4*>(p.out + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8) = val;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemMax = 227 * 1024;
@@ -489,8 +747,66 @@ static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& m
     return FX_OK;
 }
 
+static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                        int n, int relu, cudaStream_t stream) {
+    const LayerGeom& g = L.g;
+    Flat128Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.bias = L.bias;
+    p.residual = residual;
+    p.out = out;
+    p.relu = relu;
+    p.cout = g.cout;
+    p.ns = g.cout / 128;
+    p.W = g.wout;
+    p.H = g.hout;
+    p.P = g.win + 2;
+    p.chunks = g.cin / 64;
+    p.R = std::max(1, std::min(g.hout, 256 / p.P));  // two 128-pixel M-tiles per work tile
+    p.tiles_per_img = (p.H + p.R - 1) / p.R;
+    p.n_work = n * p.tiles_per_img;
+    p.a_box_bytes = (p.R + 2) * p.P * 128;
+    p.a_stage_bytes = (p.a_box_bytes + 1023) & ~1023;
+    const int reach_rows = 256 + 2 * p.P + 2;
+    p.slack_bytes = (std::max(0, reach_rows * 128 - p.a_stage_bytes) + 1023) & ~1023;
+    p.a_stages = 3;
+    const int fixed = 1024 + p.a_stages * p.a_stage_bytes + p.slack_bytes + 8 * 4096 + 512 + 8 * (2 * 3 + 2 * 8 + 4) + 64;
+    p.b_stages = std::min(6, (kSmemMax - fixed) / (128 * 128));
+    if (p.b_stages < 2) return set_error(e, FX_ERR_UNSUPPORTED, "flat128_conv: tile does not fit in shared memory");
+    const int smem = fixed + p.b_stages * 128 * 128;
+    CUtensorMap ma, mb;
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.P, (uint32_t)(p.R + 2), 1};
+    int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat128 A");
+    if (rc != FX_OK) return rc;
+    const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+    const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+    const uint32_t bbox[2] = {64, 128};
+    rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat128 B");
+    if (rc != FX_OK) return rc;
+    static bool attr_done[16] = {};
+    if (!attr_done[e->device & 15]) {
+        FX_CUDA(e, cudaFuncSetAttribute(flat128_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_done[e->device & 15] = true;
+    }
+    int grid = std::min(e->sm_count, p.n_work * p.ns);
+    grid -= grid % p.ns;
+    if (grid < p.ns) grid = p.ns;
+    flat128_conv_kernel<<<grid, kFlatThreads, smem, stream>>>(ma, mb, p);
+    FX_LAUNCH_CHECK(e, "flat128_conv_kernel");
+    return FX_OK;
+}
+
+static bool flat128_supported(const LayerGeom& g) {
+    return g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin % 64 == 0 && g.cout % 128 == 0 && g.win + 2 <= 64 &&
+           g.win >= 16;
+}
+
 // Can this conv+bn group run on the flat kernel?
 bool flat_supported(const LayerGeom& g) {
+    if (flat128_supported(g)) return true;
     if (g.cin == 3) return g.kh == 7 && g.kw == 7 && g.stride == 2 && g.pad == 3 && g.hin == kCrop && g.win == kCrop && g.cout == 64;
     return g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin % 64 == 0 && g.cin <= 128 && g.cout % 64 == 0 &&
            g.win + 2 <= 128 && g.win >= 8;
@@ -545,6 +861,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
         return pool ? launch_flat<32, 4, 4, true>(e, ma, mb, p, smem, stream) : launch_flat<32, 4, 4, false>(e, ma, mb, p, smem, stream);
     }
     if (pool) return set_error(e, FX_ERR_INVALID, "flat_conv: only the stem has a fused max-pool");
+    if (flat128_supported(g)) return flat128_conv(e, L, in, residual, out, n, relu, stream);
     p.P = g.win + 2;
     p.chunks = g.cin / 64;
     p.x0 = -1;
