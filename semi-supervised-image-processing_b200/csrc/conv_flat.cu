@@ -569,19 +569,22 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 mbar_wait(afull0 + 8 * astage, aphase);
                 tc_fence_after();
                 const uint32_t a_lo_stage = (sA + astage * p.a_stage_bytes) >> 4;
-#pragma unroll 1
+                const uint32_t d0 = tmem_base + set * 256;
+#pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
                     mbar_wait(bfull0 + 8 * bstage, bphase);
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        const int r = tap / KW, sx = tap - r * KW;
                         const uint32_t b_lo = (sB + bstage * BTILE) >> 4;
-                        for (int mt = 0; mt < n_mt; ++mt) {
-                            const uint32_t d = tmem_base + set * 256 + mt * 128;
-                            const uint32_t a_lo = a_lo_stage + (uint32_t)(mt * 128 + r * p.P + sx) * (ROWB / 16);
+                        const uint32_t a_lo = a_lo_stage + (uint32_t)((tap / KW) * p.P + (tap % KW)) * (ROWB / 16);
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                            umma_bf16(d0, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (c | tap | k) != 0);
+                        if (n_mt > 1) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k)
-                                umma_bf16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (c | tap | k) != 0);
+                                umma_bf16(d0 + 128, desc_hi | (uint64_t)(a_lo + 128 * (ROWB / 16) + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                                          (c | tap | k) != 0);
                         }
                         umma_commit(bempty0 + 8 * bstage);
                     }
