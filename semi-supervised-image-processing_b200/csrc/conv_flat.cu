@@ -98,7 +98,9 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nslice = blockIdx.x % p.ns;
-    const int w_first = blockIdx.x / p.ns, w_step = gridDim.x / p.ns;
+    // contiguous run of work tiles per CTA (balances the short last tile of each image, keeps halo rows in L2)
+    const int n_cta = gridDim.x / p.ns, cta = blockIdx.x / p.ns;
+    const int w_first = (int)((long long)p.n_work * cta / n_cta), w_last = (int)((long long)p.n_work * (cta + 1) / n_cta);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -133,7 +135,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_expect_tx(wbar, TAPS * p.chunks * WTILE);
             for (int kb = 0; kb < TAPS * p.chunks; ++kb) tma_load_2d(sW + kb * WTILE, &map_b, wbar, kb * (ROWB / 2), nslice * 64);
             uint32_t stage = 0, phase = 0;
-            for (int w = w_first; w < p.n_work; w += w_step) {
+            for (int w = w_first; w < w_last; ++w) {
                 const int img = w / p.tiles_per_img;
                 const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
                 for (int c = 0; c < p.chunks; ++c) {
@@ -156,7 +158,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t stage = 0, phase = 0, g_base = 0;
         const uint32_t w_lo = sW >> 4;
         const uint32_t row_units = ROWB / 16;  // descriptor address units (16 B) per smem row
-        for (int w = w_first; w < p.n_work; w += w_step) {
+        for (int w = w_first; w < w_last; ++w) {
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             const int rows_valid = min(p.R, p.H - y0);
@@ -218,7 +220,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t row_bytes = (uint32_t)Wp * 128;
         const uint32_t mbox0 = stage0 + kRing * row_bytes;  // [3][4 quarters][2 halves][64 B]
         uint32_t g = 0;
-        for (int w = w_first; w < p.n_work; w += w_step) {
+        for (int w = w_first; w < w_last; ++w) {
             const int img = w / p.tiles_per_img;
             const int t = w - img * p.tiles_per_img;
             const int y0 = t * p.rstep + p.yfirst;
@@ -340,8 +342,8 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ++g;
             if (++mt == n_mt) {
                 mt = 0;
-                w += w_step;
-                if (w >= p.n_work) return false;
+                ++w;
+                if (w >= w_last) return false;
                 tile_setup();
             }
             return true;
@@ -364,7 +366,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             cp_async_commit();
         };
 
-        bool live = w < p.n_work;
+        bool live = w < w_last;
         if (live) {
             tile_setup();
             if (grp == 1) live = advance();
@@ -457,8 +459,11 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // shared memory.  A work tile is R rows = two 128-pixel M-tiles that share every weight K-block; the two
 // accumulators (2 x 128 TMEM columns) are double-buffered across tiles.  Used for layer2's 3x3/s1 convs.
 // Warp roles: 0 = A (activation) producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = B (weight) producer,
-// 4..11 = epilogue (four warps per M-tile, two 64-column passes each through the 4 KB staging block).
+// 4..19 = epilogue (16 warps: 4 TMEM lane quarters x 2 M-tiles x 2 halves of the 128 channels; the
+// epilogue of an N=128 tile is as long as its MMAs for one warp, so it is spread wide).
 // ------------------------------------------------------------------------------------------
+constexpr int kFlat128Threads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps
+
 struct Flat128Params {
     int P, W, H, R, tiles_per_img, n_work, chunks, ns, cout;
     int a_stages, a_stage_bytes, a_box_bytes, b_stages, slack_bytes;
@@ -468,7 +473,7 @@ struct Flat128Params {
     int relu;
 };
 
-__global__ void __launch_bounds__(kFlatThreads, 1)
+__global__ void __launch_bounds__(kFlat128Threads, 1)
 flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Flat128Params p) {
     constexpr int TAPS = 9, KW = 3, ROWB = 128, KSTEPS = 4;
     constexpr int BTILE = 128 * ROWB;  // one weight K-block: 128 cout rows x 64 k
@@ -476,8 +481,8 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sB = sbase;
     const uint32_t sA = sB + p.b_stages * BTILE;
-    const uint32_t stage0 = sA + p.a_stages * p.a_stage_bytes + p.slack_bytes;  // 8 epilogue warps x 4 KB
-    const uint32_t bias0 = stage0 + 8 * 4096;                                  // 128 fp32
+    const uint32_t stage0 = sA + p.a_stages * p.a_stage_bytes + p.slack_bytes;  // 16 epilogue warps x 4 KB
+    const uint32_t bias0 = stage0 + 16 * 4096;                                 // 128 fp32
     const uint32_t bars = bias0 + 512;
     const uint32_t afull0 = bars, aempty0 = afull0 + 8 * p.a_stages;
     const uint32_t bfull0 = aempty0 + 8 * p.a_stages, bempty0 = bfull0 + 8 * p.b_stages;
@@ -486,7 +491,9 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nslice = blockIdx.x % p.ns;
-    const int w_first = blockIdx.x / p.ns, w_step = gridDim.x / p.ns;
+    // contiguous run of work tiles per CTA (balances the short last tile of each image, keeps halo rows in L2)
+    const int n_cta = gridDim.x / p.ns, cta = blockIdx.x / p.ns;
+    const int w_first = (int)((long long)p.n_work * cta / n_cta), w_last = (int)((long long)p.n_work * (cta + 1) / n_cta);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -503,7 +510,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 256);
+            mbar_init(tempty0 + 8 * i, 512);
         }
         fence_barrier_init();
     }
@@ -521,7 +528,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== A producer: one halo box per (tile, chunk) =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int w = w_first; w < p.n_work; w += w_step) {
+            for (int w = w_first; w < w_last; ++w) {
                 const int img = w / p.tiles_per_img;
                 const int y0 = (w - img * p.tiles_per_img) * p.R;
                 for (int c = 0; c < p.chunks; ++c) {
@@ -539,7 +546,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== B producer: the weight K-blocks in the order the MMA warp consumes them =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int w = w_first; w < p.n_work; w += w_step)
+            for (int w = w_first; w < w_last; ++w)
                 for (int c = 0; c < p.chunks; ++c)
                     for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(bempty0 + 8 * stage, phase ^ 1);
@@ -557,7 +564,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         constexpr uint64_t desc_hi = make_smem_desc_rowb<ROWB>(0) & 0xFFFFFFFF00000000ull;
         uint32_t astage = 0, aphase = 0, bstage = 0, bphase = 0;
         int it = 0;
-        for (int w = w_first; w < p.n_work; w += w_step, ++it) {
+        for (int w = w_first; w < w_last; ++w, ++it) {
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * p.R;
             const int rows_valid = min(p.R, p.H - y0);
@@ -608,14 +615,15 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp >= 4) {
         // ===== epilogue =====
         const int q = warp & 3;
-        const int mt = (warp - 4) >> 2;  // which M-tile of the work tile this warp handles
+        const int mt = ((warp - 4) >> 2) & 1;  // which M-tile of the work tile this warp handles
+        const int pass = (warp - 4) >> 3;      // which 64 of the 128 output channels
         const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
         const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         const int cbase = nslice * 128;
         const int rr0 = lane >> 3, ch = lane & 7;
         const bool has_res = p.residual != nullptr;
         int it = 0;
-        for (int w = w_first; w < p.n_work; w += w_step, ++it) {
+        for (int w = w_first; w < w_last; ++w, ++it) {
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * p.R;
             const int rows_valid = min(p.R, p.H - y0);
@@ -633,8 +641,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             const uint32_t taddr = tmem_base + set * 256 + mt * 128 + ((uint32_t)(q * 32) << 16);
             const uint32_t srow = stg + lane * 128;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {  // 64 output channels per pass
+            {
                 if (has_res) {
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
@@ -652,7 +659,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     uint32_t v[32];
                     tmem_ld32(taddr + pass * 64 + h * 32, v);
                     tmem_ld_wait();
-                    if (pass == 1 && h == 1) {
+                    if (h == 1) {
                         tc_fence_before();
                         mbar_arrive(tempty0 + 8 * set);
                     }
@@ -772,8 +779,8 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     p.a_stage_bytes = (p.a_box_bytes + 1023) & ~1023;
     const int reach_rows = 256 + 2 * p.P + 2;
     p.slack_bytes = (std::max(0, reach_rows * 128 - p.a_stage_bytes) + 1023) & ~1023;
-    p.a_stages = 3;
-    const int fixed = 1024 + p.a_stages * p.a_stage_bytes + p.slack_bytes + 8 * 4096 + 512 + 8 * (2 * 3 + 2 * 8 + 4) + 64;
+    p.a_stages = 2;  // chunk granularity: the next tile's chunk c loads as soon as this tile's chunk c is consumed
+    const int fixed = 1024 + p.a_stages * p.a_stage_bytes + p.slack_bytes + 16 * 4096 + 512 + 8 * (2 * 3 + 2 * 8 + 4) + 64;
     p.b_stages = std::min(6, (kSmemMax - fixed) / (128 * 128));
     if (p.b_stages < 2) return set_error(e, FX_ERR_UNSUPPORTED, "flat128_conv: tile does not fit in shared memory");
     const int smem = fixed + p.b_stages * 128 * 128;
@@ -797,7 +804,7 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
     if (grid < p.ns) grid = p.ns;
-    flat128_conv_kernel<<<grid, kFlatThreads, smem, stream>>>(ma, mb, p);
+    flat128_conv_kernel<<<grid, kFlat128Threads, smem, stream>>>(ma, mb, p);
     FX_LAUNCH_CHECK(e, "flat128_conv_kernel");
     return FX_OK;
 }
