@@ -45,6 +45,7 @@ struct FlatParams {
 };
 
 constexpr int kFlatThreads = 384;
+constexpr int kFlatPoolThreads = 128 + 16 * 32;  // pooled stem: 16 epilogue warps
 constexpr int kFlatSlots = 8;  // 8 x 64 fp32 columns = the whole TMEM
 constexpr int kEpiBytes = 8 * 4096 + 256;      // epilogue staging (8 warps x 4 KB) + bias
 constexpr int kPoolRingBytes = 6 * 56 * 128 + 2048;  // pooled stem: six half-width conv rows (56 px x 64 ch bf16) + mailboxes
@@ -80,7 +81,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
 // writes the 3x3 / stride-2 / pad-1 max-pooled rows (torchvision/models/resnet.py:200) instead of the
 // conv output: work tile = 4 pooled rows = 9 conv rows (one recomputed), `out` is [n][H/2][W/2][64].
 template <int ROWB, int KH, int KW, bool POOL>
-__global__ void __launch_bounds__(kFlatThreads, 1)
+__global__ void __launch_bounds__(POOL ? kFlatPoolThreads : kFlatThreads, 1)
 flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const FlatParams p) {
     constexpr int TAPS = KH * KW;
     constexpr int KSTEPS = ROWB / 32;  // K=16 bf16 MMAs per smem row
@@ -113,7 +114,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int i = 0; i < kFlatSlots; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, POOL ? 256 : 128);
+            mbar_init(tempty0 + 8 * i, POOL ? 512 : 128);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
@@ -203,22 +204,23 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (warp >= 4 && POOL) {
         // ===== pooled-stem epilogue: TMEM -> (+bias, ReLU) -> bf16 -> horizontal 3-max in registers ->
         //       half-width rows in a smem ring -> vertical 3-max -> NHWC [n][56][56][64] =====
-        // All eight warps work on the same M-tile (two warps per TMEM lane quarter, 32 channels each);
-        // a lane owns conv pixel x of conv row i (m = i*P + x, lanes are consecutive x).  The horizontal
-        // max over x-1, x, x+1 (kept for even x = 2*pw) comes from the neighbouring lanes by shuffle; the
-        // neighbour of lane 0 lives in the previous warp / M-tile and arrives through a 64-byte mailbox.
-        // Ring slot i % 6 holds the horizontally pooled conv row i as [pw][64 ch] (16-byte chunk index
-        // XOR-swizzled by pw).  Pooled row j of the tile = max over ring rows 2j, 2j+1, 2j+2, emitted
-        // right after the M-tile that completes row 2j+2.  Conv row -1 (first band) and the junk columns
-        // x >= W are zeros: neutral for a max over post-ReLU values (the reference pads with -inf).
+        // Sixteen warps work on the same M-tile (four per TMEM lane quarter, 16 channels each: the stem has
+        // only 16 MMAs per 128 x 64 outputs, so its epilogue must be wide to keep up); a lane owns conv pixel x
+        // of conv row i (m = i*P + x, lanes are consecutive x).  The horizontal max over x-1, x, x+1 (kept for
+        // even x = 2*pw) comes from the neighbouring lanes by shuffle; the neighbour of lane 0 lives in the
+        // previous warp / M-tile and arrives through a 32-byte mailbox.  Ring slot i % 6 holds the
+        // horizontally pooled conv row i as [pw][64 ch] (16-byte chunk index XOR-swizzled by pw).  Pooled row j
+        // of the tile = max over ring rows 2j, 2j+1, 2j+2, emitted right after the M-tile that completes row
+        // 2j+2.  Conv row -1 (first band) and the junk columns x >= W are zeros: neutral for a max over
+        // post-ReLU values (the reference pads with -inf).
         constexpr int kRing = 6;
         const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
-        const int te = threadIdx.x - 128;  // 0..255
+        const int cq = (warp - 4) >> 2;    // 16-channel group 0..3
+        const int te = threadIdx.x - 128;  // 0..511
         const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         const int Wc = p.W, Wp = p.W >> 1, Hp = p.H >> 1;
         const uint32_t row_bytes = (uint32_t)Wp * 128;
-        const uint32_t mbox0 = stage0 + kRing * row_bytes;  // [3][4 quarters][2 halves][64 B]
+        const uint32_t mbox0 = stage0 + kRing * row_bytes;  // [3][4 quarters][4 channel groups][32 B]
         uint32_t g = 0;
         for (int w = w_first; w < w_last; ++w) {
             const int img = w / p.tiles_per_img;
@@ -229,19 +231,19 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
                 mbar_wait(tfull0 + 8 * slot, use & 1);
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem_base + slot * 64 + half * 32 + ((uint32_t)(q * 32) << 16), v);
+                uint32_t v[16];
+                tmem_ld16(tmem_base + slot * 64 + cq * 16 + ((uint32_t)(q * 32) << 16), v);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(tempty0 + 8 * slot);
                 const int m = mt * 128 + q * 32 + lane;
                 const int i = m / p.P, x = m - i * p.P;
                 const bool live = x < Wc && i < p.R && y0 + i >= 0;
-                unsigned c[16];
+                unsigned c[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + half * 32 + j * 8 + 4);
+                for (int j = 0; j < 2; ++j) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cq * 16 + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cq * 16 + j * 8 + 4);
                     const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
                                         __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                                         __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
@@ -253,55 +255,54 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
                 // hand the last lane's pixel to the next warp / M-tile
-                const uint32_t mb_mine = mbox0 + (((g % 3) * 4 + q) * 2 + half) * 64;
+                const uint32_t mb_mine = mbox0 + (((g % 3) * 4 + q) * 4 + cq) * 32;
                 if (lane == 31) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) sts128(mb_mine + j * 16, make_uint4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]));
+                    sts128(mb_mine, make_uint4(c[0], c[1], c[2], c[3]));
+                    sts128(mb_mine + 16, make_uint4(c[4], c[5], c[6], c[7]));
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                unsigned hm[16];
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                unsigned hm[8];
                 {
-                    const uint32_t mb_left = q > 0 ? mb_mine - 128 : mbox0 + ((((g + 2) % 3) * 4 + 3) * 2 + half) * 64;
-                    uint4 lv[4];
+                    const uint32_t mb_left = q > 0 ? mb_mine - 128 : mbox0 + ((((g + 2) % 3) * 4 + 3) * 4 + cq) * 32;
+                    uint4 lv[2];
                     const bool need_box = lane == 0 && x > 0 && (q > 0 || mt > 0);
+                    lv[0] = need_box ? lds128(mb_left) : make_uint4(0, 0, 0, 0);
+                    lv[1] = need_box ? lds128(mb_left + 16) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) lv[j] = need_box ? lds128(mb_left + j * 16) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
+                    for (int k = 0; k < 8; ++k) {
                         unsigned l = __shfl_up_sync(0xffffffffu, c[k], 1);
                         const unsigned r = __shfl_down_sync(0xffffffffu, c[k], 1);
                         if (lane == 0) l = (&lv[k >> 2].x)[k & 3];
-                        if (x == 0) l = 0u;  // no pixel to the left of the row start (the junk column of the previous row is zero anyway)
-                        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&l), *reinterpret_cast<const __nv_bfloat162*>(&c[k]));
-                        const __nv_bfloat162 bb = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&r));
-                        hm[k] = *reinterpret_cast<const unsigned*>(&bb);
+                        if (x == 0) l = 0u;  // row start: nothing to the left
+                        const __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&l), *reinterpret_cast<const __nv_bfloat162*>(&c[k]));
+                        const __nv_bfloat162 b2 = __hmax2(a2, *reinterpret_cast<const __nv_bfloat162*>(&r));
+                        hm[k] = *reinterpret_cast<const unsigned*>(&b2);
                     }
                 }
                 if (x < Wc && i < p.R && (x & 1) == 0) {
                     const int pw = x >> 1;
                     const uint32_t srow = stage0 + (uint32_t)(i % kRing) * row_bytes + (uint32_t)pw * 128;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        sts128(srow + (((half * 4 + j) ^ (pw & 7)) << 4), make_uint4(hm[4 * j], hm[4 * j + 1], hm[4 * j + 2], hm[4 * j + 3]));
+                    sts128(srow + (((cq * 2) ^ (pw & 7)) << 4), make_uint4(hm[0], hm[1], hm[2], hm[3]));
+                    sts128(srow + (((cq * 2 + 1) ^ (pw & 7)) << 4), make_uint4(hm[4], hm[5], hm[6], hm[7]));
                 }
                 // which pooled row (if any) does this M-tile complete?  row 2j+2 ends at flat index (2j+2)*P + W - 1
                 int jdone = -1;
                 for (int j = 0; 2 * j + 2 < p.R; ++j)
                     if (((2 * j + 2) * p.P + Wc - 1) / 128 == mt) jdone = j;
                 if (jdone >= 0) {
-                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    asm volatile("bar.sync 2, 512;" ::: "memory");
                     const int prow = (y0 + 1) / 2 + jdone;  // pooled row index in the image
                     const uint32_t r0 = stage0 + (uint32_t)((2 * jdone) % kRing) * row_bytes;
                     const uint32_t r1 = stage0 + (uint32_t)((2 * jdone + 1) % kRing) * row_bytes;
                     const uint32_t r2 = stage0 + (uint32_t)((2 * jdone + 2) % kRing) * row_bytes;
-                    for (int item = te; item < Wp * 8; item += 256) {
+                    for (int item = te; item < Wp * 8; item += 512) {
                         const int pw = item >> 3, ch = item & 7;
                         const uint32_t off = (uint32_t)pw * 128 + ((ch ^ (pw & 7)) << 4);
-                        const uint4 a = lds128(r0 + off), bq = lds128(r1 + off), cq = lds128(r2 + off);
+                        const uint4 a = lds128(r0 + off), bq = lds128(r1 + off), cq4 = lds128(r2 + off);
                         uint4 o;
                         const unsigned* au = &a.x;
                         const unsigned* bu = &bq.x;
-                        const unsigned* cu = &cq.x;
+                        const unsigned* cu = &cq4.x;
                         unsigned* ou = &o.x;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -752,7 +753,7 @@ static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& m
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
     if (grid < p.ns) grid = p.ns;
-    flat_conv_kernel<ROWB, KH, KW, POOL><<<grid, kFlatThreads, smem, stream>>>(ma, mb, p);
+    flat_conv_kernel<ROWB, KH, KW, POOL><<<grid, POOL ? kFlatPoolThreads : kFlatThreads, smem, stream>>>(ma, mb, p);
     FX_LAUNCH_CHECK(e, "flat_conv_kernel");
     return FX_OK;
 }

@@ -20,7 +20,8 @@
 //     accumulator in TMEM; 4 epilogue warps read it back with tcgen05.ld, add the folded-BN bias
 //     and the residual, apply ReLU, and store bf16 NHWC (or fp32 for the layer feeding avgpool).
 //   * warp-specialised, persistent over output tiles: warp 0 = TMA producer, warp 1 = MMA issuer,
-//     warp 2 = TMEM allocator, warps 4-7 = epilogue; mbarrier rings smem(full/empty) and
+//     warp 2 = TMEM allocator, warps 4-19 = epilogue (16 warps: the epilogue of a short-K tile is
+//     longer than its MMAs for four warps); mbarrier rings smem(full/empty) and
 //     tmem(full/empty).
 #include <algorithm>
 #include <cstring>
@@ -47,7 +48,7 @@ struct TcConvParams {
     int relu;
 };
 
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps (4 TMEM lane quarters x 4 column groups)
 
 template <int BN, int BK, int STAGES>
 struct TcSmem {
@@ -83,7 +84,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 128);
+            mbar_init(tempty0 + 8 * i, 512);
         }
         fence_barrier_init();
     }
@@ -155,7 +156,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> global =====
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int q = warp & 3;           // TMEM lane quarter this warp may read
+        const int cg = (warp - 4) >> 2;   // which quarter of the tile's BN columns this warp converts and stores
         const int row = q * 32 + lane;
         const int wl = row & ((1 << p.wt_log2) - 1);
         const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
@@ -178,7 +180,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            for (int c0 = cg * (BN / 4); c0 < (cg + 1) * (BN / 4); c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
