@@ -45,10 +45,11 @@ struct FlatParams {
 };
 
 constexpr int kFlatThreads = 384;
-constexpr int kFlatPoolThreads = 128 + 16 * 32;  // pooled stem: 16 epilogue warps
+constexpr int kFlatPoolThreads = 128 + 16 * 32;  // pooled stem: 8 epilogue warps + 8 pool warps
+constexpr int kPoolRing = 6;                     // conv rows kept in shared memory for the fused max-pool
 constexpr int kFlatSlots = 8;  // 8 x 64 fp32 columns = the whole TMEM
 constexpr int kEpiBytes = 8 * 4096 + 256;      // epilogue staging (8 warps x 4 KB) + bias
-constexpr int kPoolRingBytes = 6 * 56 * 128 + 2048;  // pooled stem: six half-width conv rows (56 px x 64 ch bf16) + mailboxes
+constexpr int kPoolRingBytes = 6 * 112 * 128;  // pooled stem: six conv rows (112 px x 64 ch bf16)
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -95,6 +96,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t bars = bias0 + 256;
     const uint32_t full0 = bars, empty0 = full0 + 8 * p.nstages, tfull0 = empty0 + 8 * p.nstages;
     const uint32_t tempty0 = tfull0 + 8 * kFlatSlots, wbar = tempty0 + 8 * kFlatSlots, tslot = wbar + 8;
+    const uint32_t mdone0 = tslot + 8, pool_sync0 = mdone0 + 8 * kFlatSlots;  // pooled stem only
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,13 +116,15 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int i = 0; i < kFlatSlots; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, POOL ? 512 : 128);
+            mbar_init(tempty0 + 8 * i, 128);
+            if (POOL) mbar_init(mdone0 + 8 * i, 128);
         }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tslot, 512);
     if (warp == 3) {
+        if (POOL && lane == 0) *reinterpret_cast<int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw))) = 0;
         float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         bs[lane] = __ldg(p.bias + nslice * 64 + lane);
         bs[lane + 32] = __ldg(p.bias + nslice * 64 + lane + 32);
@@ -201,117 +205,126 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             g_base += n_mt;
         }
-    } else if (warp >= 4 && POOL) {
-        // ===== pooled-stem epilogue: TMEM -> (+bias, ReLU) -> bf16 -> horizontal 3-max in registers ->
-        //       half-width rows in a smem ring -> vertical 3-max -> NHWC [n][56][56][64] =====
-        // Sixteen warps work on the same M-tile (four per TMEM lane quarter, 16 channels each: the stem has
-        // only 16 MMAs per 128 x 64 outputs, so its epilogue must be wide to keep up); a lane owns conv pixel x
-        // of conv row i (m = i*P + x, lanes are consecutive x).  The horizontal max over x-1, x, x+1 (kept for
-        // even x = 2*pw) comes from the neighbouring lanes by shuffle; the neighbour of lane 0 lives in the
-        // previous warp / M-tile and arrives through a 32-byte mailbox.  Ring slot i % 6 holds the
-        // horizontally pooled conv row i as [pw][64 ch] (16-byte chunk index XOR-swizzled by pw).  Pooled row j
-        // of the tile = max over ring rows 2j, 2j+1, 2j+2, emitted right after the M-tile that completes row
-        // 2j+2.  Conv row -1 (first band) and the junk columns x >= W are zeros: neutral for a max over
-        // post-ReLU values (the reference pads with -inf).
-        constexpr int kRing = 6;
+    } else if (warp >= 4 && warp < 12 && POOL) {
+        // ===== pooled-stem epilogue, stage 1: TMEM -> (+bias, ReLU) -> bf16 conv rows in a smem ring =====
+        // Two groups of four warps take alternate M-tiles and never synchronise with each other.  Conv
+        // row number `gr` (counted over the whole CTA: 9 per work tile) lives in ring slot gr % kRing as
+        // [x][64 ch] (16-byte chunk index XOR-swizzled by x).  Conv row -1 (first band of an image) is
+        // stored as zeros: neutral for a max over post-ReLU values (the reference pads with -inf).
+        // A row slot may be overwritten once the pool warps have released row gr - kRing (rows_released).
         const int q = warp & 3;
-        const int cq = (warp - 4) >> 2;    // 16-channel group 0..3
-        const int te = threadIdx.x - 128;  // 0..511
+        const int grp = (warp - 4) >> 2;
         const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
-        const int Wc = p.W, Wp = p.W >> 1, Hp = p.H >> 1;
-        const uint32_t row_bytes = (uint32_t)Wp * 128;
-        const uint32_t mbox0 = stage0 + kRing * row_bytes;  // [3][4 quarters][4 channel groups][32 B]
+        volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        const uint32_t row_bytes = (uint32_t)p.W * 128;
+        const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
         uint32_t g = 0;
-        for (int w = w_first; w < w_last; ++w) {
+        int tile_idx = 0;
+        for (int w = w_first; w < w_last; ++w, ++tile_idx) {
             const int img = w / p.tiles_per_img;
-            const int t = w - img * p.tiles_per_img;
-            const int y0 = t * p.rstep + p.yfirst;
-            const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
+            const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             for (int mt = 0; mt < n_mt; ++mt, ++g) {
+                if ((int)(g & 1) != grp) continue;
                 const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
-                mbar_wait(tfull0 + 8 * slot, use & 1);
-                tc_fence_after();
-                uint32_t v[16];
-                tmem_ld16(tmem_base + slot * 64 + cq * 16 + ((uint32_t)(q * 32) << 16), v);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(tempty0 + 8 * slot);
                 const int m = mt * 128 + q * 32 + lane;
                 const int i = m / p.P, x = m - i * p.P;
-                const bool live = x < Wc && i < p.R && y0 + i >= 0;
-                unsigned c[8];
+                const bool valid = x < p.W && i < p.R;
+                const int gr = tile_idx * p.R + i;  // CTA-wide conv row number
+                if (valid) {
+                    while (*rows_released < gr - kPoolRing + 1) __nanosleep(64);
+                }
+                __syncwarp();
+                mbar_wait(tfull0 + 8 * slot, use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + slot * 64 + ((uint32_t)(q * 32) << 16);
+                const uint32_t srow = stage0 + (uint32_t)(gr % kPoolRing) * row_bytes + (uint32_t)x * 128;
+                const bool keep = y0 + i >= 0;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cq * 16 + j * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cq * 16 + j * 8 + 4);
-                    const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
-                                        __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
-                                        __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
-                                        __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
-                        c[4 * j + k] = live ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + h * 32, v);
+                    tmem_ld_wait();
+                    if (h == 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty0 + 8 * slot);
                     }
-                }
-                // hand the last lane's pixel to the next warp / M-tile
-                const uint32_t mb_mine = mbox0 + (((g % 3) * 4 + q) * 4 + cq) * 32;
-                if (lane == 31) {
-                    sts128(mb_mine, make_uint4(c[0], c[1], c[2], c[3]));
-                    sts128(mb_mine + 16, make_uint4(c[4], c[5], c[6], c[7]));
-                }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                unsigned hm[8];
-                {
-                    const uint32_t mb_left = q > 0 ? mb_mine - 128 : mbox0 + ((((g + 2) % 3) * 4 + 3) * 4 + cq) * 32;
-                    uint4 lv[2];
-                    const bool need_box = lane == 0 && x > 0 && (q > 0 || mt > 0);
-                    lv[0] = need_box ? lds128(mb_left) : make_uint4(0, 0, 0, 0);
-                    lv[1] = need_box ? lds128(mb_left + 16) : make_uint4(0, 0, 0, 0);
+                    if (valid) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        unsigned l = __shfl_up_sync(0xffffffffu, c[k], 1);
-                        const unsigned r = __shfl_down_sync(0xffffffffu, c[k], 1);
-                        if (lane == 0) l = (&lv[k >> 2].x)[k & 3];
-                        if (x == 0) l = 0u;  // row start: nothing to the left
-                        const __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&l), *reinterpret_cast<const __nv_bfloat162*>(&c[k]));
-                        const __nv_bfloat162 b2 = __hmax2(a2, *reinterpret_cast<const __nv_bfloat162*>(&r));
-                        hm[k] = *reinterpret_cast<const unsigned*>(&b2);
-                    }
-                }
-                if (x < Wc && i < p.R && (x & 1) == 0) {
-                    const int pw = x >> 1;
-                    const uint32_t srow = stage0 + (uint32_t)(i % kRing) * row_bytes + (uint32_t)pw * 128;
-                    sts128(srow + (((cq * 2) ^ (pw & 7)) << 4), make_uint4(hm[0], hm[1], hm[2], hm[3]));
-                    sts128(srow + (((cq * 2 + 1) ^ (pw & 7)) << 4), make_uint4(hm[4], hm[5], hm[6], hm[7]));
-                }
-                // which pooled row (if any) does this M-tile complete?  row 2j+2 ends at flat index (2j+2)*P + W - 1
-                int jdone = -1;
-                for (int j = 0; 2 * j + 2 < p.R; ++j)
-                    if (((2 * j + 2) * p.P + Wc - 1) / 128 == mt) jdone = j;
-                if (jdone >= 0) {
-                    asm volatile("bar.sync 2, 512;" ::: "memory");
-                    const int prow = (y0 + 1) / 2 + jdone;  // pooled row index in the image
-                    const uint32_t r0 = stage0 + (uint32_t)((2 * jdone) % kRing) * row_bytes;
-                    const uint32_t r1 = stage0 + (uint32_t)((2 * jdone + 1) % kRing) * row_bytes;
-                    const uint32_t r2 = stage0 + (uint32_t)((2 * jdone + 2) % kRing) * row_bytes;
-                    for (int item = te; item < Wp * 8; item += 512) {
-                        const int pw = item >> 3, ch = item & 7;
-                        const uint32_t off = (uint32_t)pw * 128 + ((ch ^ (pw & 7)) << 4);
-                        const uint4 a = lds128(r0 + off), bq = lds128(r1 + off), cq4 = lds128(r2 + off);
-                        uint4 o;
-                        const unsigned* au = &a.x;
-                        const unsigned* bu = &bq.x;
-                        const unsigned* cu = &cq4.x;
-                        unsigned* ou = &o.x;
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
+                            const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                                __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                                __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                                __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                            uint4 o;
+                            unsigned* ou = &o.x;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __nv_bfloat162 mx = __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&au[k]),
-                                                                      *reinterpret_cast<const __nv_bfloat162*>(&bu[k])),
-                                                              *reinterpret_cast<const __nv_bfloat162*>(&cu[k]));
-                            ou[k] = *reinterpret_cast<const unsigned*>(&mx);
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
+                                ou[k] = keep ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
+                            }
+                            sts128(srow + (((h * 4 + j) ^ (x & 7)) << 4), o);
                         }
-                        if (prow < Hp) *reinterpret_cast<uint4*>(p.out + (((size_t)img * Hp + prow) * Wp + pw) * 64 + ch * 8) = o;
+                    }
+                }
+                // this group's 128 threads have written their rows of M-tile g
+                mbar_arrive(mdone0 + 8 * slot);
+            }
+        }
+    } else if (warp >= 12 && POOL) {
+        // ===== pooled-stem epilogue, stage 2: 3x3 / stride-2 / pad-1 max over the ring -> NHWC [n][56][56][64] =====
+        // Eight pool warps walk the M-tiles in order (mdone barriers), emit pooled row j of a tile as soon as
+        // the M-tile that completes conv row 2j+2 is in the ring, then release the rows nobody needs any more.
+        const int te = threadIdx.x - 12 * 32;  // 0..255
+        volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        const int Wc = p.W, Wp = p.W >> 1, Hp = p.H >> 1;
+        const uint32_t row_bytes = (uint32_t)Wc * 128;
+        const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
+        uint32_t g = 0;
+        int tile_idx = 0;
+        for (int w = w_first; w < w_last; ++w, ++tile_idx) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
+            int jnext = 0;
+            for (int mt = 0; mt < n_mt; ++mt, ++g) {
+                const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+                mbar_wait(mdone0 + 8 * slot, use & 1);
+                // pooled rows whose last conv row (2j+2) ends inside this M-tile
+                while (2 * jnext + 2 < p.R && ((2 * jnext + 2) * p.P + Wc - 1) / 128 <= mt) {
+                    const int j = jnext++;
+                    const int prow = (y0 + 1) / 2 + j;
+                    const int gr0 = tile_idx * p.R + 2 * j;
+                    const uint32_t r0 = stage0 + (uint32_t)(gr0 % kPoolRing) * row_bytes;
+                    const uint32_t r1 = stage0 + (uint32_t)((gr0 + 1) % kPoolRing) * row_bytes;
+                    const uint32_t r2 = stage0 + (uint32_t)((gr0 + 2) % kPoolRing) * row_bytes;
+                    for (int item = te; item < Wp * 8; item += 256) {
+                        const int pw = item >> 3, ch = item & 7;
+                        __nv_bfloat162 acc[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int xx = 2 * pw + dx;
+                            if (xx >= 0) {
+                                const uint32_t off = (uint32_t)xx * 128 + ((ch ^ (xx & 7)) << 4);
+                                const uint4 a = lds128(r0 + off), bq = lds128(r1 + off), cq = lds128(r2 + off);
+                                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                                const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&bq);
+                                const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&cq);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], __hmax2(ha[k], __hmax2(hb[k], hc[k])));
+                            }
+                        }
+                        if (prow < Hp)
+                            *reinterpret_cast<uint4*>(p.out + (((size_t)img * Hp + prow) * Wp + pw) * 64 + ch * 8) =
+                                *reinterpret_cast<const uint4*>(acc);
+                    }
+                    // rows gr0 and gr0+1 are not needed by later pooled rows (row gr0+2 is: it is row 2(j+1))
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (te == 0) {
+                        const bool last = 2 * (j + 1) + 2 >= p.R;  // last pooled row of the tile: its third row is free too
+                        *rows_released = gr0 + (last ? 3 : 2);
                     }
                 }
             }
@@ -736,7 +749,7 @@ static int plan_flat(FlatParams& p, bool pool = false) {
     if (n_mt_max > kFlatSlots && p.chunks > 1) return 0;  // multi-chunk tiles keep all their accumulators live
     const int reach_rows = n_mt_max * 128 + (KH - 1) * p.P + (KW - 1);  // rows a (junk) view may touch
     p.slack_bytes = (std::max(0, reach_rows * ROWB - p.stage_bytes) + 1023) & ~1023;
-    const int bar_bytes = 8 * (2 * 8 + 2 * kFlatSlots + 2) + 64;
+    const int bar_bytes = 8 * (2 * 8 + 3 * kFlatSlots + 2) + 64;
     const int fixed = 1024 + p.w_bytes + p.slack_bytes + (pool ? kPoolRingBytes + 256 : kEpiBytes) + bar_bytes;
     p.nstages = std::min(p.chunks > 1 ? 4 : 6, (kSmemMax - fixed) / p.stage_bytes);
     if (p.nstages < 2) return 0;
