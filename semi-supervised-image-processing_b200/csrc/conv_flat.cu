@@ -172,14 +172,20 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t a_lo_stage = (sA + stage * p.stage_bytes) >> 4;
-                for (int mt = 0; mt < n_mt; ++mt) {
-                    const uint32_t g = g_base + mt, slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+                // M-tiles are issued in PAIRS with the taps interleaved (tap-outer, M-tile-inner): back-to-back
+                // MMAs into one accumulator run at 56-72 cycles, alternating accumulators at the 48-cycle
+                // operand-fetch floor (profiles/r01_mma_ws_and_accumulator_probe.log).
+                for (int mt = 0; mt < n_mt; mt += 2) {
+                    const bool two = mt + 1 < n_mt;
+                    const uint32_t g0 = g_base + mt, slot0 = g0 & (kFlatSlots - 1), use0 = g0 / kFlatSlots;
+                    const uint32_t g1 = g0 + 1, slot1 = g1 & (kFlatSlots - 1), use1 = g1 / kFlatSlots;
                     if (c == 0) {
-                        mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
+                        mbar_wait(tempty0 + 8 * slot0, (use0 & 1) ^ 1);
+                        if (two) mbar_wait(tempty0 + 8 * slot1, (use1 & 1) ^ 1);
                         tc_fence_after();
                     }
                     if (elect_one_sync()) {
-                        const uint32_t d = tmem_base + slot * 64;
+                        const uint32_t d0 = tmem_base + slot0 * 64, d1 = tmem_base + slot1 * 64;
                         const uint32_t a_lo_mt = a_lo_stage + (uint32_t)(mt * 128) * row_units;
                         const uint32_t b_lo_c = w_lo + (uint32_t)c * (WTILE / 16);
 #pragma unroll
@@ -189,10 +195,18 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             const uint32_t b_lo = b_lo_c + (uint32_t)(tap * p.chunks) * (WTILE / 16);
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k)
-                                umma_bf16(d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
-                                          (c | tap | k) != 0);
+                                umma_bf16(d0, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (c | tap | k) != 0);
+                            if (two) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k)
+                                    umma_bf16(d1, desc_hi | (uint64_t)(a_lo + 128 * row_units + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                                              (c | tap | k) != 0);
+                            }
                         }
-                        if (c == p.chunks - 1) umma_commit(tfull0 + 8 * slot);
+                        if (c == p.chunks - 1) {
+                            umma_commit(tfull0 + 8 * slot0);
+                            if (two) umma_commit(tfull0 + 8 * slot1);
+                        }
                     }
                     __syncwarp();
                 }

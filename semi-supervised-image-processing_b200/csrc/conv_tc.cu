@@ -279,6 +279,8 @@ __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap map, int c0
 __global__ void __launch_bounds__(128, 1)
 umma_shift_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int kb_elems,
                         int shift_rows, int base_offset, int layout_code, float* out) {
+    const int ws_mode = base_offset >= 100;  // test hook: base_offset 100 = weight-stationary MMA with base offset 0
+    if (ws_mode) base_offset = 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int rowbytes = kb_elems * 2;
@@ -307,7 +309,11 @@ umma_shift_probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const uint64_t da = (uint64_t)(((sA + shift_rows * rowbytes) >> 4) & 0x3FFF) | hi;
         const uint64_t db = (uint64_t)((sB >> 4) & 0x3FFF) | (sbo << 32) | (1ull << 46) | ((uint64_t)layout_code << 61);
         constexpr uint32_t idesc = make_idesc<64>();
-        for (int k = 0; k < kb_elems / 16; ++k) umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0);
+        if (ws_mode) {  // weight-stationary form, every B slice latched in collector b0 and used once
+            for (int k = 0; k < kb_elems / 16; ++k) umma_ws_b0_fill(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0);
+        } else {
+            for (int k = 0; k < kb_elems / 16; ++k) umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0);
+        }
         umma_commit(bar1);
     }
     __syncwarp();
@@ -478,7 +484,7 @@ int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uin
 // ------------------------------------------------------------------------------------------
 template <int ROWB, int NACC>
 __global__ void __launch_bounds__(128, 1)
-mma_rate_kernel(int n_cols, int shift_rows, int tap_stride_rows, int iters, float* cycles_per_mma) {
+mma_rate_kernel(int n_cols, int shift_rows, int tap_stride_rows, int iters, int ws_reuse, float* cycles_per_mma) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = sbase, sB = sbase + 96 * 1024;
@@ -512,10 +518,33 @@ mma_rate_kernel(int n_cols, int shift_rows, int tap_stride_rows, int iters, floa
             for (int it = 0; it < rounds; ++it) {
 #pragma unroll
                 for (int tap = 0; tap < 8; ++tap) {
-                    const uint32_t d = tmem_base + (uint32_t)(tap % NACC) * (uint32_t)n_cols;
+                    if (ws_reuse == 0) {
+                        const uint32_t d = tmem_base + (uint32_t)(tap % NACC) * (uint32_t)n_cols;
 #pragma unroll
-                    for (int k = 0; k < KSTEPS; ++k)
-                        umma_bf16(d, hi | (uint64_t)(a0 + tap * astep + 2 * k), hi | (uint64_t)(b0 + tap * bstep + 2 * k), idesc, 1);
+                        for (int k = 0; k < KSTEPS; ++k)
+                            umma_bf16(d, hi | (uint64_t)(a0 + tap * astep + 2 * k), hi | (uint64_t)(b0 + tap * bstep + 2 * k), idesc, 1);
+                    } else {
+                        // weight-stationary: B slice k of a tap is latched in collector b<k> by the first
+                        // accumulator and re-used by the other NACC-1 (same B, different A rows and D)
+                        if constexpr (KSTEPS <= 4) {
+#pragma unroll
+                            for (int acc = 0; acc < NACC; ++acc) {
+                                const uint32_t d = tmem_base + (uint32_t)acc * (uint32_t)n_cols;
+                                const uint32_t a_lo = a0 + tap * astep + acc * 128 * (ROWB / 16);
+                                if (acc == 0 || ws_reuse == 1) {
+                                    umma_ws<0, true>(d, hi | (uint64_t)(a_lo), hi | (uint64_t)(b0 + tap * bstep), idesc, 1);
+                                    if (KSTEPS > 1) umma_ws<1, true>(d, hi | (uint64_t)(a_lo + 2), hi | (uint64_t)(b0 + tap * bstep + 2), idesc, 1);
+                                    if (KSTEPS > 2) umma_ws<2, true>(d, hi | (uint64_t)(a_lo + 4), hi | (uint64_t)(b0 + tap * bstep + 4), idesc, 1);
+                                    if (KSTEPS > 2) umma_ws<3, true>(d, hi | (uint64_t)(a_lo + 6), hi | (uint64_t)(b0 + tap * bstep + 6), idesc, 1);
+                                } else {
+                                    umma_ws<0, false>(d, hi | (uint64_t)(a_lo), hi | (uint64_t)(b0 + tap * bstep), idesc, 1);
+                                    if (KSTEPS > 1) umma_ws<1, false>(d, hi | (uint64_t)(a_lo + 2), hi | (uint64_t)(b0 + tap * bstep + 2), idesc, 1);
+                                    if (KSTEPS > 2) umma_ws<2, false>(d, hi | (uint64_t)(a_lo + 4), hi | (uint64_t)(b0 + tap * bstep + 4), idesc, 1);
+                                    if (KSTEPS > 2) umma_ws<3, false>(d, hi | (uint64_t)(a_lo + 6), hi | (uint64_t)(b0 + tap * bstep + 6), idesc, 1);
+                                }
+                            }
+                        }
+                    }
                 }
             }
             umma_commit(bar);
@@ -523,7 +552,7 @@ mma_rate_kernel(int n_cols, int shift_rows, int tap_stride_rows, int iters, floa
         __syncwarp();
         mbar_wait(bar, 0);
         t1 = clock64();
-        if (elect_one_sync()) cycles_per_mma[blockIdx.x] = (float)(t1 - t0) / (float)(rounds * 8 * KSTEPS);
+        if (elect_one_sync()) cycles_per_mma[blockIdx.x] = (float)(t1 - t0) / (float)(rounds * 8 * KSTEPS * (ws_reuse ? NACC : 1));
     }
     tc_fence_before();
     __syncthreads();
@@ -534,33 +563,36 @@ mma_rate_kernel(int n_cols, int shift_rows, int tap_stride_rows, int iters, floa
 }
 
 template <int ROWB>
-static void launch_mma_rate(int nacc, int grid, int smem, cudaStream_t stream, int n_cols, int shift_rows, int ts, int iters, float* out) {
+static void launch_mma_rate(int nacc, int grid, int smem, cudaStream_t stream, int n_cols, int shift_rows, int ts, int iters, int ws, float* out) {
     cudaFuncSetAttribute(mma_rate_kernel<ROWB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(mma_rate_kernel<ROWB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(mma_rate_kernel<ROWB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (nacc >= 4)
-        mma_rate_kernel<ROWB, 4><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, out);
+        mma_rate_kernel<ROWB, 4><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, ws, out);
     else if (nacc >= 2)
-        mma_rate_kernel<ROWB, 2><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, out);
+        mma_rate_kernel<ROWB, 2><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, ws, out);
     else
-        mma_rate_kernel<ROWB, 1><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, out);
+        mma_rate_kernel<ROWB, 1><<<grid, 128, smem, stream>>>(n_cols, shift_rows, ts, iters, ws, out);
 }
 
 // tap_stride_rows >= 1000 encodes "round-robin over (tap_stride_rows / 1000) accumulators".
 int tc_mma_rate(fx_engine* e, int n_cols, int rowb, int shift_rows, int tap_stride_rows, int iters, float* out_dev, cudaStream_t stream) {
+    // encoding of tap_stride_rows: + 1000 * accumulators + 100000 * ws (1: weight-stationary, refill every MMA; 2: fill once, re-use)
+    const int ws = tap_stride_rows / 100000;
+    tap_stride_rows %= 100000;
     const int nacc = std::max(1, tap_stride_rows / 1000);
     tap_stride_rows %= 1000;
     if ((n_cols != 64 && n_cols != 128 && n_cols != 256) || (rowb != 128 && rowb != 64 && rowb != 32))
         return set_error(e, FX_ERR_INVALID, "mma_rate: N must be 64/128/256 and rowb 128/64/32");
-    if (shift_rows < 0 || tap_stride_rows < 0 || (shift_rows + 7 * tap_stride_rows + 128) * rowb > 96 * 1024 || nacc * n_cols > 512)
+    if (shift_rows < 0 || tap_stride_rows < 0 || (shift_rows + 7 * tap_stride_rows + 128 * (ws ? nacc : 1)) * rowb > 96 * 1024 || nacc * n_cols > 512)
         return set_error(e, FX_ERR_INVALID, "mma_rate: views leave the shared-memory tile");
     const int smem = 1024 + 160 * 1024 + 64;
     if (rowb == 128)
-        launch_mma_rate<128>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, out_dev);
+        launch_mma_rate<128>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, ws, out_dev);
     else if (rowb == 64)
-        launch_mma_rate<64>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, out_dev);
+        launch_mma_rate<64>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, ws, out_dev);
     else
-        launch_mma_rate<32>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, out_dev);
+        launch_mma_rate<32>(nacc, e->sm_count, smem, stream, n_cols, shift_rows, tap_stride_rows, iters, ws, out_dev);
     FX_LAUNCH_CHECK(e, "mma_rate_kernel");
     return FX_OK;
 }
@@ -570,6 +602,7 @@ int tc_umma_shift_probe(fx_engine* e, const void* a_dev, const void* b_dev, int 
                         float* out_dev, cudaStream_t stream) {
     if (kb_elems != 64 && kb_elems != 32 && kb_elems != 16) return set_error(e, FX_ERR_INVALID, "umma probe: K block must be 64, 32 or 16");
     if (shift_rows < 0 || shift_rows > 128) return set_error(e, FX_ERR_INVALID, "umma probe: shift must be in [0,128]");
+    if (base_offset >= 100 && base_offset != 100) return set_error(e, FX_ERR_INVALID, "umma probe: base_offset 100 selects the weight-stationary form");
     const CUtensorMapSwizzle sw = kb_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kb_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     const int layout_code = kb_elems == 64 ? 2 : kb_elems == 32 ? 4 : 6;
     CUtensorMap ma, mb;

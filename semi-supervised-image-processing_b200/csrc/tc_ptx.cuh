@@ -95,6 +95,36 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Weight-stationary form: the B operand is latched in collector buffer b<ID> (fill) and re-used by later
+// MMAs (use / lastuse) without being fetched from shared memory again.
+#define FX_UMMA_WS(NAME, SUFFIX)                                                                                          \
+    __device__ __forceinline__ void NAME(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) { \
+        asm volatile(                                                                                                     \
+            "{\n\t.reg .pred p;\n\t"                                                                                     \
+            "setp.ne.b32 p, %4, 0;\n\t"                                                                                   \
+            "tcgen05.mma.ws.cta_group::1.kind::f16.collector::" SUFFIX " [%0], %1, %2, %3, p;\n\t}"                        \
+            :                                                                                                             \
+            : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)                                                 \
+            : "memory");                                                                                                  \
+    }
+FX_UMMA_WS(umma_ws_b0_fill, "b0::fill")
+FX_UMMA_WS(umma_ws_b1_fill, "b1::fill")
+FX_UMMA_WS(umma_ws_b2_fill, "b2::fill")
+FX_UMMA_WS(umma_ws_b3_fill, "b3::fill")
+FX_UMMA_WS(umma_ws_b0_use, "b0::use")
+FX_UMMA_WS(umma_ws_b1_use, "b1::use")
+FX_UMMA_WS(umma_ws_b2_use, "b2::use")
+FX_UMMA_WS(umma_ws_b3_use, "b3::use")
+FX_UMMA_WS(umma_ws_b0_discard, "b0::discard")
+#undef FX_UMMA_WS
+template <int ID, bool FILL>
+__device__ __forceinline__ void umma_ws(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (ID == 0) FILL ? umma_ws_b0_fill(d, da, db, idesc, acc) : umma_ws_b0_use(d, da, db, idesc, acc);
+    if (ID == 1) FILL ? umma_ws_b1_fill(d, da, db, idesc, acc) : umma_ws_b1_use(d, da, db, idesc, acc);
+    if (ID == 2) FILL ? umma_ws_b2_fill(d, da, db, idesc, acc) : umma_ws_b2_use(d, da, db, idesc, acc);
+    if (ID == 3) FILL ? umma_ws_b3_fill(d, da, db, idesc, acc) : umma_ws_b3_use(d, da, db, idesc, acc);
+}
+
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
