@@ -45,6 +45,37 @@ TRUNK_FLOP_PER_IMAGE = 2 * 1_813_561_344  # 1.8136 GMAC, 2 FLOP/
 PRE_BYTES_BF16 = IMG_BYTES + 224 * 224 * 3 * 2  # source read once + bf16 NHWC(3) written once
 WEIGHT_SEED = 1234
 
+# MACs per image of the 20 conv groups in fx_load_weights order and the kernel family that runs each
+_M = 115_605_504
+LAYER_MACS = [118_013_952, _M, _M, _M, _M, _M // 2, _M, 6_422_528, _M, _M, _M // 2, _M, 6_422_528, _M, _M, _M // 2, _M, 6_422_528, _M, _M]
+assert sum(LAYER_MACS) == 1_813_561_344
+LAYER_FAMILY = (["flat_conv_kernel<32,4,4,pool> (stem conv1+bn+relu+maxpool, s2d 4x4, N=64)"] + ["flat_conv_kernel<128,3,3> (layer1 3x3/s1, N=64)"] * 4 +
+                ["tc_conv_kernel (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128_conv_kernel (layer2 3x3/s1, N=128)",
+                 "tc_conv_kernel (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128_conv_kernel (layer2 3x3/s1, N=128)",
+                 "flat128_conv_kernel (layer2 3x3/s1, N=128)"] + ["tc_conv_kernel (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)"] * 10)
+EXEC_ORDER = [0, 1, 2, 3, 4, 5, 7, 6, 8, 9, 10, 12, 11, 13, 14, 15, 17, 16, 18, 19]  # launch order of the slots inside fx_forward
+LAUNCH_PROFILE = ROOT / "profiles" / "r01_launches_v5.csv"  # ncu launch list (batch 256) used for the DRAM-traffic column
+
+
+def profiled_traffic():
+    """DRAM bytes (read + write) per launch from the committed ncu launch list: {slot: bytes}, {'preprocess': bytes}."""
+    import csv
+
+    if not LAUNCH_PROFILE.exists():
+        return None
+    rows = list(csv.DictReader(l for l in open(LAUNCH_PROFILE) if not l.startswith("==")))
+    per_id = {}
+    for r in rows:
+        if r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            per_id.setdefault(r["ID"], [r["Kernel Name"], 0.0])[1] += float(r["Metric Value"].replace(",", ""))
+    launches = list(per_id.values())
+    if len(launches) != 22 or "preprocess" not in launches[0][0]:
+        return None
+    out = {"preprocess": launches[0][1]}
+    for k, slot in enumerate(EXEC_ORDER):
+        out[slot] = launches[1 + k][1]
+    return out
+
 
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -298,10 +329,12 @@ def main():
     ms_max = float(t.item())
     value = world * K * B / (ms_max / 1e3)
 
-    # ---- per-kernel-family timing (separate pass, same stream, CUDA events) ----------------------
+    # ---- per-launch timing (separate pass, same stream, CUDA events inside the library: fx_profile_*) ----
     k_prof = min(K, 30)
     pre_ms, trunk_ms = [], []
+    layer_ms = np.zeros(21, np.float64)
     emb = scratch[:B]
+    eng.profile(True)
     for i in range(k_prof):
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         src = batch_view(W + K + i)
@@ -313,10 +346,31 @@ def main():
         c.synchronize()
         pre_ms.append(a.elapsed_time(b))
         trunk_ms.append(b.elapsed_time(c))
+        layer_ms += eng.profile_read()
+    eng.profile(False)
+    layer_ms /= k_prof
     pre_avg, trunk_avg = statistics.mean(pre_ms), statistics.mean(trunk_ms)
     peaks = load_peaks()
     tf = TRUNK_FLOP_PER_IMAGE * B / (trunk_avg / 1e3) / 1e12
     gbs = PRE_BYTES_BF16 * B / (pre_avg / 1e3) / 1e9
+    traffic = profiled_traffic() if B == 256 and args.precision == "bf16" else None
+    families = {}
+    for slot in range(20):
+        f = families.setdefault(LAYER_FAMILY[slot], {"launches": 0, "ms": 0.0, "flop": 0.0, "traffic": 0.0})
+        f["launches"] += 1
+        f["ms"] += float(layer_ms[slot])
+        f["flop"] += 2.0 * LAYER_MACS[slot] * B
+        if traffic:
+            f["traffic"] += traffic[slot]
+    kernels = []
+    for name, f in families.items():
+        ach = f["flop"] / (f["ms"] / 1e3) / 1e12
+        kernels.append({"kernel": name, "launches_per_step": f["launches"], "avg_launch_ms": f["ms"] / f["launches"],
+                        "share_of_trunk": f["ms"] / float(layer_ms.sum()), "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"],
+                        "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"], "flop_per_launch": f["flop"] / f["launches"],
+                        "traffic": (f["traffic"] / f["launches"]) if traffic else None})
+    kernels.sort(key=lambda k: -k["share_of_trunk"])
+    dominant = kernels[0]
 
     # ---- e2e: host buffers through fx_embed_host ---------------------------------------------------
     k_e2e = min(K, 50)
@@ -359,13 +413,20 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_BYTES, "d2h_bytes_per_step": B * 512 * 4,
                     "steps": k_e2e, "api": "fx_embed_host_async/wait, 2 slots (pinned host uint8 in, host fp32 [B,512] out)"},
             "gpu_launches": int(launches * world),
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["tf_sustained"], "traffic": None,
-                         "kernel": "tc_conv_kernel family (20 implicit-GEMM launches + maxpool/avgpool) per batch",
-                         "flop_per_image": TRUNK_FLOP_PER_IMAGE, "avg_ms": trunk_avg, "peak_src": peaks["src"] + " sustained bf16",
-                         "frac_of_burst_peak": tf / peaks["tf_burst"]},
+            # dominant kernel family of the step (largest share of device time), timed per launch by CUDA events
+            "roofline": {"bound": "tensor", "achieved": dominant["achieved"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": dominant["frac"], "traffic": dominant["traffic"], "kernel": dominant["kernel"],
+                         "flop_per_launch": dominant["flop_per_launch"], "avg_launch_ms": dominant["avg_launch_ms"],
+                         "launches_per_step": dominant["launches_per_step"], "share_of_trunk": dominant["share_of_trunk"],
+                         "peak_src": peaks["src"] + " sustained bf16 (kernel timed inside a long step)",
+                         "traffic_src": str(LAUNCH_PROFILE.relative_to(ROOT)) if dominant["traffic"] else None},
+            "roofline_trunk": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                               "frac": tf / peaks["tf_sustained"], "frac_of_burst_peak": tf / peaks["tf_burst"],
+                               "kernel": "whole trunk: 20 conv launches + avgpool per batch", "flop_per_image": TRUNK_FLOP_PER_IMAGE,
+                               "avg_ms": trunk_avg},
+            "roofline_kernels": kernels,
             "roofline_preprocess": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                                    "traffic": None, "kernel": "preprocess_kernel<bf16 staging>", "bytes_per_image": PRE_BYTES_BF16,
+                                    "traffic": traffic["preprocess"] if traffic else None, "kernel": "preprocess_kernel<bf16 staging>", "bytes_per_image": PRE_BYTES_BF16,
                                     "avg_ms": pre_avg, "peak_src": peaks["src"]},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,

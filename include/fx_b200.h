@@ -164,6 +164,15 @@ int fx_embed_host_wait(fx_handle h, int slot);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 uint64_t fx_launch_count(fx_handle h);
 
+/*
+ * Per-launch timing of fx_forward for roofline reporting: with profiling enabled every launch of the
+ * trunk is bracketed by CUDA events on the launching stream.  fx_profile_read waits for the last
+ * fx_forward and returns milliseconds for slots 0..19 = the conv groups in fx_load_weights order
+ * (slot 0 = fused stem incl. max-pool) and slot 20 = global average pool.  capacity >= 21.
+ */
+int fx_profile_enable(fx_handle h, int on);
+int fx_profile_read(fx_handle h, float *ms, int capacity);
+
 /* ---- test / inspection entry points (used by tests/ for per-layer parity) ---- */
 
 /*

@@ -121,9 +121,23 @@ static int pack_layer(fx_engine* e, const fx_conv_bn& src, int hin, int win, Pac
     return FX_OK;
 }
 
+// fx_profile_*: bracket launch `slot` (conv layer index, or 20 = avgpool) with events on the launching stream.
+struct ProfScope {
+    fx_engine* e;
+    int slot;
+    cudaStream_t s;
+    ProfScope(fx_engine* e_, int slot_, cudaStream_t s_) : e(e_), slot(slot_), s(s_) {
+        if (e->prof_on) cudaEventRecord(e->prof_ev[2 * slot], s);
+    }
+    ~ProfScope() {
+        if (e->prof_on) cudaEventRecord(e->prof_ev[2 * slot + 1], s);
+    }
+};
+
 // One conv layer on NHWC activations in the engine's precision.  Layer 0 reads the staging tensor.
 static int run_conv(fx_engine* e, int li, const void* in, const void* residual, void* out, float* out_f32, int n, int relu,
                     cudaStream_t stream) {
+    ProfScope ps(e, li, stream);
     const PackedLayer& L = e->layers[li];
     if (e->precision == FX_PRECISION_BF16) {
         if (!out_f32 && flat_supported(L.g))
@@ -147,10 +161,12 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
     int rc;
     // stem: conv1+bn1+relu -> maxpool            (resnet.py:268-271)
     if (bf16) {  // one kernel: the max-pool runs in the conv epilogue
+        ProfScope ps(e, 0, stream);
         if ((rc = flat_conv(e, e->layers[0], static_cast<const __nv_bfloat16*>(e->in0), nullptr, static_cast<__nv_bfloat16*>(A), n, 1,
                             true, stream)) != FX_OK)
             return rc;
     } else {
+        ProfScope ps(e, 0, stream);
         if ((rc = run_conv(e, 0, e->in0, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
         if ((rc = maxpool_3x3s2(e, B, A, n, 112, 112, 64, bf16, stream)) != FX_OK) return rc;
     }
@@ -175,6 +191,7 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
             }
         }
     // avgpool + flatten                         (resnet.py:278-279; src/feature_extraction.py:293)
+    ProfScope ps(e, kNumLayers, stream);
     return avgpool_7x7(e, e->final_f32, false, emb, n, 49, kEmbed, stream);
 }
 
@@ -210,6 +227,8 @@ void fx_destroy(fx_handle e) {
         if (hs.done) cudaEventDestroy(hs.done);
     }
     cudaFree(e->emb_dev);
+    for (auto& ev : e->prof_ev)
+        if (ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
@@ -406,6 +425,27 @@ int fx_embed_host(fx_handle e, const uint8_t* src_host, size_t total_bytes, cons
 }
 
 uint64_t fx_launch_count(fx_handle e) { return e ? e->launches : 0; }
+
+int fx_profile_enable(fx_handle e, int on) {
+    if (!e) return FX_ERR_INVALID;
+    FX_CUDA(e, cudaSetDevice(e->device));
+    if (on && !e->prof_ev[0])
+        for (auto& ev : e->prof_ev) FX_CUDA(e, cudaEventCreate(&ev));
+    e->prof_on = on != 0;
+    return FX_OK;
+}
+
+int fx_profile_read(fx_handle e, float* ms, int capacity) {
+    if (!e) return FX_ERR_INVALID;
+    if (!ms || capacity < kNumLayers + 1 || !e->prof_ev[0]) return set_error(e, FX_ERR_INVALID, "fx_profile_read: profiling was never enabled / buffer too small");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    for (int i = 0; i <= kNumLayers; ++i) {
+        ms[i] = 0.f;
+        if (cudaEventSynchronize(e->prof_ev[2 * i + 1]) == cudaSuccess) cudaEventElapsedTime(&ms[i], e->prof_ev[2 * i], e->prof_ev[2 * i + 1]);
+    }
+    cudaGetLastError();  // an unrecorded slot reports an error we do not care about
+    return FX_OK;
+}
 
 // ---- test / inspection entry points -------------------------------------------------------
 

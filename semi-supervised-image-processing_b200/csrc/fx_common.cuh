@@ -113,6 +113,10 @@ struct fx_engine {
     size_t act_bytes = 0;
     void* tc_state = nullptr;  // tcgen05 path: tensor maps etc. (conv_tc.cu)
 
+    // per-launch timing of fx_forward (fx_profile_*): event pairs for the 20 convs + avgpool
+    bool prof_on = false;
+    cudaEvent_t prof_ev[2 * (FX_NUM_CONV_LAYERS + 1)] = {};
+
     // host-buffer path (fx_embed_host*): two pipelined slots
     struct HostSlot {
         uint8_t* src_dev = nullptr;

@@ -100,6 +100,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.fx_launch_count(self._h))
 
+    def profile(self, on: bool) -> None:
+        """Bracket every trunk launch of forward() with CUDA events (fx_profile_enable)."""
+        self._check(self._lib.fx_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> np.ndarray:
+        """ms per launch of the last forward(): [0..19] conv groups in LAYER_TABLE order (0 = fused stem), [20] avgpool."""
+        ms = np.zeros(N.NUM_CONV_LAYERS + 1, np.float32)
+        self._check(self._lib.fx_profile_read(self._h, ms.ctypes.data, ms.size))
+        return ms
+
     # -- weights ------------------------------------------------------------------------------
     def load_state_dict(self, state: Dict[str, torch.Tensor]) -> None:
         """Takes a torchvision resnet18 ``state_dict`` (fc.* ignored); BN is folded in the library."""
