@@ -246,6 +246,209 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the Cout >= 256 layers (layer3 / layer4).  Measured: the single-CTA
+// kernel above is bound by L2->SM delivery (~12.4 TB/s chip-wide; a 128 x 256 tile needs 96 B/clk/SM at the
+// tensor floor).  Here two CTAs of a cluster compute one 256 x 256 tile with ONE M=256 MMA stream issued by
+// the even CTA: each CTA loads its own 128 A rows and only HALF of the weight K-block (128 of the 256 Cout
+// rows), so the weight bytes per SM halve (64 B/clk/SM at the floor).  Barriers: the leader's `full`
+// barrier counts the bytes of both CTAs' TMA loads; tcgen05.commit multicasts `empty` / `tmem full` to both.
+// ------------------------------------------------------------------------------------------
+template <int BN, int BK, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
+    constexpr int kA = 128 * BK * 2, kB = (BN / 2) * BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = sbase, sB = sbase + STAGES * kA;
+    const uint32_t bars = sB + STAGES * kB;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t tslot = tempty0 + 16;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    constexpr uint32_t kTmemCols = 2 * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(full0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
+            mbar_init(empty0 + 8 * i, 1);  // multicast commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);                       // multicast commit
+            mbar_init(tempty0 + 8 * i, 2 * (kTcThreads - 128));  // every epilogue thread of both CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tslot, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    const int num_kb = p.kh * p.kw * p.cchunks;
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
+    const int pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles_n;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 A rows + own half of the weight K-block =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = pair; t < pair_tiles; t += n_pairs) {
+                const int n_tile = t % p.n_tiles_n;
+                int m_tile = (t / p.n_tiles_n) * 2 + (int)rank;
+                const int tw = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int th = m_tile % p.tiles_h;
+                const int tg = m_tile / p.tiles_h;  // >= tiles_g for the odd leftover: every load is out of bounds -> zeros
+                const int w0 = (tw << p.wt_log2) * p.cw_mul - p.pad_w;
+                const int h0 = (th << p.ht_log2) * p.ch_mul - p.pad_h;
+                const int n0 = tg << p.nt_log2;
+                int kb = 0;
+                for (int r = 0; r < p.kh; ++r)
+                    for (int s = 0; s < p.kw; ++s)
+                        for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
+                            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                            if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * (kA + kB));
+                            tma_load_4d_2cta(sA + stage * kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                            tma_load_2d_2cta(sB + stage * kB, &map_b, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
+                            if (!leader) mbar_arrive_leader(full0 + 8 * stage);
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int t = pair; t < pair_tiles; t += n_pairs, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t a_lo = (sA + stage * kA) >> 4, b_lo = (sB + stage * kB) >> 4;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (kb | k) != 0);
+                        umma_commit_2cta(empty0 + 8 * stage);
+                        if (kb == num_kb - 1) umma_commit_2cta(tfull0 + 8 * as);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): own 128 accumulator rows -> (+bias, +residual, ReLU) -> global =====
+        const int q = warp & 3;
+        const int cg = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const int wl = row & ((1 << p.wt_log2) - 1);
+        const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
+        const int nl = row >> (p.wt_log2 + p.ht_log2);
+        int it = 0;
+        for (int t = pair; t < pair_tiles; t += n_pairs, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int n_tile = t % p.n_tiles_n;
+            int m_tile = (t / p.n_tiles_n) * 2 + (int)rank;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int tg = m_tile / p.tiles_h;
+            const int ow = (tw << p.wt_log2) + wl, oh = (th << p.ht_log2) + hl, img = (tg << p.nt_log2) + nl;
+            const bool valid = ow < p.wo && oh < p.ho && img < p.batch;
+            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
+            const size_t obase = pix * p.cout + (size_t)n_tile * BN;
+
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = cg * (BN / 4); c0 < (cg + 1) * (BN / 4); c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b = __ldg(bp + j);
+                        f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                    }
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint4 rv = __ldg(rp + j);
+                            const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                f[8 * j + 2 * k] += __uint_as_float(u[k] << 16);
+                                f[8 * j + 2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (p.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 o;
+                            unsigned* u = &o.x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                                u[k] = *reinterpret_cast<const unsigned*>(&h2);
+                            }
+                            op[j] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_leader(tempty0 + 8 * as);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory / barriers stay alive until both CTAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // TMA probe (test entry point): one box load -> shared memory -> global, raw bytes.
 // ------------------------------------------------------------------------------------------
 __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap map, int c0, int c1, int c2, int c3, int bytes,
@@ -367,6 +570,22 @@ static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb,
     return FX_OK;
 }
 
+template <int BN, int BK, int STAGES>
+static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, cudaStream_t stream) {
+    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 16;
+    static bool attr_done[16] = {};
+    if (!attr_done[e->device & 15]) {
+        FX_CUDA(e, cudaFuncSetAttribute(tc2_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_done[e->device & 15] = true;
+    }
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
+    const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
+    const int pairs = std::max(1, std::min(pair_tiles, e->sm_count / 2));
+    tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, p);  // cluster dims are a kernel attribute
+    FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
+    return FX_OK;
+}
+
 int tc_init(fx_engine* e) {
     TcState* st = new TcState();
     e->tc_state = st;
@@ -435,7 +654,7 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
         if (rc != FX_OK) return rc;
         const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
         const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
-        const uint32_t bbox[2] = {64, (uint32_t)bn};
+        const uint32_t bbox[2] = {64, (uint32_t)(bn == 256 ? 128 : bn)};  // the CTA-pair kernel loads half a K-block per CTA
         const uint32_t be[2] = {1, 1};
         rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B");
         if (rc != FX_OK) return rc;
@@ -450,7 +669,7 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     switch (bn) {
         case 64: return launch_tc<64, 64, 8>(e, ma, mb, p, stream);
         case 128: return launch_tc<128, 64, 6>(e, ma, mb, p, stream);
-        default: return launch_tc<256, 64, 4>(e, ma, mb, p, stream);
+        default: return launch_tc2<256, 64, 6>(e, ma, mb, p, stream);
     }
 }
 
