@@ -55,7 +55,8 @@ struct TcSmem {
     static constexpr int kA = 128 * BK * 2;
     static constexpr int kB = BN * BK * 2;
     static constexpr int kBars = (2 * STAGES + 4) * 8;
-    static constexpr int kTotal = 1024 /*align slack*/ + STAGES * (kA + kB) + kBars + 16;
+    static constexpr int kBias = 512 * 4;  // folded-BN bias of every output channel (cout <= 512)
+    static constexpr int kTotal = 1024 /*align slack*/ + STAGES * (kA + kB) + kBars + 16 + kBias;
 };
 
 template <int BN, int BK, int STAGES>
@@ -69,9 +70,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
     const uint32_t tslot = tempty0 + 16;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
+    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) bias_s[i] = __ldg(p.bias + i);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -176,30 +179,40 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
             const size_t obase = pix * p.cout + (size_t)n_tile * BN;
 
+            // the residual does not depend on the accumulator: fetch this thread's BN/4 channels while the MMAs
+            // of the tile are still running, so the load latency is off the epilogue's critical path
+            constexpr int kResVec = BN / 32;  // uint4 (8 bf16) per thread
+            uint4 res[kResVec];
+            const bool has_res = valid && p.residual != nullptr;
+            if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg * (BN / 4));
+#pragma unroll
+                for (int j = 0; j < kResVec; ++j) res[j] = __ldg(rp + j);
+            }
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c0 = cg * (BN / 4); c0 < (cg + 1) * (BN / 4); c0 += 16) {
+#pragma unroll
+            for (int ci = 0; ci < BN / 64; ++ci) {
+                const int c0 = cg * (BN / 4) + ci * 16;
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+                    const float4* bp = reinterpret_cast<const float4*>(bias_s + n_tile * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 b = __ldg(bp + j);
+                        const float4 b = bp[j];
                         f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
                         f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
                         f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
                         f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
                     }
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+                    if (has_res) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const uint4 rv = __ldg(rp + j);
+                            const uint4 rv = res[ci * 2 + j];
                             const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -264,6 +277,8 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
     const uint32_t tslot = tempty0 + 16;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) bias_s[i] = __ldg(p.bias + i);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -379,30 +394,40 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
             const size_t obase = pix * p.cout + (size_t)n_tile * BN;
 
+            // the residual does not depend on the accumulator: fetch this thread's BN/4 channels while the MMAs
+            // of the tile are still running, so the load latency is off the epilogue's critical path
+            constexpr int kResVec = BN / 32;  // uint4 (8 bf16) per thread
+            uint4 res[kResVec];
+            const bool has_res = valid && p.residual != nullptr;
+            if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg * (BN / 4));
+#pragma unroll
+                for (int j = 0; j < kResVec; ++j) res[j] = __ldg(rp + j);
+            }
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c0 = cg * (BN / 4); c0 < (cg + 1) * (BN / 4); c0 += 16) {
+#pragma unroll
+            for (int ci = 0; ci < BN / 64; ++ci) {
+                const int c0 = cg * (BN / 4) + ci * 16;
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+                    const float4* bp = reinterpret_cast<const float4*>(bias_s + n_tile * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 b = __ldg(bp + j);
+                        const float4 b = bp[j];
                         f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
                         f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
                         f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
                         f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
                     }
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+                    if (has_res) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const uint4 rv = __ldg(rp + j);
+                            const uint4 rv = res[ci * 2 + j];
                             const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -572,7 +597,7 @@ static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb,
 
 template <int BN, int BK, int STAGES>
 static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 16;
+    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 512 * 4;
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
         FX_CUDA(e, cudaFuncSetAttribute(tc2_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
