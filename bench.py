@@ -425,6 +425,7 @@ def main():
                                "kernel": "whole trunk: 20 conv launches + avgpool per batch", "flop_per_image": TRUNK_FLOP_PER_IMAGE,
                                "avg_ms": trunk_avg},
             "roofline_kernels": kernels,
+            "layer_ms": [round(float(x), 5) for x in layer_ms],  # slots 0..19 = conv groups in fx_load_weights order, 20 = avgpool
             "roofline_preprocess": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                                     "traffic": traffic["preprocess"] if traffic else None, "kernel": "preprocess_kernel<bf16 staging>", "bytes_per_image": PRE_BYTES_BF16,
                                     "avg_ms": pre_avg, "peak_src": peaks["src"]},

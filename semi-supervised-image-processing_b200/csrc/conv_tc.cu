@@ -24,6 +24,7 @@
 //     longer than its MMAs for four warps); mbarrier rings smem(full/empty) and
 //     tmem(full/empty).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "tc_ptx.cuh"
@@ -605,7 +606,8 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
-    const int pairs = std::max(1, std::min(pair_tiles, e->sm_count / 2));
+    int pairs = std::max(1, std::min(pair_tiles, e->sm_count / 2));
+    if (const char* dbg = getenv("FX_DEBUG_TC_PAIRS")) pairs = std::max(1, std::min(pairs, atoi(dbg)));  // fabric experiments only
     tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, p);  // cluster dims are a kernel attribute
     FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
     return FX_OK;
