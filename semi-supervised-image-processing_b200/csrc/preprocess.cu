@@ -237,90 +237,72 @@ __device__ __forceinline__ void preprocess_fast(const uint8_t* __restrict__ base
         else if (f - 1 < img.ksv && f - 1 < NTV) v = __ldg(vk + y * img.ksv + (f - 1));  // taps past the count are zero in the table
         s_vt[i] = v;
     }
-    // ---- work split: thread (rg, cw) owns the 12 byte columns [12*cw, 12*cw+12) = output pixels 4*cw .. 4*cw+3 of
-    //      every 4th row (rg = 0..3); 4 x 56 = 224 of the 256 threads.  Shared memory is touched a word at a time in the
-    //      band (3 words per thread-row), which is what bounds this kernel (LSU), not HBM. ----
-    const int cw = tid % 56, rg = tid / 56;
-    const int x0 = 4 * cw;
-    int xoff[4], kx[4][NTH];
+    // ---- per-thread horizontal taps for its byte columns b = tid, tid + 256, tid + 512 ----
+    int off[3], kx[3][NTH], ocol[3], lutc[3];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        xoff[q] = (__ldg(hx_min + x0 + q) - img.col_lo) * 3;
+    for (int q = 0; q < 3; ++q) {
+        const int b = min(tid + q * kPreThreads, kRowBytes - 1);
+        const int x = b / 3, c = b - 3 * x;
+        off[q] = (__ldg(hx_min + x) - img.col_lo) * 3 + c;
 #pragma unroll
-        for (int i = 0; i < NTH; ++i) kx[q][i] = i < img.ksh ? __ldg(hk + (x0 + q) * img.ksh + i) : 0;
+        for (int i = 0; i < NTH; ++i) kx[q][i] = i < img.ksh ? __ldg(hk + x * img.ksh + i) : 0;
+        lutc[q] = c * 256;
+        if (MODE == 0) {
+            ocol[q] = c * kCrop * kCrop + x;
+        } else if (MODE == 1) {
+            const int px = x + kIn0Pad;
+            ocol[q] = (px >> 1) * kS2dC + (px & 1) * 3 + c;
+        } else {
+            ocol[q] = (x + kIn0Pad) * 4 + c;
+        }
     }
+    const bool has2 = tid + 2 * kPreThreads < kRowBytes;  // 672 = 2 * 256 + 160
     __syncthreads();
-    if (rg < 4) {
-        // ---- horizontal pass: staged source rows -> uint8 band (zero-weight taps read valid smem, contribute 0) ----
-        for (int r = rg; r < nrows; r += 4) {
-            const uint8_t* rowp = s_src + (size_t)r * src_pitch + s_shift[r];
-            unsigned wv[3] = {0u, 0u, 0u};
+    // ---- horizontal pass: staged source rows -> uint8 band (zero-weight taps read valid smem, contribute 0) ----
+#pragma unroll 2
+    for (int r = 0; r < nrows; ++r) {
+        const uint8_t* rowp = s_src + (size_t)r * src_pitch + s_shift[r];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint8_t* pp = rowp + xoff[q];
+        for (int q = 0; q < 3; ++q) {
+            if (q < 2 || has2) {
+                int acc = 1 << 21;
+                const uint8_t* pp = rowp + off[q];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    int acc = 1 << 21;
-#pragma unroll
-                    for (int i = 0; i < NTH; ++i) acc += kx[q][i] * (int)pp[3 * i + c];
-                    const int j = 3 * q + c;
-                    wv[j >> 2] |= (unsigned)clip8(acc) << (8 * (j & 3));
-                }
+                for (int i = 0; i < NTH; ++i) acc += kx[q][i] * (int)pp[3 * i];
+                s_tmp[r * kRowBytes + tid + q * kPreThreads] = (uint8_t)clip8(acc);
             }
-            unsigned* trow = reinterpret_cast<unsigned*>(s_tmp + r * kRowBytes + 12 * cw);
-            trow[0] = wv[0];
-            trow[1] = wv[1];
-            trow[2] = wv[2];
         }
     }
     __syncthreads();
-    if (rg < 4) {
-        // ---- vertical pass + table lookup + store ----
-        const int px0 = x0 + kIn0Pad;  // odd: the first pixel is the dx = 1 half of s2d pixel X0
-        for (int yy = rg; yy < y1 - y0; yy += 4) {
-            const int y = y0 + yy;
-            const int ym = s_vt[yy * 8];
-            int kv[NTV];
+    // ---- vertical pass + table lookup + store ----
+#pragma unroll 2
+    for (int yy = 0; yy < y1 - y0; ++yy) {
+        const int y = y0 + yy;
+        const int ym = s_vt[yy * 8];
+        int kv[NTV];
 #pragma unroll
-            for (int i = 0; i < NTV; ++i) kv[i] = s_vt[yy * 8 + 1 + i];
-            const unsigned* colp = reinterpret_cast<const unsigned*>(s_tmp + ym * kRowBytes + 12 * cw);
-            int v[12];
+        for (int i = 0; i < NTV; ++i) kv[i] = s_vt[yy * 8 + 1 + i];
+        size_t orow;
+        if (MODE == 0) {
+            orow = img_idx * 3 * kCrop * kCrop + (size_t)y * kCrop;
+        } else if (MODE == 1) {
+            const int py = y + kIn0Pad;
+            orow = ((img_idx * kS2dH + (py >> 1)) * kS2dW) * kS2dC + (py & 1) * 6;
+        } else {
+            orow = ((img_idx * kIn0H + (y + kIn0Pad)) * kIn0W) * 4;
+        }
+        const uint8_t* colp = s_tmp + ym * kRowBytes + tid;
 #pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                unsigned word[NTV];
+        for (int q = 0; q < 3; ++q) {
+            if (q < 2 || has2) {
+                int acc = 1 << 21;
 #pragma unroll
-                for (int i = 0; i < NTV; ++i) word[i] = colp[i * (kRowBytes / 4) + w];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int acc = 1 << 21;
-#pragma unroll
-                    for (int i = 0; i < NTV; ++i) acc += kv[i] * (int)((word[i] >> (8 * k)) & 255u);
-                    v[4 * w + k] = clip8(acc);
-                }
-            }
-            if (MODE == 1) {
-                unsigned short h[12];
-#pragma unroll
-                for (int j = 0; j < 12; ++j) h[j] = __bfloat16_as_ushort(s_lutb[(j % 3) * 256 + v[j]]);
-                const int py = y + kIn0Pad;
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) +
-                                   ((img_idx * kS2dH + (py >> 1)) * kS2dW + (px0 >> 1)) * kS2dC + (py & 1) * 6;
-                // pixel x0 (dx = 1 of pair X0): elements 3,4,5; pixels x0+1, x0+2 = pair X0+1: 0..5; pixel x0+3: 0,1,2 of X0+2
-                reinterpret_cast<unsigned short*>(o)[3] = h[0];
-                *reinterpret_cast<unsigned*>(o + 4) = (unsigned)h[1] | ((unsigned)h[2] << 16);
-                *reinterpret_cast<unsigned*>(o + kS2dC) = (unsigned)h[3] | ((unsigned)h[4] << 16);
-                *reinterpret_cast<unsigned*>(o + kS2dC + 2) = (unsigned)h[5] | ((unsigned)h[6] << 16);
-                *reinterpret_cast<unsigned*>(o + kS2dC + 4) = (unsigned)h[7] | ((unsigned)h[8] << 16);
-                *reinterpret_cast<unsigned*>(o + 2 * kS2dC) = (unsigned)h[9] | ((unsigned)h[10] << 16);
-                reinterpret_cast<unsigned short*>(o)[2 * kS2dC + 2] = h[11];
-            } else if (MODE == 0) {
-                float* o = reinterpret_cast<float*>(out) + img_idx * 3 * kCrop * kCrop + (size_t)y * kCrop + x0;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) o[(j % 3) * kCrop * kCrop + j / 3] = s_lut[(j % 3) * 256 + v[j]];
-            } else {
-                float* o = reinterpret_cast<float*>(out) + ((img_idx * kIn0H + (y + kIn0Pad)) * kIn0W + (x0 + kIn0Pad)) * 4;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) o[(j / 3) * 4 + j % 3] = s_lut[(j % 3) * 256 + v[j]];
+                for (int i = 0; i < NTV; ++i) acc += kv[i] * (int)colp[q * kPreThreads + i * kRowBytes];
+                const int v = clip8(acc);
+                if (MODE == 1)
+                    reinterpret_cast<__nv_bfloat16*>(out)[orow + ocol[q]] = s_lutb[lutc[q] + v];
+                else
+                    reinterpret_cast<float*>(out)[orow + ocol[q]] = s_lut[lutc[q] + v];
             }
         }
     }
