@@ -152,6 +152,11 @@ static bool build_geom(int h, int w, GeomTableHost& g) {
         }
     }
     if (g.band == 0) return false;  // down-scaling factor too large for the shared-memory band
+    if (g.band == 16)  // the fast path's row-pair aligned bands: crop rows [16k-1, 16k+15)
+        for (int k = 0; k < 15; ++k) {
+            const int y0 = std::max(0, 16 * k - 1), y1 = std::min(kCrop, 16 * k + 15) - 1;
+            g.max_rows = std::max(g.max_rows, vmn[y1] + vct[y1] - vmn[y0]);
+        }
     g.blob.resize(kGeomHdr + (size_t)kCrop * (g.ksh + g.ksv));
     std::memcpy(&g.blob[0], hmn.data(), sizeof(int32_t) * kCrop);
     std::memcpy(&g.blob[kCrop], hct.data(), sizeof(int32_t) * kCrop);
@@ -274,6 +279,55 @@ __device__ __forceinline__ void preprocess_fast(const uint8_t* __restrict__ base
         }
     }
     __syncthreads();
+    if (MODE == 1) {
+        // ---- vertical pass, space-to-depth output: a thread produces one whole s2d pixel = crop rows (2Y-3, 2Y-2) x
+        //      columns (2X-3, 2X-2) x 3 channels + 4 zero channels = 32 bytes = one DRAM sector, written by two
+        //      16-byte stores (partial-sector writes made L2 read every output sector back: +88 MB per batch) ----
+        const int Y0 = 8 * (int)blockIdx.x + 1;  // s2d row of this band's first pair
+        constexpr int kXs = kCrop / 2 + 1;       // 113 s2d columns carry data (X = 1 .. 113)
+        for (int idx = tid; idx < 8 * kXs; idx += kPreThreads) {
+            const int pj = idx / kXs, X = idx - pj * kXs + 1;
+            const int Y = Y0 + pj;
+            if (Y > kCrop / 2 + 1) break;  // Y = 113 is the last row pair with data (crop row 223)
+            unsigned short h[12];
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = 2 * Y - 3 + dy;
+                const bool yok = y >= 0 && y < kCrop;
+                const int yy = yok ? y - y0 : 0;
+                const int ym = s_vt[yy * 8];
+                int kv[NTV];
+#pragma unroll
+                for (int i = 0; i < NTV; ++i) kv[i] = s_vt[yy * 8 + 1 + i];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int x = 2 * X - 3 + dx;
+                    const bool ok = yok && x >= 0 && x < kCrop;
+                    const uint8_t* colp = s_tmp + ym * kRowBytes + 3 * (ok ? x : 0);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        int acc = 1 << 21;
+#pragma unroll
+                        for (int i = 0; i < NTV; ++i) acc += kv[i] * (int)colp[i * kRowBytes + c];
+                        h[(dy * 2 + dx) * 3 + c] = ok ? __bfloat16_as_ushort(s_lutb[c * 256 + clip8(acc)]) : (unsigned short)0;
+                    }
+                }
+            }
+            uint4 lo, hi;
+            lo.x = (unsigned)h[0] | ((unsigned)h[1] << 16);
+            lo.y = (unsigned)h[2] | ((unsigned)h[3] << 16);
+            lo.z = (unsigned)h[4] | ((unsigned)h[5] << 16);
+            lo.w = (unsigned)h[6] | ((unsigned)h[7] << 16);
+            hi.x = (unsigned)h[8] | ((unsigned)h[9] << 16);
+            hi.y = (unsigned)h[10] | ((unsigned)h[11] << 16);
+            hi.z = 0u;
+            hi.w = 0u;
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + ((img_idx * kS2dH + Y) * kS2dW + X) * kS2dC);
+            o[0] = lo;
+            o[1] = hi;
+        }
+        return;
+    }
     // ---- vertical pass + table lookup + store ----
 #pragma unroll 2
     for (int yy = 0; yy < y1 - y0; ++yy) {
@@ -318,9 +372,12 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
                                                                  int tmp_bytes, int rowbuf_bytes) {
     extern __shared__ __align__(16) uint8_t smem[];
     const ImgDev img = imgs[blockIdx.y];
-    const int y0 = blockIdx.x * img.band;
+    // MODE 1 fast path: bands are aligned to the row PAIRS of the space-to-depth tensor (crop rows 2Y-3, 2Y-2), so a
+    // thread can write whole 32-byte s2d pixels: band b = pairs 8b .. 8b+7 = crop rows 16b-1 .. 16b+14 (15 bands).
+    const bool pair_bands = MODE == 1 && img.fast;
+    const int y0 = pair_bands ? max(0, 16 * (int)blockIdx.x - 1) : blockIdx.x * img.band;
     if (y0 >= kCrop) return;
-    const int y1 = min(kCrop, y0 + img.band);
+    const int y1 = pair_bands ? min(kCrop, 16 * (int)blockIdx.x + 15) : min(kCrop, y0 + img.band);
     const int C = img.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -622,7 +679,8 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
         // fast path: RGB, few taps, and the band's source rows + uint8 band fit in 96 KB (2 blocks / SM)
         const int src_pitch = ((ge->col_hi - ge->col_lo) * 3 + 15 + 16 + 3 * kFastTaps) & ~15;
         const int need = 16 * 8 * 4 + (kMaxTmpRows + 8) * 4 + ge->max_rows * src_pitch + (ge->max_rows + kFastTaps) * kRowBytes + 16;
-        im.fast = d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->band <= 16 && need <= 96 * 1024;
+        im.fast = d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->band == 16 && ge->max_rows <= kMaxTmpRows &&
+                  need <= 96 * 1024;
         if (im.fast) {
             nth = std::max(nth, ge->cnt_h);
             ntv = std::max(ntv, ge->cnt_v);
@@ -639,7 +697,9 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     const int tmp_bytes = (max_tmp + 15) & ~15;
     const int rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
     const int smem = 3072 + std::max(max_tmp ? tmp_bytes + kPreWarps * rowbuf : 0, fast_smem);
-    dim3 grid((kCrop + min_band - 1) / min_band, n);
+    int bands = (kCrop + min_band - 1) / min_band;
+    if (mode == PreOut::IN0_BF16 && fast_smem) bands = std::max(bands, 15);  // row-pair aligned bands of the fast path
+    dim3 grid(bands, n);
     const int ih = nth <= 2 ? 0 : (nth <= 4 ? 1 : 2), iv = ntv <= 2 ? 0 : (ntv <= 4 ? 1 : 2);
     pre_kernels()[((int)mode * 3 + ih) * 3 + iv]<<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32, e->lut_bf16,
                                                                                    tmp_bytes, rowbuf);
