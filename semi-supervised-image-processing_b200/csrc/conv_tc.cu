@@ -47,6 +47,12 @@ struct TcConvParams {
     __nv_bfloat16* out;
     float* out_f32;
     int relu;
+    // grouped launch: `ds_tiles` extra tiles (after the main ones) compute the block's 1x1 / stride-2 downsample conv
+    // (torchvision/models/resnet.py:239-243) on the SAME input and output tiling: one tap, no padding, no ReLU,
+    // weights from map_b2.  It shares the launch (and fills the tail wave) of the block's 3x3 / stride-2 conv1.
+    int ds_tiles;
+    const float* ds_bias;
+    __nv_bfloat16* ds_out;
 };
 
 constexpr int kTcThreads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps (4 TMEM lane quarters x 4 column groups)
@@ -56,13 +62,14 @@ struct TcSmem {
     static constexpr int kA = 128 * BK * 2;
     static constexpr int kB = BN * BK * 2;
     static constexpr int kBars = (2 * STAGES + 4) * 8;
-    static constexpr int kBias = 512 * 4;  // folded-BN bias of every output channel (cout <= 512)
+    static constexpr int kBias = 2 * 512 * 4;  // folded-BN bias of every output channel (cout <= 512), main + downsample
     static constexpr int kTotal = 1024 /*align slack*/ + STAGES * (kA + kB) + kBars + 16 + kBias;
 };
 
 template <int BN, int BK, int STAGES>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_b2, const TcConvParams p) {
     using L = TcSmem<BN, BK, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,7 +82,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
-    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) bias_s[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) {
+        bias_s[i] = __ldg(p.bias + i);
+        if (p.ds_tiles) bias_s[512 + i] = __ldg(p.ds_bias + i);
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -104,24 +114,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t0 = blockIdx.x; t0 < p.total_tiles + p.ds_tiles; t0 += gridDim.x) {
+                const bool ds = t0 >= p.total_tiles;
+                const int t = ds ? t0 - p.total_tiles : t0;
                 const int n_tile = t % p.n_tiles_n;
                 int m_tile = t / p.n_tiles_n;
                 const int tw = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
                 const int th = m_tile % p.tiles_h;
                 const int tg = m_tile / p.tiles_h;
-                const int w0 = (tw << p.wt_log2) * p.cw_mul - p.pad_w;
-                const int h0 = (th << p.ht_log2) * p.ch_mul - p.pad_h;
+                const int w0 = (tw << p.wt_log2) * p.cw_mul - (ds ? 0 : p.pad_w);
+                const int h0 = (th << p.ht_log2) * p.ch_mul - (ds ? 0 : p.pad_h);
                 const int n0 = tg << p.nt_log2;
+                const int kh = ds ? 1 : p.kh, kw = ds ? 1 : p.kw;
+                const CUtensorMap* mb = ds ? &map_b2 : &map_b;
                 int kb = 0;
-                for (int r = 0; r < p.kh; ++r)
-                    for (int s = 0; s < p.kw; ++s)
+                for (int r = 0; r < kh; ++r)
+                    for (int s = 0; s < kw; ++s)
                         for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
                             mbar_expect_tx(full0 + 8 * stage, L::kA + L::kB);
                             tma_load_4d(sA + stage * L::kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            tma_load_2d(sB + stage * L::kB, &map_b, full0 + 8 * stage, kb * BK, n_tile * BN);
+                            tma_load_2d(sB + stage * L::kB, mb, full0 + 8 * stage, kb * BK, n_tile * BN);
                             if (++stage == STAGES) {
                                 stage = 0;
                                 phase ^= 1;
@@ -135,12 +149,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
         uint32_t stage = 0, phase = 0;
         int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        for (int t0 = blockIdx.x; t0 < p.total_tiles + p.ds_tiles; t0 += gridDim.x, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             mbar_wait(tempty0 + 8 * as, aphase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int nkb = t0 >= p.total_tiles ? p.cchunks : num_kb;
+            for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 if (elect_one_sync()) {
@@ -149,7 +164,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int k = 0; k < BK / 16; ++k)
                         umma_bf16(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (kb | k) != 0);
                     umma_commit(empty0 + 8 * stage);  // frees the smem slot once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
+                    if (kb == nkb - 1) umma_commit(tfull0 + 8 * as);
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -167,7 +182,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
         const int nl = row >> (p.wt_log2 + p.ht_log2);
         int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        for (int t0 = blockIdx.x; t0 < p.total_tiles + p.ds_tiles; t0 += gridDim.x, ++it) {
+            const bool ds = t0 >= p.total_tiles;
+            const int t = ds ? t0 - p.total_tiles : t0;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int n_tile = t % p.n_tiles_n;
             int m_tile = t / p.n_tiles_n;
@@ -184,7 +201,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // of the tile are still running, so the load latency is off the epilogue's critical path
             constexpr int kResVec = BN / 32;  // uint4 (8 bf16) per thread
             uint4 res[kResVec];
-            const bool has_res = valid && p.residual != nullptr;
+            const bool has_res = valid && !ds && p.residual != nullptr;
             if (has_res) {
                 const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg * (BN / 4));
 #pragma unroll
@@ -201,7 +218,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(bias_s + n_tile * BN + c0);
+                    const float4* bp = reinterpret_cast<const float4*>(bias_s + (ds ? 512 : 0) + n_tile * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 b = bp[j];
@@ -222,16 +239,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
                     }
-                    if (p.relu) {
+                    if (p.relu && !ds) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
-                    if (p.out_f32) {
+                    if (p.out_f32 && !ds) {
                         float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     } else {
-                        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+                        uint4* op = reinterpret_cast<uint4*>((ds ? p.ds_out : p.out) + obase + c0);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             uint4 o;
@@ -269,7 +286,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 template <int BN, int BK, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
+tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_b2, const TcConvParams p) {
     constexpr int kA = 128 * BK * 2, kB = (BN / 2) * BK * 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -279,7 +297,10 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t tslot = tempty0 + 16;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) bias_s[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) {
+        bias_s[i] = __ldg(p.bias + i);
+        if (p.ds_tiles) bias_s[512 + i] = __ldg(p.ds_bias + i);
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -316,24 +337,28 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ===== TMA producer (both CTAs): own 128 A rows + own half of the weight K-block =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int t = pair; t < pair_tiles; t += n_pairs) {
+            for (int t0 = pair; t0 < pair_tiles + p.ds_tiles; t0 += n_pairs) {
+                const bool ds = t0 >= pair_tiles;
+                const int t = ds ? t0 - pair_tiles : t0;
                 const int n_tile = t % p.n_tiles_n;
                 int m_tile = (t / p.n_tiles_n) * 2 + (int)rank;
                 const int tw = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
                 const int th = m_tile % p.tiles_h;
                 const int tg = m_tile / p.tiles_h;  // >= tiles_g for the odd leftover: every load is out of bounds -> zeros
-                const int w0 = (tw << p.wt_log2) * p.cw_mul - p.pad_w;
-                const int h0 = (th << p.ht_log2) * p.ch_mul - p.pad_h;
+                const int w0 = (tw << p.wt_log2) * p.cw_mul - (ds ? 0 : p.pad_w);
+                const int h0 = (th << p.ht_log2) * p.ch_mul - (ds ? 0 : p.pad_h);
                 const int n0 = tg << p.nt_log2;
+                const int kh = ds ? 1 : p.kh, kw = ds ? 1 : p.kw;
+                const CUtensorMap* mb = ds ? &map_b2 : &map_b;
                 int kb = 0;
-                for (int r = 0; r < p.kh; ++r)
-                    for (int s = 0; s < p.kw; ++s)
+                for (int r = 0; r < kh; ++r)
+                    for (int s = 0; s < kw; ++s)
                         for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
                             if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * (kA + kB));
                             tma_load_4d_2cta(sA + stage * kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            tma_load_2d_2cta(sB + stage * kB, &map_b, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
+                            tma_load_2d_2cta(sB + stage * kB, mb, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
                             if (!leader) mbar_arrive_leader(full0 + 8 * stage);
                             if (++stage == STAGES) {
                                 stage = 0;
@@ -349,12 +374,13 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int t = pair; t < pair_tiles; t += n_pairs, ++it) {
+            for (int t0 = pair; t0 < pair_tiles + p.ds_tiles; t0 += n_pairs, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * as, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int nkb = t0 >= pair_tiles ? p.cchunks : num_kb;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     if (elect_one_sync()) {
@@ -363,7 +389,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         for (int k = 0; k < BK / 16; ++k)
                             umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (kb | k) != 0);
                         umma_commit_2cta(empty0 + 8 * stage);
-                        if (kb == num_kb - 1) umma_commit_2cta(tfull0 + 8 * as);
+                        if (kb == nkb - 1) umma_commit_2cta(tfull0 + 8 * as);
                     }
                     __syncwarp();
                     if (++stage == STAGES) {
@@ -382,7 +408,9 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
         const int nl = row >> (p.wt_log2 + p.ht_log2);
         int it = 0;
-        for (int t = pair; t < pair_tiles; t += n_pairs, ++it) {
+        for (int t0 = pair; t0 < pair_tiles + p.ds_tiles; t0 += n_pairs, ++it) {
+            const bool ds = t0 >= pair_tiles;
+            const int t = ds ? t0 - pair_tiles : t0;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int n_tile = t % p.n_tiles_n;
             int m_tile = (t / p.n_tiles_n) * 2 + (int)rank;
@@ -399,7 +427,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // of the tile are still running, so the load latency is off the epilogue's critical path
             constexpr int kResVec = BN / 32;  // uint4 (8 bf16) per thread
             uint4 res[kResVec];
-            const bool has_res = valid && p.residual != nullptr;
+            const bool has_res = valid && !ds && p.residual != nullptr;
             if (has_res) {
                 const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg * (BN / 4));
 #pragma unroll
@@ -416,7 +444,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(bias_s + n_tile * BN + c0);
+                    const float4* bp = reinterpret_cast<const float4*>(bias_s + (ds ? 512 : 0) + n_tile * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 b = bp[j];
@@ -437,16 +465,16 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             }
                         }
                     }
-                    if (p.relu) {
+                    if (p.relu && !ds) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
                     }
-                    if (p.out_f32) {
+                    if (p.out_f32 && !ds) {
                         float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     } else {
-                        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+                        uint4* op = reinterpret_cast<uint4*>((ds ? p.ds_out : p.out) + obase + c0);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             uint4 o;
@@ -583,22 +611,24 @@ int tc_encode_map(fx_engine* e, CUtensorMap* m, const void* base, int rank, cons
 }
 
 template <int BN, int BK, int STAGES>
-static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, cudaStream_t stream) {
+static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const TcConvParams& p,
+                     cudaStream_t stream) {
     using L = TcSmem<BN, BK, STAGES>;
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
         FX_CUDA(e, cudaFuncSetAttribute(tc_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         attr_done[e->device & 15] = true;
     }
-    const int grid = std::min(p.total_tiles, e->sm_count);
-    tc_conv_kernel<BN, BK, STAGES><<<grid, kTcThreads, L::kTotal, stream>>>(ma, mb, p);
+    const int grid = std::min(p.total_tiles + p.ds_tiles, e->sm_count);
+    tc_conv_kernel<BN, BK, STAGES><<<grid, kTcThreads, L::kTotal, stream>>>(ma, mb, mb2, p);
     FX_LAUNCH_CHECK(e, "tc_conv_kernel");
     return FX_OK;
 }
 
 template <int BN, int BK, int STAGES>
-static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 512 * 4;
+static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, TcConvParams p,
+                      cudaStream_t stream) {
+    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4;
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
         FX_CUDA(e, cudaFuncSetAttribute(tc2_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -606,9 +636,10 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
-    int pairs = std::max(1, std::min(pair_tiles, e->sm_count / 2));
+    if (p.ds_tiles) p.ds_tiles = pair_tiles;  // the downsample conv has the same tiling, counted in pair tiles here
+    int pairs = std::max(1, std::min(pair_tiles + p.ds_tiles, e->sm_count / 2));
     if (const char* dbg = getenv("FX_DEBUG_TC_PAIRS")) pairs = std::max(1, std::min(pairs, atoi(dbg)));  // fabric experiments only
-    tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, p);  // cluster dims are a kernel attribute
+    tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, mb2, p);  // cluster dims are a kernel attribute
     FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
     return FX_OK;
 }
@@ -647,9 +678,17 @@ static void choose_tile(int n, int ho, int wo, int& wt, int& ht, int& nt) {
         }
 }
 
+// ds / ds_out (optional): the block's 1x1 / stride-2 downsample conv, run as extra tiles of the same launch.
 int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
-                   __nv_bfloat16* out, float* out_f32, int n, int relu, cudaStream_t stream) {
+                   __nv_bfloat16* out, float* out_f32, int n, int relu, cudaStream_t stream, const PackedLayer* ds,
+                   __nv_bfloat16* ds_out) {
     const LayerGeom& g = L.g;
+    if (ds) {
+        const LayerGeom& d = ds->g;
+        if (!(d.kh == 1 && d.kw == 1 && d.pad == 0 && d.stride == g.stride && d.cin == g.cin && d.cout == g.cout && d.hin == g.hin &&
+              d.win == g.win && d.hout == g.hout && d.wout == g.wout && ds_out && !residual && !out_f32))
+            return set_error(e, FX_ERR_INVALID, "tc_conv: the grouped downsample conv must be the 1x1 twin of the strided conv");
+    }
     TcConvParams p;
     std::memset(&p, 0, sizeof(p));
     p.batch = n;
@@ -693,16 +732,28 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     p.ch_mul = g.stride;
     p.pad_w = g.pad;
     p.pad_h = g.pad;
+    CUtensorMap mb2 = mb;
+    if (ds) {
+        const uint64_t bd[2] = {(uint64_t)ds->k_bf16, (uint64_t)g.cout};
+        const uint64_t bs[1] = {(uint64_t)ds->k_bf16 * 2};
+        const uint32_t bbox[2] = {64, (uint32_t)(bn == 256 ? 128 : bn)};
+        const uint32_t be[2] = {1, 1};
+        int rc = tc_encode_map(e, &mb2, ds->w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "downsample B");
+        if (rc != FX_OK) return rc;
+        p.ds_tiles = p.total_tiles;
+        p.ds_bias = ds->bias;
+        p.ds_out = ds_out;
+    }
     switch (bn) {
-        case 64: return launch_tc<64, 64, 8>(e, ma, mb, p, stream);
-        case 128: return launch_tc<128, 64, 6>(e, ma, mb, p, stream);
-        default: return launch_tc2<256, 64, 6>(e, ma, mb, p, stream);
+        case 64: return launch_tc<64, 64, 8>(e, ma, mb, mb2, p, stream);
+        case 128: return launch_tc<128, 64, 6>(e, ma, mb, mb2, p, stream);
+        default: return launch_tc2<256, 64, 6>(e, ma, mb, mb2, p, stream);
     }
 }
 
 int tc_conv(fx_engine* e, int li, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, float* out_f32,
             int n, int relu, cudaStream_t stream) {
-    return tc_conv_packed(e, e->layers[li], in, residual, out, out_f32, n, relu, stream);
+    return tc_conv_packed(e, e->layers[li], in, residual, out, out_f32, n, relu, stream, nullptr, nullptr);
 }
 
 // Test hook behind fx_debug_tma_probe (engine.cu): encode an arbitrary 4-D bf16 map, load one box.

@@ -14,7 +14,8 @@
 namespace fx {
 
 int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual,
-                   __nv_bfloat16* out, float* out_f32, int n, int relu, cudaStream_t stream);
+                   __nv_bfloat16* out, float* out_f32, int n, int relu, cudaStream_t stream, const PackedLayer* ds = nullptr,
+                   __nv_bfloat16* ds_out = nullptr);
 int tc_tma_probe(fx_engine* e, const void* base, const uint64_t* dims, const uint64_t* strides, const uint32_t* box,
                  const uint32_t* estr, int swizzle, const int* coords, int bytes, uint8_t* out_dev, cudaStream_t stream);
 
@@ -184,8 +185,15 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
                 li += 2;
             } else {
                 // out = relu(conv2(relu(conv1(x))) + downsample(x))
-                if ((rc = run_conv(e, li, A, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
-                if ((rc = run_conv(e, li + 2, A, nullptr, C, nullptr, n, 0, stream)) != FX_OK) return rc;
+                if (bf16) {  // conv1 (3x3/s2) and the 1x1/s2 downsample read the same input: one grouped launch
+                    ProfScope ps(e, li, stream);
+                    if ((rc = tc_conv_packed(e, e->layers[li], static_cast<const __nv_bfloat16*>(A), nullptr, static_cast<__nv_bfloat16*>(B),
+                                             nullptr, n, 1, stream, &e->layers[li + 2], static_cast<__nv_bfloat16*>(C))) != FX_OK)
+                        return rc;
+                } else {
+                    if ((rc = run_conv(e, li, A, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
+                    if ((rc = run_conv(e, li + 2, A, nullptr, C, nullptr, n, 0, stream)) != FX_OK) return rc;
+                }
                 if ((rc = run_conv(e, li + 1, B, C, A, nullptr, n, 1, stream)) != FX_OK) return rc;
                 li += 3;
             }

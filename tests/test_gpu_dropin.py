@@ -130,3 +130,50 @@ def test_pipelined_slots_equal_the_synchronous_call():
     eng.embed_host_wait(1)
     for i in range(4):
         assert np.array_equal(outs[i].numpy(), sync[i])
+
+
+def test_config1_256_png_images_batch_32(tmp_path_factory):
+    # BASELINE.json configs[0]: 256 synthetic 224x224 uint8 images, batch 32, against the CPU fp32 path on the same files
+    root = tmp_path_factory.mktemp("c1")
+    imgs = list(synthetic.noise_images(256, 224, 224, seed=0))
+    synthetic.write_png_dataset(root, imgs, n_labeled=32)
+    records = fx.discover_image_records(root)
+    res = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=32)
+    ref = _oracle(records, 32)
+    assert res.embeddings.shape == (256, 512) and not res.failures
+    rel = np.linalg.norm(res.embeddings - ref.embeddings, axis=1) / np.linalg.norm(ref.embeddings, axis=1)
+    cos = (res.embeddings * ref.embeddings).sum(1) / (np.linalg.norm(res.embeddings, axis=1) * np.linalg.norm(ref.embeddings, axis=1))
+    assert rel.max() <= 1e-2 and cos.min() >= 0.999, (rel.max(), cos.min())
+    # the sanity statistics the reference logs (src/feature_extraction.py:334-356) agree to the same tolerance
+    a, b = fx.run_sanity_checks(res.embeddings), fx.run_sanity_checks(ref.embeddings)
+    assert abs(a["mean_abs_mean"] - b["mean_abs_mean"]) <= 1e-2 * b["mean_abs_mean"]
+    assert abs(a["mean_std"] - b["mean_std"]) <= 2e-2 * b["mean_std"]
+
+
+def test_size_independent_properties_at_scale():
+    # 4096 device-resident images, batch 256 (the config-2 shape): rows depend on their own image only, so
+    # (a) a permutation of the inputs permutes the rows bit-exactly, (b) duplicated images give identical rows,
+    # (c) every value is finite.  No oracle needed at this size.
+    from ssip_b200.engine import uniform_descs
+
+    eng = fx.get_engine(torch.device("cuda:0"), min_batch=256)
+    n, b = 4096, 256
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randint(0, 256, (n, 224 * 224 * 3), dtype=torch.uint8, device="cuda", generator=gen)
+    x[1000] = x[7]  # duplicates in different batches and positions
+    x[4095] = x[7]
+    descs = uniform_descs(b, 224, 224)
+
+    def run(t):
+        out = torch.empty((n, 512), dtype=torch.float32, device="cuda")
+        for s in range(0, n, b):
+            eng.embed_device(t[s : s + b].reshape(-1), descs, b, out=out[s : s + b])
+        torch.cuda.synchronize()
+        return out
+
+    base = run(x)
+    perm = torch.randperm(n, device="cuda", generator=gen)
+    assert torch.equal(run(x[perm].contiguous()), base[perm])
+    assert torch.equal(base[1000], base[7]) and torch.equal(base[4095], base[7])
+    assert bool(torch.isfinite(base).all())
+    assert float((base[0] - base[1]).abs().max()) > 0  # different images do differ
