@@ -53,8 +53,8 @@ LAYER_FAMILY = (["flat_conv_kernel<32,4,4,pool> (stem conv1+bn+relu+maxpool, s2d
                 ["tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128_conv_kernel (layer2 3x3/s1, N=128)",
                  "tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128_conv_kernel (layer2 3x3/s1, N=128)",
                  "flat128_conv_kernel (layer2 3x3/s1, N=128)"] + ["tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)"] * 10)
-EXEC_ORDER = [0, 1, 2, 3, 4, 5, 7, 6, 8, 9, 10, 12, 11, 13, 14, 15, 17, 16, 18, 19]  # launch order of the slots inside fx_forward
-LAUNCH_PROFILE = ROOT / "profiles" / "r01_launches_v6.csv"  # ncu launch list (batch 256) used for the DRAM-traffic column
+EXEC_ORDER = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 13, 14, 15, 16, 18, 19]  # launch order of the slots inside fx_forward (the 1x1 downsample slots 7, 12, 17 ride in the launches of slots 5, 10, 15)
+LAUNCH_PROFILE = ROOT / "profiles" / "r01_launches_v7.csv"  # ncu launch list (batch 256) used for the DRAM-traffic column
 
 
 def profiled_traffic():
@@ -69,9 +69,9 @@ def profiled_traffic():
         if r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             per_id.setdefault(r["ID"], [r["Kernel Name"], 0.0])[1] += float(r["Metric Value"].replace(",", ""))
     launches = list(per_id.values())
-    if len(launches) != 22 or "preprocess" not in launches[0][0]:
+    if len(launches) != 2 + len(EXEC_ORDER) or "preprocess" not in launches[0][0]:
         return None
-    out = {"preprocess": launches[0][1]}
+    out = {"preprocess": launches[0][1], 7: 0.0, 12: 0.0, 17: 0.0}
     for k, slot in enumerate(EXEC_ORDER):
         out[slot] = launches[1 + k][1]
     return out
@@ -357,7 +357,7 @@ def main():
     families = {}
     for slot in range(20):
         f = families.setdefault(LAYER_FAMILY[slot], {"launches": 0, "ms": 0.0, "flop": 0.0, "traffic": 0.0})
-        f["launches"] += 1
+        f["launches"] += 0 if slot in (7, 12, 17) else 1  # the downsample convs share the launch of their block's conv1
         f["ms"] += float(layer_ms[slot])
         f["flop"] += 2.0 * LAYER_MACS[slot] * B
         if traffic:
