@@ -53,6 +53,7 @@ struct TcConvParams {
     int ds_tiles;
     const float* ds_bias;
     __nv_bfloat16* ds_out;
+    int split_full, split_tail;  // CTA-pair kernel only: see the work-unit comment in tc2_conv_kernel
 };
 
 constexpr int kTcThreads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps (4 TMEM lane quarters x 4 column groups)
@@ -287,7 +288,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 template <int BN, int BK, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_b2, const TcConvParams p) {
+                const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_bh, const TcConvParams p) {
     constexpr int kA = 128 * BK * 2, kB = (BN / 2) * BK * 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -332,14 +333,20 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int num_kb = p.kh * p.kw * p.cchunks;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles_n;
+    // Work units.  Normally one unit = one 256 x BN pair tile (+ the grouped downsample tiles).  With a SPLIT TAIL
+    // (p.split_tail > 0; layer4 at batch 256 has 98 tiles for 74 pairs) the tiles of the last, mostly empty wave are
+    // cut into two 256 x BN/2 halves so that the tail wave costs half a tile time: unit u < split_full is full tile
+    // u, the others are (tile split_full + (u - split_full) / 2, half (u - split_full) & 1), N = BN/2 MMAs.
+    const int n_units = p.split_tail ? p.split_full + 2 * p.split_tail : pair_tiles + p.ds_tiles;
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own 128 A rows + own half of the weight K-block =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int t0 = pair; t0 < pair_tiles + p.ds_tiles; t0 += n_pairs) {
-                const bool ds = t0 >= pair_tiles;
-                const int t = ds ? t0 - pair_tiles : t0;
+            for (int t0 = pair; t0 < n_units; t0 += n_pairs) {
+                const bool ds = !p.split_tail && t0 >= pair_tiles;
+                const int half = (p.split_tail && t0 >= p.split_full) ? ((t0 - p.split_full) & 1) : -1;
+                const int t = ds ? t0 - pair_tiles : (half >= 0 ? p.split_full + ((t0 - p.split_full) >> 1) : t0);
                 const int n_tile = t % p.n_tiles_n;
                 int m_tile = (t / p.n_tiles_n) * 2 + (int)rank;
                 const int tw = m_tile % p.tiles_w;
@@ -356,9 +363,13 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int s = 0; s < kw; ++s)
                         for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                            if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * (kA + kB));
+                            if (leader) mbar_expect_tx(full0 + 8 * stage, half >= 0 ? 2 * (kA + kB / 2) : 2 * (kA + kB));
                             tma_load_4d_2cta(sA + stage * kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            tma_load_2d_2cta(sB + stage * kB, mb, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
+                            if (half >= 0)
+                                tma_load_2d_2cta(sB + stage * kB, &map_bh, full0 + 8 * stage, kb * BK,
+                                                 n_tile * BN + half * (BN / 2) + (int)rank * (BN / 4));
+                            else
+                                tma_load_2d_2cta(sB + stage * kB, mb, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
                             if (!leader) mbar_arrive_leader(full0 + 8 * stage);
                             if (++stage == STAGES) {
                                 stage = 0;
@@ -374,12 +385,14 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int t0 = pair; t0 < pair_tiles + p.ds_tiles; t0 += n_pairs, ++it) {
+            constexpr uint32_t idesc_half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)(256 >> 4) << 24);
+            for (int t0 = pair; t0 < n_units; t0 += n_pairs, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * as, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                const int nkb = t0 >= pair_tiles ? p.cchunks : num_kb;
+                const int nkb = (!p.split_tail && t0 >= pair_tiles) ? p.cchunks : num_kb;
+                const uint32_t idesc_u = (p.split_tail && t0 >= p.split_full) ? idesc_half : idesc;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
@@ -387,7 +400,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint32_t a_lo = (sA + stage * kA) >> 4, b_lo = (sB + stage * kB) >> 4;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (kb | k) != 0);
+                            umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc_u, (kb | k) != 0);
                         umma_commit_2cta(empty0 + 8 * stage);
                         if (kb == nkb - 1) umma_commit_2cta(tfull0 + 8 * as);
                     }
@@ -408,9 +421,15 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
         const int nl = row >> (p.wt_log2 + p.ht_log2);
         int it = 0;
-        for (int t0 = pair; t0 < pair_tiles + p.ds_tiles; t0 += n_pairs, ++it) {
-            const bool ds = t0 >= pair_tiles;
-            const int t = ds ? t0 - pair_tiles : t0;
+        for (int t0 = pair; t0 < n_units; t0 += n_pairs, ++it) {
+            const bool ds = !p.split_tail && t0 >= pair_tiles;
+            const int half = (p.split_tail && t0 >= p.split_full) ? ((t0 - p.split_full) & 1) : -1;
+            const int t = ds ? t0 - pair_tiles : (half >= 0 ? p.split_full + ((t0 - p.split_full) >> 1) : t0);
+            // output channels of this unit handled by this warp: BN/4 (full tile) or BN/8 (half tile) per column group
+            const int cpg = half >= 0 ? BN / 8 : BN / 4;
+            const int ch0 = (half >= 0 ? half * (BN / 2) : 0) + cg * cpg;  // first channel within the tile's BN
+            const int tc0 = cg * cpg;                                      // first accumulator column
+            const int nci = cpg / 16;
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int n_tile = t % p.n_tiles_n;
             int m_tile = (t / p.n_tiles_n) * 2 + (int)rank;
@@ -429,18 +448,20 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             uint4 res[kResVec];
             const bool has_res = valid && !ds && p.residual != nullptr;
             if (has_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + cg * (BN / 4));
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + ch0);
 #pragma unroll
-                for (int j = 0; j < kResVec; ++j) res[j] = __ldg(rp + j);
+                for (int j = 0; j < kResVec; ++j)
+                    if (j < 2 * nci) res[j] = __ldg(rp + j);
             }
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
             for (int ci = 0; ci < BN / 64; ++ci) {
-                const int c0 = cg * (BN / 4) + ci * 16;
+                if (ci >= nci) break;
+                const int c0 = ch0 + ci * 16;
                 uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
+                tmem_ld16(taddr + tc0 + ci * 16, v);
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
@@ -626,8 +647,8 @@ static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb,
 }
 
 template <int BN, int BK, int STAGES>
-static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, TcConvParams p,
-                      cudaStream_t stream) {
+static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mbh,
+                      TcConvParams p, cudaStream_t stream) {
     constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4;
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
@@ -638,8 +659,14 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb
     const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
     if (p.ds_tiles) p.ds_tiles = pair_tiles;  // the downsample conv has the same tiling, counted in pair tiles here
     int pairs = std::max(1, std::min(pair_tiles + p.ds_tiles, e->sm_count / 2));
+    // split the tail wave into half-N units when it would leave more than half of the pairs idle
+    const int tail = pair_tiles % pairs;
+    if (!p.ds_tiles && pair_tiles > pairs && tail > 0 && 2 * tail <= pairs && !getenv("FX_DEBUG_NO_SPLIT")) {
+        p.split_tail = tail;
+        p.split_full = pair_tiles - tail;
+    }
     if (const char* dbg = getenv("FX_DEBUG_TC_PAIRS")) pairs = std::max(1, std::min(pairs, atoi(dbg)));  // fabric experiments only
-    tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, mb2, p);  // cluster dims are a kernel attribute
+    tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, mb2, mbh, p);  // cluster dims are a kernel attribute
     FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
     return FX_OK;
 }
@@ -744,10 +771,19 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
         p.ds_bias = ds->bias;
         p.ds_out = ds_out;
     }
+    CUtensorMap mbh = mb;
+    if (bn == 256) {  // quarter-of-a-K-block box for the split-tail half tiles of the CTA-pair kernel
+        const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+        const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+        const uint32_t bbox[2] = {64, 64};
+        const uint32_t be[2] = {1, 1};
+        int rc = tc_encode_map(e, &mbh, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B (half tile)");
+        if (rc != FX_OK) return rc;
+    }
     switch (bn) {
         case 64: return launch_tc<64, 64, 8>(e, ma, mb, mb2, p, stream);
         case 128: return launch_tc<128, 64, 6>(e, ma, mb, mb2, p, stream);
-        default: return launch_tc2<256, 64, 6>(e, ma, mb, mb2, p, stream);
+        default: return launch_tc2<256, 64, 6>(e, ma, mb, mb2, mbh, p, stream);
     }
 }
 
