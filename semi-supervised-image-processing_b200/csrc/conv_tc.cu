@@ -747,7 +747,7 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
         if (rc != FX_OK) return rc;
         const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
         const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
-        const uint32_t bbox[2] = {64, (uint32_t)(bn == 256 ? 128 : bn)};  // the CTA-pair kernel loads half a K-block per CTA
+        const uint32_t bbox[2] = {64, (uint32_t)(bn >= 128 ? bn / 2 : bn)};  // the CTA-pair kernel loads half a K-block per CTA
         const uint32_t be[2] = {1, 1};
         rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B");
         if (rc != FX_OK) return rc;
@@ -763,7 +763,7 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     if (ds) {
         const uint64_t bd[2] = {(uint64_t)ds->k_bf16, (uint64_t)g.cout};
         const uint64_t bs[1] = {(uint64_t)ds->k_bf16 * 2};
-        const uint32_t bbox[2] = {64, (uint32_t)(bn == 256 ? 128 : bn)};
+        const uint32_t bbox[2] = {64, (uint32_t)(bn >= 128 ? bn / 2 : bn)};
         const uint32_t be[2] = {1, 1};
         int rc = tc_encode_map(e, &mb2, ds->w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "downsample B");
         if (rc != FX_OK) return rc;
@@ -772,17 +772,17 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
         p.ds_out = ds_out;
     }
     CUtensorMap mbh = mb;
-    if (bn == 256) {  // quarter-of-a-K-block box for the split-tail half tiles of the CTA-pair kernel
+    if (bn >= 128) {  // quarter-of-a-K-block box for the split-tail half tiles of the CTA-pair kernel
         const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
         const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
-        const uint32_t bbox[2] = {64, 64};
+        const uint32_t bbox[2] = {64, (uint32_t)(bn / 4)};
         const uint32_t be[2] = {1, 1};
         int rc = tc_encode_map(e, &mbh, L.w_bf16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "conv B (half tile)");
         if (rc != FX_OK) return rc;
     }
     switch (bn) {
         case 64: return launch_tc<64, 64, 8>(e, ma, mb, mb2, p, stream);
-        case 128: return launch_tc<128, 64, 6>(e, ma, mb, mb2, p, stream);
+        case 128: return launch_tc2<128, 64, 8>(e, ma, mb, mb2, mbh, p, stream);
         default: return launch_tc2<256, 64, 6>(e, ma, mb, mb2, mbh, p, stream);
     }
 }
