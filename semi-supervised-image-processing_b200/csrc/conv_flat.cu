@@ -49,8 +49,7 @@ constexpr int kFlatPoolThreads = 128 + 16 * 32;  // pooled stem: 8 epilogue warp
 constexpr int kPoolRing = 6;                     // conv rows kept in shared memory for the fused max-pool
 constexpr int kFlatSlots = 8;  // 8 x 64 fp32 columns = the whole TMEM
 constexpr int kEpiBytes = 8 * 4096 + 256;      // epilogue staging (8 warps x 4 KB) + bias
-constexpr int kPoolRowBytes = 56 * 128 + 1024;       // pooled stem ring row: 56 horizontally pooled pixels x 64 ch bf16 + 8 boundary pixels
-constexpr int kPoolRingBytes = kPoolRing * kPoolRowBytes;
+constexpr int kPoolRingBytes = 6 * 112 * 128;  // pooled stem: six conv rows (112 px x 64 ch bf16)
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -221,22 +220,17 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             g_base += n_mt;
         }
     } else if (warp >= 4 && warp < 12 && POOL) {
-        // ===== pooled-stem epilogue, stage 1: TMEM -> (+bias, ReLU) -> bf16 -> horizontal 3-max -> smem ring =====
-        // Two groups of four warps take alternate M-tiles and never synchronise with each other.  A lane owns conv
-        // pixel x of conv row i (m = i*P + x; lanes are consecutive x, lane parity = x parity).  Even-x lanes keep
-        // hmax[pw = x/2] = max(c[x-1], c[x], c[x+1]) with the neighbours fetched by warp shuffle; only lane 0 cannot
-        // see its left neighbour (lane 31 of the previous warp, possibly of the other group's M-tile), so lane 0
-        // stores max(c[x], c[x+1]) and every lane 31 parks its raw pixel in the row's boundary slot (m >> 5) & 7
-        // for the pool warps to fold in.  The ring therefore holds HALF-width rows: this kernel is bound by
-        // shared-memory bandwidth (N=64 operand fetch + epilogue traffic), and this cuts the epilogue's share 3x.
-        // Conv row number `gr` (counted over the whole CTA: 9 per work tile) lives in ring slot gr % kPoolRing as
-        // [pw][64 ch] (+ 8 boundary pixels), 16-byte chunks XOR-swizzled by pw.  Conv row -1 (first band of an
-        // image) and the junk columns x >= W are zeros: neutral for a max over post-ReLU values (the reference
-        // pads with -inf).  A slot may be overwritten once the pool warps have released row gr - kPoolRing.
+        // ===== pooled-stem epilogue, stage 1: TMEM -> (+bias, ReLU) -> bf16 conv rows in a smem ring =====
+        // Two groups of four warps take alternate M-tiles and never synchronise with each other.  Conv
+        // row number `gr` (counted over the whole CTA: 9 per work tile) lives in ring slot gr % kRing as
+        // [x][64 ch] (16-byte chunk index XOR-swizzled by x).  Conv row -1 (first band of an image) is
+        // stored as zeros: neutral for a max over post-ReLU values (the reference pads with -inf).
+        // A row slot may be overwritten once the pool warps have released row gr - kRing (rows_released).
         const int q = warp & 3;
         const int grp = (warp - 4) >> 2;
         const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        const uint32_t row_bytes = (uint32_t)p.W * 128;
         const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
         uint32_t g = 0;
         int tile_idx = 0;
@@ -257,10 +251,8 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_wait(tfull0 + 8 * slot, use & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + slot * 64 + ((uint32_t)(q * 32) << 16);
-                const uint32_t rbase = stage0 + (uint32_t)(gr % kPoolRing) * kPoolRowBytes;
-                const bool keep = valid && y0 + i >= 0;
-                const bool owner = valid && (x & 1) == 0;
-                const int pw = x >> 1;
+                const uint32_t srow = stage0 + (uint32_t)(gr % kPoolRing) * row_bytes + (uint32_t)x * 128;
+                const bool keep = y0 + i >= 0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v[32];
@@ -270,55 +262,38 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         tc_fence_before();
                         mbar_arrive(tempty0 + 8 * slot);
                     }
-                    unsigned c[16];
+                    if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
-                        const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
-                                            __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
-                                            __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
-                                            __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
+                            const float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                                __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                                __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                                __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                            uint4 o;
+                            unsigned* ou = &o.x;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
-                            c[4 * j + k] = keep ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(f[2 * k], 0.f), fmaxf(f[2 * k + 1], 0.f));
+                                ou[k] = keep ? *reinterpret_cast<const unsigned*>(&h2) : 0u;
+                            }
+                            sts128(srow + (((h * 4 + j) ^ (x & 7)) << 4), o);
                         }
                     }
-                    // lane 31's raw pixel -> the row's boundary slot (the left neighbour of the next warp's lane 0)
-                    if (lane == 31 && valid) {
-                        const uint32_t bb = rbase + kPoolRowBytes - 1024 + (uint32_t)((m >> 5) & 7) * 128 + h * 64;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) sts128(bb + j * 16, make_uint4(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]));
-                    }
-                    unsigned hm[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        unsigned l = __shfl_up_sync(0xffffffffu, c[k], 1);
-                        const unsigned r = __shfl_down_sync(0xffffffffu, c[k], 1);
-                        if (lane == 0 || x == 0) l = 0u;  // lane 0: folded in by the pool warps; x == 0: row start
-                        const __nv_bfloat162 a2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&l), *reinterpret_cast<const __nv_bfloat162*>(&c[k]));
-                        const __nv_bfloat162 b2 = __hmax2(a2, *reinterpret_cast<const __nv_bfloat162*>(&r));
-                        hm[k] = *reinterpret_cast<const unsigned*>(&b2);
-                    }
-                    if (owner) {
-                        const uint32_t srow = rbase + (uint32_t)pw * 128;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            sts128(srow + (((h * 4 + j) ^ (pw & 7)) << 4), make_uint4(hm[4 * j], hm[4 * j + 1], hm[4 * j + 2], hm[4 * j + 3]));
-                    }
                 }
-                // this group's 128 threads have written their part of M-tile g
+                // this group's 128 threads have written their rows of M-tile g
                 mbar_arrive(mdone0 + 8 * slot);
             }
         }
     } else if (warp >= 12 && POOL) {
-        // ===== pooled-stem epilogue, stage 2: vertical 3-max over the ring (+ boundary fix-up) -> NHWC [n][56][56][64] =====
-        // Eight pool warps walk the M-tiles in order (mdone barriers), emit pooled row j of a tile as soon as the
-        // M-tile that completes conv row 2j+2 is in the ring, then release the rows nobody needs any more.
+        // ===== pooled-stem epilogue, stage 2: 3x3 / stride-2 / pad-1 max over the ring -> NHWC [n][56][56][64] =====
+        // Eight pool warps walk the M-tiles in order (mdone barriers), emit pooled row j of a tile as soon as
+        // the M-tile that completes conv row 2j+2 is in the ring, then release the rows nobody needs any more.
         const int te = threadIdx.x - 12 * 32;  // 0..255
         volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
         const int Wc = p.W, Wp = p.W >> 1, Hp = p.H >> 1;
+        const uint32_t row_bytes = (uint32_t)Wc * 128;
         const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
         uint32_t g = 0;
         int tile_idx = 0;
@@ -334,27 +309,25 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int j = jnext++;
                     const int prow = (y0 + 1) / 2 + j;
                     const int gr0 = tile_idx * p.R + 2 * j;
+                    const uint32_t r0 = stage0 + (uint32_t)(gr0 % kPoolRing) * row_bytes;
+                    const uint32_t r1 = stage0 + (uint32_t)((gr0 + 1) % kPoolRing) * row_bytes;
+                    const uint32_t r2 = stage0 + (uint32_t)((gr0 + 2) % kPoolRing) * row_bytes;
                     for (int item = te; item < Wp * 8; item += 256) {
                         const int pw = item >> 3, ch = item & 7;
-                        const uint32_t off = (uint32_t)pw * 128 + ((ch ^ (pw & 7)) << 4);
                         __nv_bfloat162 acc[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) acc[k] = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-                        for (int di = 0; di < 3; ++di) {
-                            const int i = 2 * j + di;  // conv row within the tile
-                            const uint32_t rbase = stage0 + (uint32_t)((gr0 + di) % kPoolRing) * kPoolRowBytes;
-                            const uint4 a = lds128(rbase + off);
-                            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int xx = 2 * pw + dx;
+                            if (xx >= 0) {
+                                const uint32_t off = (uint32_t)xx * 128 + ((ch ^ (xx & 7)) << 4);
+                                const uint4 a = lds128(r0 + off), bq = lds128(r1 + off), cq = lds128(r2 + off);
+                                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                                const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&bq);
+                                const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&cq);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], ha[k]);
-                            // the owner lane of x = 2*pw was lane 0 of its warp: its left neighbour sits in the boundary slot
-                            const int m = i * p.P + 2 * pw;
-                            if ((m & 31) == 0 && pw > 0) {
-                                const uint4 bv = lds128(rbase + kPoolRowBytes - 1024 + (uint32_t)(((m - 1) >> 5) & 7) * 128 + ch * 16);
-                                const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&bv);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], hb[k]);
+                                for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], __hmax2(ha[k], __hmax2(hb[k], hc[k])));
                             }
                         }
                         if (prow < Hp)
