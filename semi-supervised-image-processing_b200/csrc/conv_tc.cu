@@ -1,8 +1,9 @@
-// bf16 implicit-GEMM convolution on the Blackwell tensor cores (tcgen05 + TMEM), fed by TMA.
-//
-// Stands in for every Conv2d+BatchNorm2d(+ReLU)(+residual add) group of the frozen ResNet-18 trunk
-// the reference runs at src/feature_extraction.py:290-291 (torchvision/models/resnet.py:89-105,
-// 197-206,266-282).  BN is folded into the weights/bias on the host (engine.cu).
+// bf16 implicit-GEMM convolution on the Blackwell tensor cores (tcgen05 + TMEM), fed by TMA: the
+// PER-TAP kernels.  They serve the Conv2d+BatchNorm2d(+ReLU)(+residual add) groups of the frozen
+// ResNet-18 trunk (src/feature_extraction.py:290-291; torchvision/models/resnet.py:89-105,197-206,
+// 266-282) that the halo-tile kernels of conv_flat.cu do not: the stride-2 3x3 convs, the 1x1/s2
+// downsample convs and all of layer3 / layer4 (14x14 and 7x7 planes).  BN is folded into the
+// weights/bias on the host (engine.cu).
 //
 // GEMM view: M = n*ho*wo output pixels, N = cout, K = (kh, kw, cin) with cin innermost.
 //   * activations are NHWC bf16, so the K-slice of one filter tap (r, s) and 64 input channels of
@@ -11,18 +12,16 @@
 //     K-major SWIZZLE_128B operand tile.  Conv zero padding = TMA out-of-bounds zero fill;
 //     stride-2 convs = TMA element strides.  No im2col buffer ever exists.
 //   * weights are packed [cout][K] bf16; one 2-D TMA load per K-slice gives the B operand tile.
-//   * conv1 (7x7/s2, cin 3) reads the channel-padded, spatially padded staging tensor the
-//     preprocess kernel writes ([230][232][4] per image): the 8-pixel x 4-channel window of one
-//     filter row is 64 contiguous bytes, windows of neighbouring outputs overlap by 48 bytes,
-//     which a tensor map with a 16-byte stride on the `ow` dimension describes directly
-//     (K = 7 rows x 32, SWIZZLE_64B).
-//   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered fp32
-//     accumulator in TMEM; 4 epilogue warps read it back with tcgen05.ld, add the folded-BN bias
-//     and the residual, apply ReLU, and store bf16 NHWC (or fp32 for the layer feeding avgpool).
+//   * one elected thread (elect.sync in warp-uniform code) issues tcgen05.mma into a double-buffered
+//     fp32 accumulator in TMEM; 16 epilogue warps read it back with tcgen05.ld, add the folded-BN
+//     bias (shared memory) and the residual (prefetched before the accumulator wait), apply ReLU, and
+//     store bf16 NHWC (or fp32 for the layer feeding avgpool).
 //   * warp-specialised, persistent over output tiles: warp 0 = TMA producer, warp 1 = MMA issuer,
-//     warp 2 = TMEM allocator, warps 4-19 = epilogue (16 warps: the epilogue of a short-K tile is
-//     longer than its MMAs for four warps); mbarrier rings smem(full/empty) and
-//     tmem(full/empty).
+//     warp 2 = TMEM allocator, warps 4-19 = epilogue; mbarrier rings smem(full/empty), tmem(full/empty).
+//   * tc_conv_kernel: one CTA per 128 x BN tile (BN = 64).  tc2_conv_kernel: CTA PAIR (cta_group::2) per
+//     256 x BN tile (BN = 128 / 256), half of every weight K-block per CTA -- the single-CTA form is bound
+//     by the chip-wide L2->SM delivery (~12.4 TB/s measured); grouped launch of a block's 1x1/s2
+//     downsample conv as extra tiles; split tail wave (half-N units) when the last wave is mostly empty.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
