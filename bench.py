@@ -171,7 +171,7 @@ def synth_host(n: int, seed: int) -> np.ndarray:
     return rng.integers(0, 256, (n, IMG_H, IMG_W, 3), dtype=np.uint8)
 
 
-def run_reference(args, rank: int):
+def run_reference(args, rank: int, json_fd: int):
     """--impl reference: the CPU path alone, rank 0 only."""
     if rank != 0:
         return
@@ -215,7 +215,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line, json_fd)
 
 
 def workload_config(args, world: int):
@@ -230,7 +230,35 @@ def workload_config(args, world: int):
             "parallelism": f"image-sharded dp{world}"}
 
 
+def bind_to_gpu_numa_node(gpu_index: int) -> None:
+    """Pin this process to the CPU cores NVML reports as local to its GPU, so that the pinned host buffers
+    (first touch) and the H2D copies stay on the GPU's socket.  Best effort: silently skipped without NVML."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
+def emit(line: dict, fd: int) -> None:
+    """The ONE JSON line, written to the process's original stdout (everything else, including what NCCL or
+    other native libraries print on fd 1, has been redirected to stderr)."""
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # keep stdout clean for the one JSON line: native libraries (e.g. "NCCL version ...") write to fd 1 as well
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -251,7 +279,7 @@ def main():
         args.batch = 256 if world == 1 else 512
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, json_fd)
         return
 
     if not torch.cuda.is_available():
@@ -260,6 +288,8 @@ def main():
     from ssip_b200.engine import Engine, uniform_descs
     from ssip_b200.feature_extraction import _seeded_backbone
 
+    all_cpus = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -398,6 +428,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core again
         cores = host_cores()
         sample = synth_host(512, 5)
         rate, done, secs = cpu_port_rate(list(sample), 32, args.cpu_budget, cores)
@@ -433,7 +464,7 @@ def main():
             "clocks": clocks,
             "finite": finite,
         }
-        print(json.dumps(line), flush=True)
+        emit(line, json_fd)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
