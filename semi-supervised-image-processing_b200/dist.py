@@ -88,3 +88,23 @@ def concat_in_rank_order(parts: Sequence[Sequence]) -> List:
     for p in parts:
         merged.extend(p)
     return merged
+
+
+def bind_to_gpu_numa_node(gpu_index: int) -> bool:
+    """Pin this process to the CPU cores NVML reports as local to its GPU (host decode threads, pinned staging
+    buffers and H2D copies then stay on the GPU's socket).  Best effort; returns whether the affinity changed."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return True
+    except Exception:
+        pass
+    return False

@@ -378,6 +378,8 @@ def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_s
     eng = get_engine(device, min_batch=batch_size)
     logging.info("Beginning feature extraction over %d records", len(records))
     distributed = fxdist.ensure_process_group("nccl")
+    if distributed:
+        fxdist.bind_to_gpu_numa_node(eng.device_index)  # one rank per GPU: stay on that GPU's socket
     rank, size = fxdist.world()
     lo, hi = fxdist.shard_bounds(len(records), rank, size) if distributed else (0, len(records))
     local, kept, failures, times = _extract_local(records[lo:hi], eng, batch_size)
