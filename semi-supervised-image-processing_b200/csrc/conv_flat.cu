@@ -100,6 +100,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     const int nslice = blockIdx.x % p.ns;
     // contiguous run of work tiles per CTA (balances the short last tile of each image, keeps halo rows in L2)
     const int n_cta = gridDim.x / p.ns, cta = blockIdx.x / p.ns;
@@ -134,11 +135,17 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tslot_ptr;
 
+    // the resident weight slice is constant data: fetch it before waiting for the previous kernel (PDL)
+    if (warp == 0 && elect_one_sync()) {
+        mbar_expect_tx(wbar, TAPS * p.chunks * WTILE);
+        for (int kb = 0; kb < TAPS * p.chunks; ++kb) tma_load_2d(sW + kb * WTILE, &map_b, wbar, kb * (ROWB / 2), nslice * 64);
+    }
+    __syncwarp();
+    pdl_wait();
+
     if (warp == 0) {
-        // ===== TMA producer: the weight slice once, then one halo box per (tile, chunk) =====
+        // ===== TMA producer: one halo box per (tile, chunk) =====
         if (elect_one_sync()) {
-            mbar_expect_tx(wbar, TAPS * p.chunks * WTILE);
-            for (int kb = 0; kb < TAPS * p.chunks; ++kb) tma_load_2d(sW + kb * WTILE, &map_b, wbar, kb * (ROWB / 2), nslice * 64);
             uint32_t stage = 0, phase = 0;
             for (int w = w_first; w < w_last; ++w) {
                 const int img = w / p.tiles_per_img;
@@ -518,6 +525,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     const int nslice = blockIdx.x % p.ns;
     // contiguous run of work tiles per CTA (balances the short last tile of each image, keeps halo rows in L2)
     const int n_cta = gridDim.x / p.ns, cta = blockIdx.x / p.ns;
@@ -551,6 +559,7 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tslot_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         // ===== A producer: one halo box per (tile, chunk) =====
@@ -780,7 +789,7 @@ static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& m
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
     if (grid < p.ns) grid = p.ns;
-    flat_conv_kernel<ROWB, KH, KW, POOL><<<grid, POOL ? kFlatPoolThreads : kFlatThreads, smem, stream>>>(ma, mb, p);
+    FX_CUDA(e, launch_pdl(flat_conv_kernel<ROWB, KH, KW, POOL>, dim3(grid), dim3(POOL ? kFlatPoolThreads : kFlatThreads), smem, stream, ma, mb, p));
     FX_LAUNCH_CHECK(e, "flat_conv_kernel");
     return FX_OK;
 }
@@ -832,7 +841,7 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
     if (grid < p.ns) grid = p.ns;
-    flat128_conv_kernel<<<grid, kFlat128Threads, smem, stream>>>(ma, mb, p);
+    FX_CUDA(e, launch_pdl(flat128_conv_kernel, dim3(grid), dim3(kFlat128Threads), smem, stream, ma, mb, p));
     FX_LAUNCH_CHECK(e, "flat128_conv_kernel");
     return FX_OK;
 }

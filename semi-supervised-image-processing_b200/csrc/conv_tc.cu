@@ -72,6 +72,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_b2, const TcConvParams p) {
     using L = TcSmem<BN, BK, STAGES>;
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = sbase, sB = sbase + STAGES * L::kA;
     const uint32_t bars = sB + STAGES * L::kB;
@@ -107,6 +108,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tslot_ptr;
+    pdl_wait();
 
     const int num_kb = p.kh * p.kw * p.cchunks;
 
@@ -290,6 +292,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_bh, const TcConvParams p) {
     constexpr int kA = 128 * BK * 2, kB = (BN / 2) * BK * 2;
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = sbase, sB = sbase + STAGES * kA;
     const uint32_t bars = sB + STAGES * kB;
@@ -328,6 +331,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tslot_ptr;
+    pdl_wait();
 
     const int num_kb = p.kh * p.kw * p.cchunks;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
@@ -640,7 +644,7 @@ static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb,
         attr_done[e->device & 15] = true;
     }
     const int grid = std::min(p.total_tiles + p.ds_tiles, e->sm_count);
-    tc_conv_kernel<BN, BK, STAGES><<<grid, kTcThreads, L::kTotal, stream>>>(ma, mb, mb2, p);
+    FX_CUDA(e, launch_pdl(tc_conv_kernel<BN, BK, STAGES>, dim3(grid), dim3(kTcThreads), L::kTotal, stream, ma, mb, mb2, p));
     FX_LAUNCH_CHECK(e, "tc_conv_kernel");
     return FX_OK;
 }
@@ -665,7 +669,7 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb
         p.split_full = pair_tiles - tail;
     }
     if (const char* dbg = getenv("FX_DEBUG_TC_PAIRS")) pairs = std::max(1, std::min(pairs, atoi(dbg)));  // fabric experiments only
-    tc2_conv_kernel<BN, BK, STAGES><<<2 * pairs, kTcThreads, kSmem, stream>>>(ma, mb, mb2, mbh, p);  // cluster dims are a kernel attribute
+    FX_CUDA(e, launch_pdl(tc2_conv_kernel<BN, BK, STAGES>, dim3(2 * pairs), dim3(kTcThreads), kSmem, stream, ma, mb, mb2, mbh, p));  // cluster dims are a kernel attribute
     FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
     return FX_OK;
 }

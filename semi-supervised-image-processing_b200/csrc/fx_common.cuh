@@ -151,6 +151,30 @@ const char* cuda_err_text(cudaError_t err);
         (e)->launches++;                                                                             \
     } while (0)
 
+// Programmatic dependent launch: the kernels of a step are launched with the stream-serialization attribute; each
+// signals `launch_dependents` at once and executes `griddepcontrol.wait` after its set-up (barrier init, TMEM
+// allocation, resident-weight loads -- nothing that depends on, or could disturb, an earlier kernel) and BEFORE its
+// first dependent global read or any global write.  The next kernel's prologue then overlaps this kernel's tail.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // preprocess.cu
 enum class PreOut : int { NCHW_F32 = 0, IN0_BF16 = 1, IN0_F32 = 2 };
 int preprocess_init(fx_engine* e);

@@ -386,11 +386,13 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const uint8_t* 
     uint8_t* s_tmp = smem + 3072;                                   // [rows][224*C]
     uint8_t* s_row = s_tmp + tmp_bytes + warp * rowbuf_bytes;       // per-warp staged source row
 
+    pdl_launch_dependents();
     if (MODE == 1) {
         for (int i = tid; i < 768; i += kPreThreads) s_lutb[i] = lut_bf16[i];
     } else {
         for (int i = tid; i < 768; i += kPreThreads) s_lut[i] = lut_f32[i];
     }
+    pdl_wait();  // the staging tensor may still be read by the previous batch's stem kernel
 
     if (img.fast) {  // block-uniform
         preprocess_fast<MODE, NTH, NTV>(src + img.src_off, img, out, s_lut, s_lutb, smem + 3072, y0, y1, blockIdx.y);
@@ -701,8 +703,9 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     if (mode == PreOut::IN0_BF16 && fast_smem) bands = std::max(bands, 15);  // row-pair aligned bands of the fast path
     dim3 grid(bands, n);
     const int ih = nth <= 2 ? 0 : (nth <= 4 ? 1 : 2), iv = ntv <= 2 ? 0 : (ntv <= 4 ? 1 : 2);
-    pre_kernels()[((int)mode * 3 + ih) * 3 + iv]<<<grid, kPreThreads, smem, stream>>>(src_dev, e->img_dev, out, e->lut_f32, e->lut_bf16,
-                                                                                   tmp_bytes, rowbuf);
+    FX_CUDA(e, launch_pdl(pre_kernels()[((int)mode * 3 + ih) * 3 + iv], grid, dim3(kPreThreads), smem, stream, src_dev,
+                          static_cast<const ImgDev*>(e->img_dev), out, static_cast<const float*>(e->lut_f32),
+                          static_cast<const __nv_bfloat16*>(e->lut_bf16), tmp_bytes, rowbuf));
     FX_LAUNCH_CHECK(e, "preprocess_kernel");
     return FX_OK;
 }

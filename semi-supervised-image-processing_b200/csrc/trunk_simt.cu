@@ -222,6 +222,8 @@ int maxpool_3x3s2(fx_engine* e, const void* in, void* out, int n, int h, int w, 
 // ------------------------------------------------------------------------------------------
 template <bool BF16>
 __global__ void avgpool_kernel(const void* __restrict__ in_, float* __restrict__ out, int n, int hw, int c) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * c) return;
     const int img = i / c, ch = i - img * c;
@@ -237,9 +239,9 @@ __global__ void avgpool_kernel(const void* __restrict__ in_, float* __restrict__
 int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n, int hw, int c, cudaStream_t stream) {
     const int total = n * c;
     if (in_is_bf16)
-        avgpool_kernel<true><<<(total + 127) / 128, 128, 0, stream>>>(in, out, n, hw, c);
+        FX_CUDA(e, launch_pdl(avgpool_kernel<true>, dim3((total + 127) / 128), dim3(128), 0, stream, in, out, n, hw, c));
     else
-        avgpool_kernel<false><<<(total + 127) / 128, 128, 0, stream>>>(in, out, n, hw, c);
+        FX_CUDA(e, launch_pdl(avgpool_kernel<false>, dim3((total + 127) / 128), dim3(128), 0, stream, in, out, n, hw, c));
     FX_LAUNCH_CHECK(e, "avgpool_kernel");
     return FX_OK;
 }
