@@ -49,6 +49,8 @@ typedef enum fx_precision { FX_PRECISION_BF16 = 0, FX_PRECISION_FP32 = 1 } fx_pr
 #define FX_CROP 224
 #define FX_EMBED_DIM 512
 #define FX_NUM_CONV_LAYERS 20
+#define FX_MAX_LANES 2
+#define FX_HOST_SLOTS 4
 
 /*
  * One decoded image inside a packed uint8 buffer, exactly what PIL hands the reference's
@@ -137,6 +139,17 @@ int fx_forward(fx_handle h, int n, float *emb_dev, void *stream);
  * batch_tensor) instead of running the preprocess kernel; lets the trunk be checked alone. */
 int fx_stage_nchw_f32(fx_handle h, const float *in_dev, int n, void *stream);
 
+/*
+ * Lanes.  A handle owns FX_MAX_LANES independent sets of staging / activation buffers (the weights are shared).
+ * fx_select_lane makes `lane` the target of the following fx_preprocess / fx_stage_nchw_f32 / fx_forward / fx_embed
+ * calls on this handle.  Batches queued on DIFFERENT lanes and DIFFERENT streams are independent and overlap on the
+ * GPU: every trunk kernel is a persistent one-CTA-per-SM grid, so the other lane's kernels fill the SMs that the tail
+ * of each kernel (and the launch gap behind it) leaves idle -- about +7 % images/s at batch 256.  The reference loop
+ * (src/feature_extraction.py:272-300) is strictly serial; results do not depend on the lane.  Lane 0 exists from
+ * fx_create, lane 1 is allocated on first selection.  The host-buffer slots below use lane == slot by themselves.
+ */
+int fx_select_lane(fx_handle h, int lane);
+
 /* fx_preprocess + fx_forward. */
 int fx_embed(fx_handle h, const uint8_t *src_dev, const fx_image_desc *descs_host, int n, float *emb_dev,
              void *stream);
@@ -151,11 +164,12 @@ int fx_embed_host(fx_handle h, const uint8_t *src_host, size_t total_bytes, cons
                   int n, float *emb_host);
 
 /*
- * The same, pipelined: two slots (0, 1).  fx_embed_host_async queues the H2D copy of the batch on the
- * library's copy stream, the kernels and the D2H of the embeddings on its compute stream, and returns;
- * fx_embed_host_wait(slot) blocks until that slot's embeddings are in emb_host.  Alternating the slots
- * overlaps the copy of batch i+1 with the kernels of batch i.  src_host / emb_host must stay valid (and
- * should be pinned) until the wait returns.  fx_embed_host == async on slot 0 + wait.
+ * The same, pipelined over FX_HOST_SLOTS slots (0..3).  fx_embed_host_async queues the H2D copy of the batch on the
+ * library's copy stream, then the kernels and the D2H of the embeddings on the compute stream of lane (slot % 2), and
+ * returns; fx_embed_host_wait(slot) blocks until that slot's embeddings are in emb_host.  Cycling through the slots
+ * keeps two batches computing (one per lane, overlapping each other's kernel tails) while the copies of the next
+ * ones are already in flight.  src_host / emb_host must stay valid (and should be pinned) until the wait returns.
+ * fx_embed_host == async on slot 0 + wait.
  */
 int fx_embed_host_async(fx_handle h, int slot, const uint8_t *src_host, size_t total_bytes,
                         const fx_image_desc *descs_host, int n, float *emb_host);
@@ -189,6 +203,11 @@ int fx_debug_conv(fx_handle h, const fx_conv_bn *layer, int hin, int win, const 
  * (torchvision/models/resnet.py:197-200,268-271).  in_dev fp32 NHWC [n][224][224][3] (normalised),
  * out_dev fp32 NHWC [n][56][56][64].  BF16 engines only.  Synchronises `stream`. */
 int fx_debug_stem_pool(fx_handle h, const fx_conv_bn *layer, const float *in_dev, int n, float *out_dev, void *stream);
+
+/* Copy the raw conv1 staging buffer of the first n staged images to out_dev (device pointer, `bytes` must be
+ * n * per-image size: bf16 [115][116][16] space-to-depth = 426,880 B, fp32 [230][232][4] = 853,760 B).  Lets
+ * tests compare what fx_preprocess hands the trunk with the oracle, padding included.  Synchronises `stream`. */
+int fx_debug_staging(fx_handle h, int n, void *out_dev, size_t bytes, void *stream);
 
 /* Copy out the folded parameters of loaded layer `layer` as the kernels see them (fp32,
  * [cout][kh][kw][cin] order, bf16-rounded in BF16 precision) -- host pointers, either may be NULL. */

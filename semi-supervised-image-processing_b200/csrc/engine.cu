@@ -37,6 +37,9 @@ int set_error(fx_engine* e, int code, const std::string& msg) {
     return code;
 }
 
+void lane_store(fx_engine* e);
+int select_lane(fx_engine* e, int lane);
+
 // Input spatial size of every conv layer of the 224x224 network, in fx_load_weights order.
 static const int kLayerHin[kNumLayers] = {224, 56, 56, 56, 56, 56, 28, 56, 28, 28, 28, 14, 28, 14, 14, 14, 7, 14, 7, 7};
 
@@ -203,6 +206,70 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
     return avgpool_7x7(e, e->final_f32, false, emb, n, 49, kEmbed, stream);
 }
 
+// ---- lanes (fx_common.cuh): the engine's per-batch fields are the active lane's; swap on selection ----
+void lane_store(fx_engine* e) {
+    fx_engine::Lane& ln = e->lanes[e->cur_lane];
+    ln.in0 = e->in0;
+    for (int i = 0; i < 3; ++i) ln.act[i] = e->act[i];
+    ln.final_f32 = e->final_f32;
+    ln.img_dev = e->img_dev;
+    ln.img_host = e->img_host;
+    ln.img_host_free = e->img_host_free;
+    ln.staged = e->staged;
+}
+
+static void lane_load(fx_engine* e, int lane) {
+    const fx_engine::Lane& ln = e->lanes[lane];
+    e->cur_lane = lane;
+    e->in0 = ln.in0;
+    for (int i = 0; i < 3; ++i) e->act[i] = ln.act[i];
+    e->final_f32 = ln.final_f32;
+    e->img_dev = ln.img_dev;
+    e->img_host = ln.img_host;
+    e->img_host_free = ln.img_host_free;
+    e->staged = ln.staged;
+}
+
+// Allocate the active lane's buffers (its fields must be null).
+static int lane_alloc(fx_engine* e) {
+    const bool bf16 = e->precision == FX_PRECISION_BF16;
+    const size_t esz = bf16 ? 2 : 4, mb = (size_t)e->max_batch;
+    const size_t in0_bytes = bf16 ? mb * kS2dH * kS2dW * kS2dC * 2 : mb * kIn0H * kIn0W * kIn0C * 4;
+    e->act_bytes = mb * 112 * 112 * 64 * esz;  // largest activation: the conv1 output of the unfused (fp32) stem
+    int rc = FX_OK;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (rc != FX_OK) return;
+        cudaError_t a = cudaMalloc(p, bytes);
+        if (a != cudaSuccess) rc = set_error(e, a == cudaErrorMemoryAllocation ? FX_ERR_NOMEM : FX_ERR_CUDA,
+                                             std::string("cudaMalloc: ") + cudaGetErrorString(a));
+    };
+    alloc(&e->in0, in0_bytes);
+    alloc(&e->act[0], mb * 56 * 56 * 64 * esz);
+    alloc(&e->act[1], e->act_bytes);
+    alloc(&e->act[2], mb * 56 * 56 * 64 * esz);
+    alloc(reinterpret_cast<void**>(&e->final_f32), mb * 49 * kEmbed * sizeof(float));
+    if (rc != FX_OK) return rc;
+    // the pad region of the staging tensor is conv zero padding and is never written again
+    FX_CUDA(e, cudaMemset(e->in0, 0, in0_bytes));
+    if ((rc = preprocess_lane_init(e)) != FX_OK) return rc;
+    e->staged = 0;
+    e->lanes[e->cur_lane].allocated = true;
+    return FX_OK;
+}
+
+int select_lane(fx_engine* e, int lane) {
+    if (lane < 0 || lane >= FX_MAX_LANES) return set_error(e, FX_ERR_INVALID, "lane out of range");
+    if (lane == e->cur_lane) return FX_OK;
+    lane_store(e);
+    lane_load(e, lane);
+    if (!e->lanes[lane].allocated) {
+        int rc = lane_alloc(e);
+        lane_store(e);
+        if (rc != FX_OK) return rc;
+    }
+    return FX_OK;
+}
+
 }  // namespace fx
 
 using namespace fx;
@@ -225,19 +292,26 @@ void fx_destroy(fx_handle e) {
     for (auto& L : e->layers) free_layer(L);
     preprocess_free(e);
     tc_free(e);
-    cudaFree(e->in0);
-    for (auto& a : e->act) cudaFree(a);
-    cudaFree(e->final_f32);
+    lane_store(e);
+    for (auto& ln : e->lanes) {
+        cudaFree(ln.in0);
+        for (auto& a : ln.act) cudaFree(a);
+        cudaFree(ln.final_f32);
+        cudaFree(ln.img_dev);
+        if (ln.img_host) cudaFreeHost(ln.img_host);
+        if (ln.img_host_free) cudaEventDestroy(ln.img_host_free);
+    }
     for (auto& hs : e->slots) {
         cudaFree(hs.src_dev);
         cudaFree(hs.emb_dev);
         if (hs.copied) cudaEventDestroy(hs.copied);
         if (hs.done) cudaEventDestroy(hs.done);
     }
+    for (auto& st : e->lane_stream)
+        if (st) cudaStreamDestroy(st);
     cudaFree(e->emb_dev);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
-    if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
 }
@@ -274,28 +348,12 @@ int fx_create(fx_handle* out, int device, int max_batch, int precision) {
         fx_destroy(e);
         return rc;
     };
-    const size_t esz = precision == FX_PRECISION_BF16 ? 2 : 4;
-    const size_t in0_bytes = precision == FX_PRECISION_BF16 ? (size_t)max_batch * kS2dH * kS2dW * kS2dC * 2
-                                                            : (size_t)max_batch * kIn0H * kIn0W * kIn0C * 4;
-    e->act_bytes = (size_t)max_batch * 112 * 112 * 64 * esz;  // largest activation: conv1 output
-    int rc = FX_OK;
-    auto alloc = [&](void** p, size_t bytes) {
-        if (rc != FX_OK) return;
-        cudaError_t a = cudaMalloc(p, bytes);
-        if (a != cudaSuccess) rc = set_error(e, a == cudaErrorMemoryAllocation ? FX_ERR_NOMEM : FX_ERR_CUDA,
-                                             std::string("cudaMalloc: ") + cudaGetErrorString(a));
-    };
-    alloc(&e->in0, in0_bytes);
-    alloc(&e->act[0], (size_t)max_batch * 56 * 56 * 64 * esz);
-    alloc(&e->act[1], e->act_bytes);
-    alloc(&e->act[2], (size_t)max_batch * 56 * 56 * 64 * esz);
-    alloc(reinterpret_cast<void**>(&e->final_f32), (size_t)max_batch * 49 * kEmbed * sizeof(float));
-    alloc(reinterpret_cast<void**>(&e->emb_dev), (size_t)max_batch * kEmbed * sizeof(float));
+    int rc = lane_alloc(e);  // lane 0
     if (rc != FX_OK) return fail(rc);
-    // the pad region of the staging tensor is conv zero padding and is never written again
-    if ((err = cudaMemset(e->in0, 0, in0_bytes)) != cudaSuccess) return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
-    if ((err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
-        return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
+    {
+        cudaError_t a = cudaMalloc(reinterpret_cast<void**>(&e->emb_dev), (size_t)max_batch * kEmbed * sizeof(float));
+        if (a != cudaSuccess) return fail(set_error(e, FX_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(a)));
+    }
     if ((err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
     if ((rc = preprocess_init(e)) != FX_OK) return fail(rc);
@@ -364,18 +422,24 @@ int fx_forward(fx_handle e, int n, float* emb_dev, void* stream) {
     return forward(e, n, emb_dev, static_cast<cudaStream_t>(stream));
 }
 
+int fx_select_lane(fx_handle e, int lane) {
+    if (!e) return FX_ERR_INVALID;
+    FX_CUDA(e, cudaSetDevice(e->device));
+    return select_lane(e, lane);
+}
+
 int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, int n, float* emb_dev, void* stream) {
     int rc = fx_preprocess(e, src_dev, descs, n, stream);
     if (rc != FX_OK) return rc;
     return fx_forward(e, n, emb_dev, stream);
 }
 
-// Host-buffer path, pipelined over two slots: the H2D copy of one batch (copy stream) overlaps the
-// kernels of the previous one (compute stream); the D2H of the embeddings follows the kernels.
+// Host-buffer path, pipelined over FX_HOST_SLOTS slots: the H2D copy of a batch (copy stream) overlaps the kernels
+// of the earlier ones (two lane streams); the D2H of the embeddings follows the kernels on the lane's stream.
 int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
                         float* emb_host) {
     if (!e) return FX_ERR_INVALID;
-    if (slot < 0 || slot > 1 || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || !emb_host)))
+    if (slot < 0 || slot >= FX_HOST_SLOTS || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || !emb_host)))
         return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: bad arguments");
     for (int i = 0; i < n; ++i) {
         const size_t need = descs[i].offset + (size_t)descs[i].height * descs[i].width * descs[i].channels;
@@ -405,10 +469,16 @@ int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t t
     }
     FX_CUDA(e, cudaMemcpyAsync(hs.src_dev, src_host, total_bytes, cudaMemcpyHostToDevice, e->copy_stream));
     FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
-    cudaStream_t s = e->own_stream;
+    const int lane = slot % FX_MAX_LANES;
+    if (!e->lane_stream[lane]) FX_CUDA(e, cudaStreamCreateWithFlags(&e->lane_stream[lane], cudaStreamNonBlocking));
+    cudaStream_t s = e->lane_stream[lane];
     FX_CUDA(e, cudaStreamWaitEvent(s, hs.copied, 0));
-    int rc = fx_embed(e, hs.src_dev, descs, n, hs.emb_dev, s);
+    const int caller_lane = e->cur_lane;  // the caller's selection is restored afterwards
+    int rc = select_lane(e, lane);
+    if (rc == FX_OK) rc = fx_embed(e, hs.src_dev, descs, n, hs.emb_dev, s);
+    const int rc2 = select_lane(e, caller_lane);
     if (rc != FX_OK) return rc;
+    if (rc2 != FX_OK) return rc2;
     FX_CUDA(e, cudaMemcpyAsync(emb_host, hs.emb_dev, sizeof(float) * kEmbed * n, cudaMemcpyDeviceToHost, s));
     FX_CUDA(e, cudaEventRecord(hs.done, s));
     hs.busy = true;
@@ -417,7 +487,7 @@ int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t t
 
 int fx_embed_host_wait(fx_handle e, int slot) {
     if (!e) return FX_ERR_INVALID;
-    if (slot < 0 || slot > 1) return set_error(e, FX_ERR_INVALID, "fx_embed_host_wait: bad slot");
+    if (slot < 0 || slot >= FX_HOST_SLOTS) return set_error(e, FX_ERR_INVALID, "fx_embed_host_wait: bad slot");
     fx_engine::HostSlot& hs = e->slots[slot];
     if (!hs.busy) return FX_OK;
     FX_CUDA(e, cudaSetDevice(e->device));
@@ -534,6 +604,17 @@ int fx_debug_stem_pool(fx_handle e, const fx_conv_bn* layer, const float* in_dev
     free_layer(L);
     if (rc == FX_OK && serr != cudaSuccess) rc = set_error(e, FX_ERR_CUDA, std::string("fx_debug_stem_pool: ") + cudaGetErrorString(serr));
     return rc;
+}
+
+int fx_debug_staging(fx_handle e, int n, void* out_dev, size_t bytes, void* stream_) {
+    if (!e) return FX_ERR_INVALID;
+    const size_t per = e->precision == FX_PRECISION_BF16 ? (size_t)kS2dH * kS2dW * kS2dC * 2 : (size_t)kIn0H * kIn0W * kIn0C * 4;
+    if (n < 0 || n > e->staged || !out_dev || bytes != per * (size_t)n) return set_error(e, FX_ERR_INVALID, "fx_debug_staging: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    FX_CUDA(e, cudaMemcpyAsync(out_dev, e->in0, bytes, cudaMemcpyDeviceToDevice, stream));
+    FX_CUDA(e, cudaStreamSynchronize(stream));
+    return FX_OK;
 }
 
 int fx_debug_folded(fx_handle e, int layer, float* weight_host, float* bias_host) {

@@ -56,12 +56,16 @@ struct GeomTableHost {
     int max_rows;            // source rows a band touches (upper bound)
     int col_lo, col_hi;      // source pixel columns touched by the crop [lo, hi)
     int cnt_h, cnt_v;        // largest tap count actually used inside the crop, per axis
+    int s2d_rows;            // source rows a band of the s2d kernel touches (upper bound)
+    bool noclip;             // all taps >= 0 and sums small enough that clip8 never clips
     std::vector<int32_t> blob;  // packed device image, layout in preprocess.cu
 };
 
 struct GeomEntry {
     int32_t* dev = nullptr;  // device copy of blob
     int ksh = 0, ksv = 0, band = 0, max_rows = 0, col_lo = 0, col_hi = 0, cnt_h = 0, cnt_v = 0;
+    int s2d_rows = 0;
+    bool noclip = false;
 };
 
 // Per-image record consumed by the preprocess kernel.
@@ -104,6 +108,9 @@ struct fx_engine {
     fx::ImgDev* img_dev = nullptr;       // [max_batch]
     fx::ImgDev* img_host = nullptr;      // pinned, [max_batch]
     cudaEvent_t img_host_free = nullptr; // img_host may be rewritten once this has fired
+    float norm_a[3] = {}, norm_b[3] = {};  // Normalize o ToTensor as one FMA per value (preprocess.cu, NormFma)
+    bool norm_fma_ok = false;            // ... proven equal to the bf16 table for all 768 inputs at start-up
+    bool pre_force_banded = false;       // FX_DEBUG_PRE_BANDED=1: measurement knob (preprocess.cu)
 
     // trunk
     fx::PackedLayer layers[fx::kNumLayers];
@@ -117,17 +124,36 @@ struct fx_engine {
     bool prof_on = false;
     cudaEvent_t prof_ev[2 * (FX_NUM_CONV_LAYERS + 1)] = {};
 
-    // host-buffer path (fx_embed_host*): two pipelined slots
+    // Lanes: independent sets of the per-batch buffers above (in0, act, final_f32, img_dev, img_host, img_host_free,
+    // staged).  The fields above are the ACTIVE lane's; fx_select_lane swaps them with the stored copy.  Batches
+    // queued on different lanes and different streams overlap on the GPU: every trunk kernel is a persistent
+    // one-CTA-per-SM grid, so the CTAs of the other lane's next kernel fill the SMs that a kernel's tail (and the
+    // launch gap behind it) would leave idle.  Lane 1 is allocated on first use.
+    struct Lane {
+        void* in0 = nullptr;
+        void* act[3] = {nullptr, nullptr, nullptr};
+        float* final_f32 = nullptr;
+        fx::ImgDev* img_dev = nullptr;
+        fx::ImgDev* img_host = nullptr;
+        cudaEvent_t img_host_free = nullptr;
+        int staged = 0;
+        bool allocated = false;
+    } lanes[FX_MAX_LANES];
+    int cur_lane = 0;
+
+    // host-buffer path (fx_embed_host*): FX_HOST_SLOTS pipelined slots (device copies of one batch's packed images and
+    // embeddings); slot s computes on lane s % FX_MAX_LANES, whose stream serialises the slots that share its buffers.
+    // Four slots keep two batches computing (one per lane) while the H2D copies of the next two are already queued.
     struct HostSlot {
         uint8_t* src_dev = nullptr;
         size_t cap = 0;
         float* emb_dev = nullptr;
         cudaEvent_t copied = nullptr, done = nullptr;
         bool busy = false;
-    } slots[2];
+    } slots[FX_HOST_SLOTS];
     float* emb_dev = nullptr;
-    cudaStream_t own_stream = nullptr;   // kernels + D2H of the host-buffer path
-    cudaStream_t copy_stream = nullptr;  // H2D of the host-buffer path
+    cudaStream_t lane_stream[FX_MAX_LANES] = {};  // kernels + D2H of the host-buffer path, one per lane
+    cudaStream_t copy_stream = nullptr;           // H2D of the host-buffer path
 };
 
 namespace fx {
@@ -179,6 +205,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 enum class PreOut : int { NCHW_F32 = 0, IN0_BF16 = 1, IN0_F32 = 2 };
 int preprocess_init(fx_engine* e);
 void preprocess_free(fx_engine* e);
+int preprocess_lane_init(fx_engine* e);  // per-lane descriptor buffers -> the active lane's fields
 int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode,
                    void* out, cudaStream_t stream);
 int stage_nchw_run(fx_engine* e, const float* in_dev, int n, cudaStream_t stream);

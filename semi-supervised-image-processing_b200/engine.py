@@ -96,6 +96,11 @@ class Engine:
     def _stream(self) -> ctypes.c_void_p:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def select_lane(self, lane: int) -> None:
+        """Target lane (0/1) of the following preprocess/forward/embed_device calls: an independent set of staging and
+        activation buffers, so that batches queued on different lanes and different CUDA streams overlap (fx_select_lane)."""
+        self._check(self._lib.fx_select_lane(self._h, int(lane)))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.fx_launch_count(self._h))
@@ -193,7 +198,8 @@ class Engine:
         return out
 
     def embed_host_async(self, slot: int, packed_host, descs, n: int, total_bytes: int, out) -> None:
-        """Queue one host batch on pipeline slot 0/1 (H2D overlaps the previous batch's kernels); pair with embed_host_wait."""
+        """Queue one host batch on pipeline slot 0..HOST_SLOTS-1 (H2D overlaps earlier batches' kernels, which run on lane
+        slot % 2); pair with embed_host_wait."""
         src_ptr = packed_host.data_ptr() if isinstance(packed_host, torch.Tensor) else packed_host.ctypes.data
         dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
         self._slot_keep[slot] = (packed_host, descs, out)  # the library reads/writes them until the wait
@@ -213,6 +219,17 @@ class Engine:
         return np.concatenate(chunks, axis=0) if chunks else np.empty((0, N.EMBED_DIM), np.float32)
 
     # -- test hooks ---------------------------------------------------------------------------
+    def staged_crop(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """What fx_preprocess handed the trunk (bf16 engines): the raw space-to-depth staging tensor
+        [n,115,116,16] and its rearrangement back to the zero-padded crop [n,3,230,232] (both bf16, on the device)."""
+        if self.precision != "bf16":
+            raise TypeError("staged_crop: bf16 engines only")
+        raw = torch.empty((n, 115, 116, 16), dtype=torch.bfloat16, device=self.device)
+        self._check(self._lib.fx_debug_staging(self._h, n, raw.data_ptr(), raw.numel() * 2, self._stream()))
+        # channel (dy*2+dx)*3+c of s2d pixel (Y, X) = padded pixel (2Y+dy, 2X+dx), channel c
+        v = raw[..., :12].reshape(n, 115, 116, 2, 2, 3).permute(0, 5, 1, 3, 2, 4).reshape(n, 3, 230, 232)
+        return raw, v
+
     def debug_conv(self, weight: torch.Tensor, bn: Optional[Dict[str, torch.Tensor]], stride: int, pad: int,
                    x_nhwc: torch.Tensor, residual_nhwc: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
         """Run one conv+bn group through the library: x fp32 NHWC CUDA -> fp32 NHWC CUDA."""

@@ -37,6 +37,7 @@ import numpy as np
 import torch
 from PIL import Image, UnidentifiedImageError
 
+from . import _native as N
 from . import dist as fxdist
 from .engine import Engine, pack_images
 
@@ -310,17 +311,19 @@ def _load_file(path: Path):
 def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int):
     """Single-GPU pass over `records`: embeddings + bookkeeping.
 
-    Two pipeline slots (fx_embed_host_async): while the GPU works on batch i, the host decodes batch i+1
-    into the other pinned staging buffer and its H2D copy overlaps the kernels of batch i.
+    Pipeline slots (fx_embed_host_async, N.HOST_SLOTS of them): while the GPU works on earlier batches (two at a
+    time, one per engine lane), the host decodes the next one into a free pinned staging buffer and its H2D copy
+    overlaps their kernels.
     """
     kept: List[int] = []
     failures: List[Path] = []
     times: List[float] = []
     blocks: List[np.ndarray] = []
     threads = int(os.environ.get(DECODE_THREADS_ENV, "0")) or min(32, (os.cpu_count() or 8))
-    staging: List[Optional[torch.Tensor]] = [None, None]
-    outs = [torch.empty((batch_size, 512), dtype=torch.float32).pin_memory() for _ in range(2)]
-    pending: List[Optional[Tuple[List[int], int]]] = [None, None]  # per slot: (record indices, n)
+    nslots = N.HOST_SLOTS
+    staging: List[Optional[torch.Tensor]] = [None] * nslots
+    outs = [torch.empty((batch_size, 512), dtype=torch.float32).pin_memory() for _ in range(nslots)]
+    pending: List[Optional[Tuple[List[int], int]]] = [None] * nslots  # per slot: (record indices, n)
     t_last = time.perf_counter()
 
     def finish(slot: int) -> None:
@@ -358,9 +361,9 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
             _, descs, total = pack_images(arrays, out=staging[slot].numpy())
             eng.embed_host_async(slot, staging[slot], descs, len(arrays), total, outs[slot])
             pending[slot] = (ok, len(arrays))
-            slot ^= 1
-        finish(slot)
-        finish(slot ^ 1)
+            slot = (slot + 1) % nslots
+        for k in range(nslots):  # oldest first
+            finish((slot + k) % nslots)
     order = np.argsort(np.asarray(kept, dtype=np.int64), kind="stable") if kept else np.zeros(0, np.int64)
     local = np.concatenate(blocks, axis=0)[order] if blocks else np.empty((0, 512), np.float32)
     kept = [kept[i] for i in order]

@@ -113,8 +113,10 @@ def test_channel_policy_errors_propagate_like_the_reference(tmp_path):
 
 
 def test_pipelined_slots_equal_the_synchronous_call():
+    from ssip_b200 import _native as N
+
     eng = fx.get_engine(torch.device("cuda:0"), min_batch=16)
-    batches = [list(synthetic.noise_images(16, 224, 224, seed=s)) for s in range(4)]
+    batches = [list(synthetic.noise_images(16, 224, 224, seed=s)) for s in range(7)]
     sync = []
     packed = []
     for b in batches:
@@ -122,14 +124,17 @@ def test_pipelined_slots_equal_the_synchronous_call():
         pinned = torch.from_numpy(buf.copy()).pin_memory()
         packed.append((pinned, descs, total))
         sync.append(eng.embed_host(pinned, descs, 16, total))
-    outs = [torch.empty((16, 512)).pin_memory() for _ in range(4)]
-    for i, (pinned, descs, total) in enumerate(packed):
-        eng.embed_host_wait(i & 1)
-        eng.embed_host_async(i & 1, pinned, descs, 16, total, outs[i])
-    eng.embed_host_wait(0)
-    eng.embed_host_wait(1)
-    for i in range(4):
-        assert np.array_equal(outs[i].numpy(), sync[i])
+    for nslots in (2, N.HOST_SLOTS):  # slots cycle over both lanes; more batches than slots -> every slot is reused
+        outs = [torch.empty((16, 512)).pin_memory() for _ in batches]
+        for i, (pinned, descs, total) in enumerate(packed):
+            eng.embed_host_wait(i % nslots)
+            eng.embed_host_async(i % nslots, pinned, descs, 16, total, outs[i])
+        for s in range(nslots):
+            eng.embed_host_wait(s)
+        for i in range(len(batches)):
+            assert np.array_equal(outs[i].numpy(), sync[i])
+    with pytest.raises(N.FxError):
+        eng.embed_host_async(N.HOST_SLOTS, packed[0][0], packed[0][1], 16, packed[0][2], outs[0])
 
 
 def test_config1_256_png_images_batch_32(tmp_path_factory):

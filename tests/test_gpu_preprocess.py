@@ -97,3 +97,53 @@ def test_errors_are_loud(eng):
         eng.preprocess_nchw(torch.from_numpy(buf).cuda(), descs, 1)
     assert err.value.status == N.FX_ERR_UNSUPPORTED
     assert eng.preprocess_nchw(torch.zeros(16, dtype=torch.uint8).cuda(), uniform_descs(0, 1, 1), 0).shape[0] == 0
+
+
+# ---- bf16 conv1 staging tensor (what the trunk actually reads) ------------------------------------
+
+@pytest.fixture(scope="module")
+def eng_b():
+    e = Engine(0, max_batch=64, precision="bf16")
+    yield e
+    e.close()
+
+
+def _check_staging(eng_b, images):
+    buf, descs, total = pack_images(images)
+    dev = torch.from_numpy(buf[: max(total, 1)]).cuda()
+    eng_b.preprocess(dev, descs, len(images))
+    raw, padded = eng_b.staged_crop(len(images))
+    raw, padded = raw.cpu(), padded.cpu()
+    for i, img in enumerate(images):
+        want = torch.from_numpy(rp.c_preprocess_rgb(img if img.ndim == 3 else np.repeat(img[:, :, None], 3, 2))).to(torch.bfloat16)
+        assert torch.equal(padded[i, :, 3:227, 3:227], want), f"image {i} {img.shape}"
+    # conv zero padding of the normalised tensor + unused channels / column: exactly zero
+    z = padded.clone()
+    z[:, :, 3:227, 3:227] = 0
+    assert not z.any()
+    assert not raw[..., 12:].any()
+
+
+@pytest.mark.parametrize("shape", [(224, 224), (512, 512), (256, 256), (300, 500), (500, 300), (448, 448), (225, 224), (640, 480), (100, 130)])
+def test_bf16_staging_column_walk_kernel_bit_exact(eng_b, shape):
+    """All-RGB, few-tap batches take preprocess_s2d_kernel: staging == bf16(oracle), padding == 0."""
+    _check_staging(eng_b, synthetic.ragged_images([shape] * 3, seed=shape[0] + shape[1]))
+
+
+def test_bf16_staging_mixed_batch_and_gray(eng_b):
+    """Mixed geometry classes (incl. >5 taps and gray carriage) fall back to the banded kernel; same contract."""
+    imgs = synthetic.ragged_images([(224, 224), (1000, 700), (512, 512), (2048, 1536), (61, 67)], seed=3)
+    imgs.append(np.ascontiguousarray(synthetic.mri_like_images(1, 512, seed=4)[0][..., 0]))
+    _check_staging(eng_b, imgs)
+    # a fast batch right after a mixed one reuses the same staging buffer: padding must still be zero
+    _check_staging(eng_b, list(synthetic.noise_images(64, 224, 224, seed=1)))
+
+
+def test_bf16_staging_equals_the_fp32_transform_rounded(eng_b, eng):
+    x = list(synthetic.mri_like_images(5, 512, seed=9))
+    buf, descs, total = pack_images(x)
+    dev = torch.from_numpy(buf[:total]).cuda()
+    f32 = eng.preprocess_nchw(dev, descs, len(x))
+    eng_b.preprocess(dev, descs, len(x))
+    _, padded = eng_b.staged_crop(len(x))
+    assert torch.equal(padded[:, :, 3:227, 3:227], f32.to(torch.bfloat16))

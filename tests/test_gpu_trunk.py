@@ -15,6 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import reference_path as rp
+from ssip_b200 import _native as N
 from ssip_b200 import synthetic
 from ssip_b200.engine import Engine, pack_images, uniform_descs
 
@@ -266,3 +267,30 @@ def test_device_resident_path_and_launch_count(eng_bf16):
     host = _embed(eng_bf16, list(x))
     assert np.array_equal(out.cpu().numpy(), host)
     assert np.isfinite(host).all()
+
+
+def test_lanes_are_independent_and_give_identical_rows(eng_bf16):
+    """fx_select_lane: two batches in flight on two lanes / two streams give the rows the serial path gives."""
+    eng_bf16.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+    xa = synthetic.noise_images(24, 224, 224, seed=31)
+    xb = synthetic.mri_like_images(24, 512, seed=32)
+    want_a, want_b = _embed(eng_bf16, list(xa)), _embed(eng_bf16, list(xb))
+    da = torch.from_numpy(xa.reshape(-1)).cuda()
+    db = torch.from_numpy(xb.reshape(-1)).cuda()
+    s1 = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):  # interleave: lane 0 / default stream, lane 1 / side stream
+        eng_bf16.select_lane(0)
+        oa = eng_bf16.embed_device(da, uniform_descs(24, 224, 224), 24)
+        eng_bf16.select_lane(1)
+        with torch.cuda.stream(s1):
+            ob = eng_bf16.embed_device(db, uniform_descs(24, 512, 512), 24)
+        outs.append((oa, ob))
+    eng_bf16.select_lane(0)
+    torch.cuda.synchronize()
+    for oa, ob in outs:
+        assert np.array_equal(oa.cpu().numpy(), want_a)
+        assert np.array_equal(ob.cpu().numpy(), want_b)
+    with pytest.raises(N.FxError):
+        eng_bf16.select_lane(2)
