@@ -51,6 +51,11 @@ typedef enum fx_precision { FX_PRECISION_BF16 = 0, FX_PRECISION_FP32 = 1 } fx_pr
 #define FX_NUM_CONV_LAYERS 20
 #define FX_MAX_LANES 2
 #define FX_HOST_SLOTS 4
+#define FX_MAX_CLASSES 32
+
+/* Geometry of the fused preprocess (fx_set_transform). */
+#define FX_TRANSFORM_EXTRACT 0   /* Resize(256) -> CenterCrop(224): src/feature_extraction.py:200-207 (default) */
+#define FX_TRANSFORM_SQUARE224 1 /* Resize((224,224)), no crop: eval transform of src/training/common.py:111-117 */
 
 /*
  * One decoded image inside a packed uint8 buffer, exactly what PIL hands the reference's
@@ -149,6 +154,29 @@ int fx_stage_nchw_f32(fx_handle h, const float *in_dev, int n, void *stream);
  * fx_create, lane 1 is allocated on first selection.  The host-buffer slots below use lane == slot by themselves.
  */
 int fx_select_lane(fx_handle h, int lane);
+
+/*
+ * Which deterministic transform the preprocess kernels apply from now on (all lanes).  Both end in ToTensor +
+ * Normalize with the ImageNet constants and use Pillow's fixed-point antialiased bilinear resampler, bit-exactly.
+ * FX_TRANSFORM_SQUARE224 is the reference's evaluation transform for the classifier-head inference paths
+ * (generate_pseudo_labels src/training/semi_supervised.py:44-72, evaluate_model src/training/common.py:439-506,
+ * compute_probs src/threshold_sweep.py:21-38): each axis is resampled independently to 224, nothing is cropped.
+ */
+int fx_set_transform(fx_handle h, int transform);
+
+/*
+ * Classifier head of the fine-tuned model (create_model, src/training/common.py:299-304: resnet18 with
+ * fc = nn.Linear(512, num_classes)): weight fp32 [num_classes][512], bias fp32 [num_classes] (host pointers).
+ */
+int fx_load_head(fx_handle h, const float *weight, const float *bias, int num_classes);
+
+/*
+ * Replaces `outputs = model(inputs); probs = torch.softmax(outputs, dim=1)` of the three inference loops named
+ * above on the n images staged on the active lane: trunk -> emb_dev fp32 [n][512] (required, caller owned) ->
+ * logits_dev fp32 [n][num_classes] and probs_dev fp32 [n][num_classes] (either may be NULL).  The head runs in
+ * fp32 with a fixed summation order in either precision mode.
+ */
+int fx_classify(fx_handle h, int n, float *emb_dev, float *logits_dev, float *probs_dev, void *stream);
 
 /* fx_preprocess + fx_forward. */
 int fx_embed(fx_handle h, const uint8_t *src_dev, const fx_image_desc *descs_host, int n, float *emb_dev,

@@ -204,3 +204,21 @@ int fxo_preprocess_rgb(const uint8_t *src, int h, int w, float *out_chw) {
     free(crop);
     return rc;
 }
+
+/*
+ * Evaluation transform of the classifier-head paths (src/training/common.py:111-117):
+ * Resize((224, 224)) -- each axis resampled independently, no crop -- then ToTensor + Normalize.
+ * torchvision hands (w, h) = (224, 224) to Image.resize (tv:transforms/_functional_pil.py:242-253), whose
+ * passes are skipped per axis when the size already matches.  fp32 CHW [3][224][224].
+ */
+int fxo_preprocess_square224_rgb(const uint8_t *src, int h, int w, float *out_chw) {
+    static float lut[3 * 256];
+    static int lut_ready = 0;
+    if (!lut_ready) { fxo_build_lut(lut); lut_ready = 1; }
+    uint8_t *rs = (uint8_t *)malloc((size_t)224 * 224 * 3);
+    fxo_resize_bilinear_u8(src, h, w, 3, rs, 224, 224);
+    for (int ch = 0; ch < 3; ++ch)
+        for (int i = 0; i < 224 * 224; ++i) out_chw[(size_t)ch * 224 * 224 + i] = lut[ch * 256 + rs[(size_t)i * 3 + ch]];
+    free(rs);
+    return 0;
+}

@@ -168,6 +168,82 @@ def port_embed_arrays(
 
 
 # --------------------------------------------------------------------------------------------
+# Classifier-head inference: restatement of the three reference loops that run the
+# fine-tuned resnet18 in eval mode.  Same third-party calls; no training, no plots.
+# --------------------------------------------------------------------------------------------
+
+HEAD_SEED = 4321
+
+
+def port_eval_transform() -> Callable[[Image.Image], torch.Tensor]:
+    """build_transforms()["eval"] (src/training/common.py:111-117)."""
+    return transforms.Compose(
+        [transforms.Resize((CROP, CROP)), transforms.ToTensor(), transforms.Normalize(mean=MEAN, std=STD)]
+    )
+
+
+_HEAD_CACHE: dict = {}
+
+
+def make_classifier(num_classes: int = 2, seed: int = WEIGHT_SEED, randomize_bn: bool = True) -> nn.Module:
+    """create_model(num_classes, pretrained=False) (src/training/common.py:299-304) with the seeded backbone and a
+    seeded fc that is CALIBRATED on 16 seeded images so that each logit has mean 0 / std 2 over them: the post-ReLU
+    embeddings are all positive with large per-dimension means, so an uncalibrated random head
+    predicts one class with probability 1.0 for every input and would test nothing."""
+    net = make_backbone(seed, randomize_bn)
+    net.fc = nn.Linear(net.fc.in_features, num_classes)
+    net.eval()
+    key = (num_classes, seed, randomize_bn)
+    if key not in _HEAD_CACHE:
+        from ssip_b200 import synthetic  # seeded generators only
+
+        gen = torch.Generator().manual_seed(HEAD_SEED)
+        w = torch.randn(net.fc.weight.shape, generator=gen, dtype=torch.float64)
+        calib = list(synthetic.mri_like_images(8, 512, seed=HEAD_SEED)) + list(synthetic.noise_images(8, 300, 260, seed=HEAD_SEED + 1))
+        t = port_eval_transform()
+        x = torch.stack([t(Image.fromarray(a)) for a in calib])
+        trunk = nn.Sequential(*list(net.children())[:-1])
+        with torch.no_grad():
+            emb = torch.flatten(trunk(x), 1).double()
+        z = emb @ w.T
+        w = w * (2.0 / z.std(dim=0))[:, None]
+        bias = -(emb @ w.T).mean(dim=0)
+        _HEAD_CACHE[key] = (w.float(), bias.float())
+    w, bias = _HEAD_CACHE[key]
+    with torch.no_grad():
+        net.fc.weight.copy_(w)
+        net.fc.bias.copy_(bias)
+    return net
+
+
+def port_generate_pseudo_labels(model, data_loader, device, threshold: float = 0.7):
+    """generate_pseudo_labels (src/training/semi_supervised.py:44-72): (path, label, confidence) above threshold."""
+    model.eval()
+    out = []
+    with torch.no_grad():
+        for images, paths in data_loader:
+            probs = torch.softmax(model(images.to(device)), dim=1)
+            conf, pred = torch.max(probs, dim=1)
+            for path, p, c in zip(paths, pred.cpu().numpy(), conf.cpu().numpy()):
+                if c >= threshold:
+                    out.append((path, int(p), float(c)))
+    return out
+
+
+def port_compute_probs(model, loader, device, pos_index: int):
+    """compute_probs (src/threshold_sweep.py:21-38)."""
+    model.eval()
+    y_true, y_prob = [], []
+    with torch.no_grad():
+        for batch in loader:
+            inputs, labels = batch[:2]
+            probs = torch.softmax(model(inputs.to(device)), dim=1)[:, pos_index]
+            y_true.extend(labels.cpu().numpy().tolist())
+            y_prob.extend(probs.cpu().numpy().tolist())
+    return np.array(y_true), np.array(y_prob)
+
+
+# --------------------------------------------------------------------------------------------
 # ctypes view of the plain-C restatement (oracle/preprocess_oracle.c)
 # --------------------------------------------------------------------------------------------
 
@@ -196,6 +272,7 @@ def c_oracle() -> ctypes.CDLL:
         lib.fxo_build_lut.argtypes = [ctypes.c_void_p]
         lib.fxo_resize_crop_u8.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p]
         lib.fxo_preprocess_rgb.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        lib.fxo_preprocess_square224_rgb.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -208,6 +285,15 @@ def c_preprocess_rgb(arr: np.ndarray) -> np.ndarray:
     rc = c_oracle().fxo_preprocess_rgb(arr.ctypes.data, arr.shape[0], arr.shape[1], out.ctypes.data)
     if rc != 0:
         raise ValueError("resized image smaller than the crop")
+    return out
+
+
+def c_preprocess_square224(arr: np.ndarray) -> np.ndarray:
+    """C restatement of the evaluation transform (Resize((224,224)) + ToTensor + Normalize): fp32 [3,224,224]."""
+    arr = np.ascontiguousarray(arr, dtype=np.uint8)
+    assert arr.ndim == 3 and arr.shape[2] == 3
+    out = np.empty((3, CROP, CROP), np.float32)
+    c_oracle().fxo_preprocess_square224_rgb(arr.ctypes.data, arr.shape[0], arr.shape[1], out.ctypes.data)
     return out
 
 

@@ -309,7 +309,8 @@ void fx_destroy(fx_handle e) {
     }
     for (auto& st : e->lane_stream)
         if (st) cudaStreamDestroy(st);
-    cudaFree(e->emb_dev);
+    cudaFree(e->head_w);
+    cudaFree(e->head_b);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -350,10 +351,6 @@ int fx_create(fx_handle* out, int device, int max_batch, int precision) {
     };
     int rc = lane_alloc(e);  // lane 0
     if (rc != FX_OK) return fail(rc);
-    {
-        cudaError_t a = cudaMalloc(reinterpret_cast<void**>(&e->emb_dev), (size_t)max_batch * kEmbed * sizeof(float));
-        if (a != cudaSuccess) return fail(set_error(e, FX_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(a)));
-    }
     if ((err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
     if ((rc = preprocess_init(e)) != FX_OK) return fail(rc);
@@ -420,6 +417,40 @@ int fx_forward(fx_handle e, int n, float* emb_dev, void* stream) {
     if (!emb_dev) return set_error(e, FX_ERR_INVALID, "fx_forward: null output");
     FX_CUDA(e, cudaSetDevice(e->device));
     return forward(e, n, emb_dev, static_cast<cudaStream_t>(stream));
+}
+
+int fx_set_transform(fx_handle e, int transform) {
+    if (!e) return FX_ERR_INVALID;
+    if (transform != FX_TRANSFORM_EXTRACT && transform != FX_TRANSFORM_SQUARE224)
+        return set_error(e, FX_ERR_INVALID, "fx_set_transform: unknown transform");
+    e->transform = transform;
+    return FX_OK;
+}
+
+int fx_load_head(fx_handle e, const float* weight, const float* bias, int num_classes) {
+    if (!e) return FX_ERR_INVALID;
+    if (!weight || !bias || num_classes < 1 || num_classes > FX_MAX_CLASSES)
+        return set_error(e, FX_ERR_INVALID, "fx_load_head: null pointer or num_classes outside 1.." + std::to_string(FX_MAX_CLASSES));
+    FX_CUDA(e, cudaSetDevice(e->device));
+    FX_CUDA(e, cudaDeviceSynchronize());  // a previous head may still be in use
+    cudaFree(e->head_w);
+    cudaFree(e->head_b);
+    e->head_w = e->head_b = nullptr;
+    e->head_classes = 0;
+    FX_CUDA(e, cudaMalloc(&e->head_w, sizeof(float) * kEmbed * num_classes));
+    FX_CUDA(e, cudaMalloc(&e->head_b, sizeof(float) * num_classes));
+    FX_CUDA(e, cudaMemcpy(e->head_w, weight, sizeof(float) * kEmbed * num_classes, cudaMemcpyHostToDevice));
+    FX_CUDA(e, cudaMemcpy(e->head_b, bias, sizeof(float) * num_classes, cudaMemcpyHostToDevice));
+    e->head_classes = num_classes;
+    return FX_OK;
+}
+
+int fx_classify(fx_handle e, int n, float* emb_dev, float* logits_dev, float* probs_dev, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (!e->head_classes) return set_error(e, FX_ERR_STATE, "fx_classify: fx_load_head has not succeeded");
+    int rc = fx_forward(e, n, emb_dev, stream);
+    if (rc != FX_OK || n == 0) return rc;
+    return head_run(e, emb_dev, n, logits_dev, probs_dev, static_cast<cudaStream_t>(stream));
 }
 
 int fx_select_lane(fx_handle e, int lane) {

@@ -104,7 +104,8 @@ struct fx_engine {
     // preprocess
     float* lut_f32 = nullptr;            // [3][256]
     __nv_bfloat16* lut_bf16 = nullptr;   // [3][256]
-    std::map<std::pair<int, int>, fx::GeomEntry> geoms;
+    std::map<std::pair<int, int>, fx::GeomEntry> geoms;  // key: (height + (transform << 24), width)
+    int transform = FX_TRANSFORM_EXTRACT;
     fx::ImgDev* img_dev = nullptr;       // [max_batch]
     fx::ImgDev* img_host = nullptr;      // pinned, [max_batch]
     cudaEvent_t img_host_free = nullptr; // img_host may be rewritten once this has fired
@@ -140,6 +141,12 @@ struct fx_engine {
         bool allocated = false;
     } lanes[FX_MAX_LANES];
     int cur_lane = 0;
+    // preprocess launch plan of each lane's last batch; reused when the next batch has the same descriptor table
+    struct PrePlan {
+        bool valid = false, s2d = false;
+        int mode = 0, transform = 0, n = 0, kernel = 0, bands = 0, smem = 0, tmp_bytes = 0, rowbuf = 0;
+        std::vector<fx_image_desc> descs;
+    } pre_plan[FX_MAX_LANES];
 
     // host-buffer path (fx_embed_host*): FX_HOST_SLOTS pipelined slots (device copies of one batch's packed images and
     // embeddings); slot s computes on lane s % FX_MAX_LANES, whose stream serialises the slots that share its buffers.
@@ -151,7 +158,10 @@ struct fx_engine {
         cudaEvent_t copied = nullptr, done = nullptr;
         bool busy = false;
     } slots[FX_HOST_SLOTS];
-    float* emb_dev = nullptr;
+    // classifier head (fx_load_head)
+    float* head_w = nullptr;  // [head_classes][512]
+    float* head_b = nullptr;
+    int head_classes = 0;
     cudaStream_t lane_stream[FX_MAX_LANES] = {};  // kernels + D2H of the host-buffer path, one per lane
     cudaStream_t copy_stream = nullptr;           // H2D of the host-buffer path
 };
@@ -220,6 +230,7 @@ int simt_conv(fx_engine* e, const PackedLayer& L, const float* in, int hin_phys,
               int pad, const float* residual, float* out, int n, int relu, cudaStream_t stream);
 int maxpool_3x3s2(fx_engine* e, const void* in, void* out, int n, int h, int w, int c, bool bf16,
                   cudaStream_t stream);
+int head_run(fx_engine* e, const float* emb, int n, float* logits, float* probs, cudaStream_t stream);
 int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n, int hw, int c,
                 cudaStream_t stream);
 int f32_to_bf16(fx_engine* e, const float* in, __nv_bfloat16* out, size_t count, cudaStream_t stream);

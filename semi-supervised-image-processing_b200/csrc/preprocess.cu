@@ -126,11 +126,17 @@ static void axis_for_crop(int in_size, int out_size, int crop_off, std::vector<i
     }
 }
 
-static bool build_geom(int h, int w, GeomTableHost& g) {
-    int oh, ow;
-    resized_size(h, w, oh, ow);
-    if (oh < kCrop || ow < kCrop) return false;
-    const int top = crop_offset(oh), left = crop_offset(ow);
+static bool build_geom(int h, int w, int transform, GeomTableHost& g) {
+    int oh, ow, top, left;
+    if (transform == FX_TRANSFORM_SQUARE224) {  // Resize((224, 224)): both axes to 224 independently, no crop
+        oh = ow = kCrop;
+        top = left = 0;
+    } else {
+        resized_size(h, w, oh, ow);
+        if (oh < kCrop || ow < kCrop) return false;
+        top = crop_offset(oh);
+        left = crop_offset(ow);
+    }
     std::vector<int32_t> hmn, hct, hk, vmn, vct, vk;
     axis_for_crop(w, ow, left, hmn, hct, hk, g.ksh);
     axis_for_crop(h, oh, top, vmn, vct, vk, g.ksv);
@@ -853,11 +859,11 @@ void preprocess_free(fx_engine* e) {
 }
 
 static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
-    auto key = std::make_pair(h, w);
+    auto key = std::make_pair(h + (e->transform << 24), w);
     auto it = e->geoms.find(key);
     if (it == e->geoms.end()) {
         GeomTableHost g;
-        if (h < 1 || w < 1 || !build_geom(h, w, g))
+        if (h < 1 || w < 1 || h >= (1 << 24) || !build_geom(h, w, e->transform, g))
             return set_error(e, FX_ERR_UNSUPPORTED,
                              "image " + std::to_string(h) + "x" + std::to_string(w) +
                                  ": unsupported geometry (empty, or down-scaling factor beyond the band buffer)");
@@ -880,9 +886,37 @@ static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
     return FX_OK;
 }
 
+static int preprocess_launch(fx_engine* e, const fx_engine::PrePlan& plan, const uint8_t* src_dev, int n, PreOut mode, void* out,
+                             cudaStream_t stream) {
+    if (plan.s2d) {
+        NormFma nf;
+        std::memcpy(nf.a, e->norm_a, sizeof(nf.a));
+        std::memcpy(nf.b, e->norm_b, sizeof(nf.b));
+        FX_CUDA(e, launch_pdl(s2d_kernels()[plan.kernel], dim3(plan.bands, n), dim3(kS2dThreads), plan.smem, stream, src_dev,
+                              static_cast<const ImgDev*>(e->img_dev), static_cast<__nv_bfloat16*>(out), nf));
+        FX_LAUNCH_CHECK(e, "preprocess_s2d_kernel");
+        return FX_OK;
+    }
+    FX_CUDA(e, launch_pdl(pre_kernels()[plan.kernel], dim3(plan.bands, n), dim3(kPreThreads), plan.smem, stream, src_dev,
+                          static_cast<const ImgDev*>(e->img_dev), out, static_cast<const float*>(e->lut_f32),
+                          static_cast<const __nv_bfloat16*>(e->lut_bf16), plan.tmp_bytes, plan.rowbuf));
+    FX_LAUNCH_CHECK(e, "preprocess_kernel");
+    return FX_OK;
+}
+
 int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode, void* out,
                    cudaStream_t stream) {
     if (n == 0) return FX_OK;
+    // Steady state (same descriptor table as this lane's previous batch, e.g. every batch of a uniform dataset): the
+    // per-image records are already on the device and the launch plan is known -- no host loop, no upload, no wait.
+    fx_engine::PrePlan& plan = e->pre_plan[e->cur_lane];
+    const bool hit = plan.valid && plan.mode == (int)mode && plan.transform == e->transform && plan.n == n &&
+                     std::memcmp(plan.descs.data(), descs, sizeof(fx_image_desc) * n) == 0;
+    if (hit) {
+        FX_CUDA(e, cudaStreamWaitEvent(stream, e->img_host_free, 0));  // the upload may have been queued on another stream
+        return preprocess_launch(e, plan, src_dev, n, mode, out, stream);
+    }
+    plan.valid = false;
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
     int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
     bool all_s2d = mode == PreOut::IN0_BF16 && !e->pre_force_banded && e->norm_fma_ok;  // every image can take the column-walk kernel
@@ -935,28 +969,27 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     }
     FX_CUDA(e, cudaMemcpyAsync(e->img_dev, e->img_host, sizeof(ImgDev) * n, cudaMemcpyHostToDevice, stream));
     FX_CUDA(e, cudaEventRecord(e->img_host_free, stream));
+    plan.s2d = all_s2d;
     if (all_s2d) {
-        NormFma nf;
-        std::memcpy(nf.a, e->norm_a, sizeof(nf.a));
-        std::memcpy(nf.b, e->norm_b, sizeof(nf.b));
         const int ih = s2d_nth <= 2 ? 0 : (s2d_nth <= 4 ? 1 : 2), iv = s2d_ntv <= 2 ? 0 : (s2d_ntv <= 4 ? 1 : 2);
-        FX_CUDA(e, launch_pdl(s2d_kernels()[ih * 3 + iv], dim3(kS2dBands, n), dim3(kS2dThreads), s2d_smem, stream, src_dev,
-                              static_cast<const ImgDev*>(e->img_dev), static_cast<__nv_bfloat16*>(out), nf));
-        FX_LAUNCH_CHECK(e, "preprocess_s2d_kernel");
-        return FX_OK;
+        plan.kernel = ih * 3 + iv;
+        plan.smem = s2d_smem;
+        plan.bands = kS2dBands;
+    } else {
+        plan.tmp_bytes = (max_tmp + 15) & ~15;
+        plan.rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
+        plan.smem = 3072 + std::max(max_tmp ? plan.tmp_bytes + kPreWarps * plan.rowbuf : 0, fast_smem);
+        plan.bands = (kCrop + min_band - 1) / min_band;
+        if (mode == PreOut::IN0_BF16 && fast_smem) plan.bands = std::max(plan.bands, 15);  // row-pair aligned bands of the fast path
+        const int ih = nth <= 2 ? 0 : (nth <= 4 ? 1 : 2), iv = ntv <= 2 ? 0 : (ntv <= 4 ? 1 : 2);
+        plan.kernel = ((int)mode * 3 + ih) * 3 + iv;
     }
-    const int tmp_bytes = (max_tmp + 15) & ~15;
-    const int rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
-    const int smem = 3072 + std::max(max_tmp ? tmp_bytes + kPreWarps * rowbuf : 0, fast_smem);
-    int bands = (kCrop + min_band - 1) / min_band;
-    if (mode == PreOut::IN0_BF16 && fast_smem) bands = std::max(bands, 15);  // row-pair aligned bands of the fast path
-    dim3 grid(bands, n);
-    const int ih = nth <= 2 ? 0 : (nth <= 4 ? 1 : 2), iv = ntv <= 2 ? 0 : (ntv <= 4 ? 1 : 2);
-    FX_CUDA(e, launch_pdl(pre_kernels()[((int)mode * 3 + ih) * 3 + iv], grid, dim3(kPreThreads), smem, stream, src_dev,
-                          static_cast<const ImgDev*>(e->img_dev), out, static_cast<const float*>(e->lut_f32),
-                          static_cast<const __nv_bfloat16*>(e->lut_bf16), tmp_bytes, rowbuf));
-    FX_LAUNCH_CHECK(e, "preprocess_kernel");
-    return FX_OK;
+    plan.mode = (int)mode;
+    plan.transform = e->transform;
+    plan.n = n;
+    plan.descs.assign(descs, descs + n);
+    plan.valid = true;
+    return preprocess_launch(e, plan, src_dev, n, mode, out, stream);
 }
 
 int stage_nchw_run(fx_engine* e, const float* in_dev, int n, cudaStream_t stream) {

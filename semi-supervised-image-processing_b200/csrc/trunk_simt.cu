@@ -247,6 +247,48 @@ int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n
 }
 
 // ------------------------------------------------------------------------------------------
+// classifier head: logits = emb @ W^T + b, probs = softmax(logits) -- fc of create_model (src/training/common.py:
+// 299-304) + torch.softmax(outputs, dim=1) (src/training/semi_supervised.py:61, common.py:463, threshold_sweep.py:34).
+// One warp per image; a lane sums its 16 products in k order, the lanes combine by a fixed xor tree: the result
+// depends on the image alone.  exp through expf (not the fast intrinsic).
+// ------------------------------------------------------------------------------------------
+__global__ void head_kernel(const float* __restrict__ emb, const float* __restrict__ w, const float* __restrict__ b, int n, int classes,
+                            float* __restrict__ logits, float* __restrict__ probs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (img >= n) return;
+    float x[kEmbed / 32];
+#pragma unroll
+    for (int j = 0; j < kEmbed / 32; ++j) x[j] = emb[(size_t)img * kEmbed + j * 32 + lane];
+    float mine = 0.f, mx = -INFINITY;  // lane c keeps logit c (classes <= FX_MAX_CLASSES = 32)
+    for (int c = 0; c < classes; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < kEmbed / 32; ++j) acc = fmaf(x[j], __ldg(w + (size_t)c * kEmbed + j * 32 + lane), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc += __ldg(b + c);
+        if (lane == c) mine = acc;
+        mx = fmaxf(mx, acc);
+    }
+    if (logits && lane < classes) logits[(size_t)img * classes + lane] = mine;
+    if (!probs) return;
+    const float ev = lane < classes ? expf(mine - mx) : 0.f;
+    float sum = ev;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane < classes) probs[(size_t)img * classes + lane] = ev / sum;
+}
+
+int head_run(fx_engine* e, const float* emb, int n, float* logits, float* probs, cudaStream_t stream) {
+    FX_CUDA(e, launch_pdl(head_kernel, dim3((n + 3) / 4), dim3(128), 0, stream, emb, static_cast<const float*>(e->head_w),
+                          static_cast<const float*>(e->head_b), n, e->head_classes, logits, probs));
+    FX_LAUNCH_CHECK(e, "head_kernel");
+    return FX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // layout / precision helpers (debug entry points only)
 // ------------------------------------------------------------------------------------------
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t count) {

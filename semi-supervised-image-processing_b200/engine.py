@@ -174,6 +174,43 @@ class Engine:
         self._check(self._lib.fx_forward(self._h, n, out.data_ptr(), self._stream()))
         return out
 
+    # -- classifier head --------------------------------------------------
+    def set_transform(self, transform: int) -> None:
+        """N.TRANSFORM_EXTRACT (Resize(256)+CenterCrop(224)) or N.TRANSFORM_SQUARE224 (Resize((224,224)), the
+        evaluation transform of src/training/common.py:111-117) for the following preprocess calls."""
+        self._check(self._lib.fx_set_transform(self._h, int(transform)))
+
+    def load_head(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
+        """fc of the fine-tuned model: weight [classes,512], bias [classes] (src/training/common.py:299-304)."""
+        w = np.ascontiguousarray(weight.detach().to("cpu", torch.float32).numpy())
+        b = np.ascontiguousarray(bias.detach().to("cpu", torch.float32).numpy())
+        if w.ndim != 2 or w.shape[1] != N.EMBED_DIM or b.shape != (w.shape[0],):
+            raise ValueError(f"head must be [classes,{N.EMBED_DIM}] + [classes], got {w.shape} + {b.shape}")
+        self._check(self._lib.fx_load_head(self._h, w.ctypes.data, b.ctypes.data, int(w.shape[0])))
+        self.num_classes = int(w.shape[0])
+
+    def classify(self, n: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Trunk + head + softmax on the n staged images -> (embeddings [n,512], logits [n,C], probs [n,C]) on the device."""
+        c = getattr(self, "num_classes", 0)
+        emb = torch.empty((n, N.EMBED_DIM), dtype=torch.float32, device=self.device)
+        logits = torch.empty((n, c), dtype=torch.float32, device=self.device)
+        probs = torch.empty((n, c), dtype=torch.float32, device=self.device)
+        self._check(self._lib.fx_classify(self._h, n, emb.data_ptr(), logits.data_ptr(), probs.data_ptr(), self._stream()))
+        return emb, logits, probs
+
+    def classify_nchw(self, x_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """`model(inputs)` + softmax for an already transformed fp32 [n,3,224,224] CUDA batch (what the reference's
+        DataLoader yields)."""
+        if x_dev.dtype != torch.float32 or not x_dev.is_cuda or not x_dev.is_contiguous() or tuple(x_dev.shape[1:]) != (3, N.CROP, N.CROP):
+            raise TypeError("expected a contiguous fp32 CUDA tensor [n,3,224,224]")
+        self._check(self._lib.fx_stage_nchw_f32(self._h, x_dev.data_ptr(), x_dev.shape[0], self._stream()))
+        return self.classify(x_dev.shape[0])
+
+    def classify_device(self, packed_dev: torch.Tensor, descs, n: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Fused path: packed uint8 images on the device -> preprocess (current transform) -> trunk -> head."""
+        self.preprocess(packed_dev, descs, n)
+        return self.classify(n)
+
     # -- whole path ---------------------------------------------------------------------------
     def embed_device(self, packed_dev: torch.Tensor, descs, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Preprocess + trunk on device-resident uint8 images -> fp32 [n,512] on the device."""

@@ -147,3 +147,14 @@ def test_bf16_staging_equals_the_fp32_transform_rounded(eng_b, eng):
     eng_b.preprocess(dev, descs, len(x))
     _, padded = eng_b.staged_crop(len(x))
     assert torch.equal(padded[:, :, 3:227, 3:227], f32.to(torch.bfloat16))
+
+
+def test_repeated_descriptor_table_reuses_the_plan_with_new_pixels(eng_b):
+    """Same geometry, different images, alternating lanes/streams: the cached descriptor upload must not cache pixels."""
+    s1 = torch.cuda.Stream()
+    for rep in range(4):
+        imgs = synthetic.ragged_images([(224, 224), (512, 512), (300, 500)], seed=100 + rep)
+        eng_b.select_lane(rep & 1)
+        with torch.cuda.stream(s1 if rep & 1 else torch.cuda.current_stream()):
+            _check_staging(eng_b, imgs)
+    eng_b.select_lane(0)

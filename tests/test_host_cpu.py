@@ -267,3 +267,33 @@ def test_allgather_rows_world_size_2_gloo(tmp_path):
     )
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2 and "0" in out.stdout and "1" in out.stdout
+
+
+def test_inference_drop_ins_keep_the_reference_signatures(have_reference):
+    """Classifier-head inference loops: same names, parameters and defaults as the reference."""
+    import inspect
+    import types
+
+    from ssip_b200 import inference
+
+    for name in ("generate_pseudo_labels", "evaluate_model", "compute_probs", "build_transforms"):
+        assert callable(getattr(inference, name))
+    with pytest.raises(RuntimeError):  # no CPU path
+        inference.get_classifier(torch.nn.Linear(1, 1), torch.device("cpu"))
+    if not have_reference:
+        return
+    for name in ("matplotlib", "matplotlib.pyplot"):  # not installed here; only the plotting helpers use it
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, "/root/reference")
+    sys.path.insert(0, "/root/reference/src")
+    import src.training.common as ref_common
+    import src.training.semi_supervised as ref_semi
+    import threshold_sweep as ref_sweep
+
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()]
+
+    assert params(inference.generate_pseudo_labels) == params(ref_semi.generate_pseudo_labels)
+    assert params(inference.evaluate_model) == params(ref_common.evaluate_model)
+    assert params(inference.compute_probs) == params(ref_sweep.compute_probs)
+    assert params(inference.build_transforms) == params(ref_common.build_transforms)

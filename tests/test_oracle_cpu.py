@@ -128,3 +128,41 @@ def test_port_matches_real_reference_module(have_reference, tmp_path):
     port = rp.port_extract_embeddings(port_records, torch.device("cpu"), batch_size=2, randomize_bn=True)
     np.testing.assert_array_equal(ref.embeddings, port.embeddings)
     assert [r.relative_path for r in ref.records] == [r.relative_path for r in port.records]
+
+
+# ---- classifier-head inference -------------------------------------------
+
+
+def _head_inputs():
+    imgs = list(synthetic.mri_like_images(6, 512, seed=21))
+    imgs += synthetic.ragged_images([(300, 500), (224, 224), (640, 480), (100, 130)], seed=22)
+    return imgs, [0, 1, 1, 0, 1, 0, 0, 1, 1, 0], [f"img_{i:02d}.png" for i in range(10)]
+
+
+def test_eval_transform_restatement_matches_reference_golden(golden_dir):
+    import hashlib
+
+    g = np.load(golden_dir / "head_golden.npz")
+    imgs, _, _ = _head_inputs()
+    for i, a in enumerate(imgs):
+        out = rp.c_preprocess_square224(a)
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == str(g["transform_sha256"][i])
+
+
+def test_head_port_matches_reference_golden(golden_dir):
+    """The oracle's restatement of generate_pseudo_labels / compute_probs (and the seeded classifier) reproduce what
+    the real reference functions returned in the build container (tests/golden/make_golden_head.py)."""
+    g = np.load(golden_dir / "head_golden.npz")
+    imgs, labels, paths = _head_inputs()
+    torch.set_num_threads(8)
+    model = rp.make_classifier(2)
+    x = torch.stack([torch.from_numpy(rp.c_preprocess_square224(a)) for a in imgs])
+    with torch.no_grad():
+        logits = model(x)
+    assert np.allclose(logits.numpy(), g["logits"], rtol=0, atol=2e-4)
+    loader = [(x[i : i + 4], torch.tensor(labels[i : i + 4]), paths[i : i + 4]) for i in range(0, 10, 4)]
+    ct, cp = rp.port_compute_probs(model, [(a, b) for a, b, _ in loader], torch.device("cpu"), pos_index=1)
+    assert np.array_equal(ct, g["sweep_y_true"]) and np.allclose(cp, g["sweep_y_prob"], atol=1e-5)
+    got = rp.port_generate_pseudo_labels(model, [(a, p) for a, _, p in loader], torch.device("cpu"), float(g["pseudo_threshold"]))
+    assert [p for p, _, _ in got] == g["pseudo_paths"].tolist()
+    assert [l for _, l, _ in got] == g["pseudo_labels"].tolist()
