@@ -203,6 +203,35 @@ int fx_embed_host_async(fx_handle h, int slot, const uint8_t *src_host, size_t t
                         const fx_image_desc *descs_host, int n, float *emb_host);
 int fx_embed_host_wait(fx_handle h, int slot);
 
+/*
+ * ---- on-device post-processing of an [n][d] fp32 embedding matrix ----
+ * At N = 1M the reference's numpy / scikit-learn post-processing scans 2 GB on the host several times; these are the
+ * same reductions as single HBM-bound passes over the (gathered) device buffer.  d <= 4096.  Column statistics
+ * accumulate in fp64 with a fixed reduction shape (results do not depend on timing).
+ */
+typedef struct fx_matrix_stats {
+    int64_t nan_count, inf_count; /* run_sanity_checks raises when either is non-zero (src/feature_extraction.py:337-340) */
+    double mean_abs_mean;         /* np.abs(emb.mean(axis=0)).mean()   (:345) */
+    double mean_std;              /* emb.std(axis=0).mean(), ddof = 0  (:346) */
+} fx_matrix_stats;
+
+/* run_sanity_checks (src/feature_extraction.py:334-356) + the fit of StandardScaler (src/standardize_features.py:41-43):
+ * column mean / population std / variance as fp64 device arrays [d] (each may be NULL) and the scalars in *stats
+ * (host, may be NULL; when given the call synchronises `stream`). */
+int fx_column_stats(fx_handle h, const float *emb_dev, int64_t n, int d, double *col_mean_dev, double *col_std_dev,
+                    double *col_var_dev, fx_matrix_stats *stats, void *stream);
+
+/* StandardScaler.transform as numpy executes it in place on a float32 matrix: t = fp32(x - mean) in fp64 arithmetic,
+ * z = fp32(t / scale).  scale_dev is the caller's (std with near-constant columns replaced by 1, sklearn semantics). */
+int fx_standardize(fx_handle h, const float *emb_dev, int64_t n, int d, const double *col_mean_dev, const double *col_scale_dev,
+                   float *out_dev, void *stream);
+
+/* nearest_neighbor_probe (src/feature_extraction.py:359-398): for each of the q (<= 32) query rows, the row with the
+ * largest cosine similarity, the query itself excluded, first maximum on ties; fp32 arithmetic.  Host index / output
+ * arrays; synchronises `stream`. */
+int fx_neighbor_probe(fx_handle h, const float *emb_dev, int64_t n, int d, const int64_t *query_rows_host, int q,
+                      int64_t *neighbor_rows_host, float *similarity_host, void *stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 uint64_t fx_launch_count(fx_handle h);
 

@@ -311,6 +311,7 @@ void fx_destroy(fx_handle e) {
         if (st) cudaStreamDestroy(st);
     cudaFree(e->head_w);
     cudaFree(e->head_b);
+    cudaFree(e->post_scratch);
     for (auto& ev : e->prof_ev)
         if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -435,6 +436,7 @@ int fx_load_head(fx_handle e, const float* weight, const float* bias, int num_cl
     FX_CUDA(e, cudaDeviceSynchronize());  // a previous head may still be in use
     cudaFree(e->head_w);
     cudaFree(e->head_b);
+    cudaFree(e->post_scratch);
     e->head_w = e->head_b = nullptr;
     e->head_classes = 0;
     FX_CUDA(e, cudaMalloc(&e->head_w, sizeof(float) * kEmbed * num_classes));
@@ -531,6 +533,34 @@ int fx_embed_host(fx_handle e, const uint8_t* src_host, size_t total_bytes, cons
     int rc = fx_embed_host_async(e, 0, src_host, total_bytes, descs, n, emb_host);
     if (rc != FX_OK) return rc;
     return fx_embed_host_wait(e, 0);
+}
+
+int fx_column_stats(fx_handle e, const float* emb_dev, int64_t n, int d, double* col_mean_dev, double* col_std_dev, double* col_var_dev,
+                    fx_matrix_stats* stats, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (!emb_dev || n < 1 || d < 1 || d > 4096) return set_error(e, FX_ERR_INVALID, "fx_column_stats: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    return post_column_stats(e, emb_dev, n, d, col_mean_dev, col_std_dev, col_var_dev, stats, static_cast<cudaStream_t>(stream));
+}
+
+int fx_standardize(fx_handle e, const float* emb_dev, int64_t n, int d, const double* col_mean_dev, const double* col_scale_dev,
+                   float* out_dev, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (!emb_dev || !col_mean_dev || !col_scale_dev || !out_dev || n < 1 || d < 1 || d > 4096)
+        return set_error(e, FX_ERR_INVALID, "fx_standardize: bad arguments");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    return post_standardize(e, emb_dev, n, d, col_mean_dev, col_scale_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int fx_neighbor_probe(fx_handle e, const float* emb_dev, int64_t n, int d, const int64_t* query_rows_host, int q,
+                      int64_t* neighbor_rows_host, float* similarity_host, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    if (!emb_dev || !query_rows_host || !neighbor_rows_host || !similarity_host || n < 2 || d < 1 || d > 4096 || q < 1 || q > 32)
+        return set_error(e, FX_ERR_INVALID, "fx_neighbor_probe: bad arguments (n >= 2, 1 <= q <= 32, d <= 4096)");
+    for (int j = 0; j < q; ++j)
+        if (query_rows_host[j] < 0 || query_rows_host[j] >= n) return set_error(e, FX_ERR_INVALID, "fx_neighbor_probe: query row out of range");
+    FX_CUDA(e, cudaSetDevice(e->device));
+    return post_neighbor_probe(e, emb_dev, n, d, query_rows_host, q, neighbor_rows_host, similarity_host, static_cast<cudaStream_t>(stream));
 }
 
 uint64_t fx_launch_count(fx_handle e) { return e ? e->launches : 0; }

@@ -158,6 +158,9 @@ struct fx_engine {
         cudaEvent_t copied = nullptr, done = nullptr;
         bool busy = false;
     } slots[FX_HOST_SLOTS];
+    // on-device post-processing scratch (postprocess.cu)
+    void* post_scratch = nullptr;
+    size_t post_cap = 0;
     // classifier head (fx_load_head)
     float* head_w = nullptr;  // [head_classes][512]
     float* head_b = nullptr;
@@ -236,6 +239,14 @@ int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n
 int f32_to_bf16(fx_engine* e, const float* in, __nv_bfloat16* out, size_t count, cudaStream_t stream);
 int bf16_to_f32(fx_engine* e, const __nv_bfloat16* in, float* out, size_t count, cudaStream_t stream);
 int pad_nhwc3_to_in0(fx_engine* e, const float* in_nhwc3, void* in0, bool bf16, int n, cudaStream_t stream);
+
+// postprocess.cu (sanity statistics, StandardScaler, nearest-neighbour probe on the device)
+int post_column_stats(fx_engine* e, const float* x, long long n, int d, double* mean_dev, double* std_dev, double* var_dev,
+                      fx_matrix_stats* out, cudaStream_t stream);
+int post_standardize(fx_engine* e, const float* x, long long n, int d, const double* mean_dev, const double* scale_dev, float* out,
+                     cudaStream_t stream);
+int post_neighbor_probe(fx_engine* e, const float* x, long long n, int d, const int64_t* qidx_host, int q, int64_t* nbr_host,
+                        float* sim_host, cudaStream_t stream);
 
 // conv_tc.cu (bf16 tcgen05 implicit-GEMM path)
 int tc_init(fx_engine* e);

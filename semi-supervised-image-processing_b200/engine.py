@@ -211,6 +211,43 @@ class Engine:
         self.preprocess(packed_dev, descs, n)
         return self.classify(n)
 
+    # -- on-device post-processing of an [n,d] fp32 matrix ------------------
+    @staticmethod
+    def _matrix(x: torch.Tensor) -> Tuple[int, int]:
+        if x.dtype != torch.float32 or not x.is_cuda or not x.is_contiguous() or x.dim() != 2:
+            raise TypeError("expected a contiguous fp32 CUDA matrix [n,d]")
+        return int(x.shape[0]), int(x.shape[1])
+
+    def column_stats(self, x: torch.Tensor):
+        """run_sanity_checks' scalars + StandardScaler's fit in one call: (stats dict, mean, std, var) with the column
+        arrays as fp64 CUDA tensors [d] (fx_column_stats; fp64 accumulation, fixed reduction order)."""
+        n, d = self._matrix(x)
+        mean, std, var = (torch.empty(d, dtype=torch.float64, device=self.device) for _ in range(3))
+        st = N.MatrixStats()
+        self._check(self._lib.fx_column_stats(self._h, x.data_ptr(), n, d, mean.data_ptr(), std.data_ptr(), var.data_ptr(),
+                                              ctypes.byref(st), self._stream()))
+        return ({"nan_count": int(st.nan_count), "inf_count": int(st.inf_count), "mean_abs_mean": float(st.mean_abs_mean),
+                 "mean_std": float(st.mean_std)}, mean, std, var)
+
+    def standardize(self, x: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+        """z = fp32(fp32(x - mean) / scale) with fp64 arithmetic, as StandardScaler.transform on a float32 matrix."""
+        n, d = self._matrix(x)
+        if mean.dtype != torch.float64 or scale.dtype != torch.float64 or mean.numel() != d or scale.numel() != d:
+            raise TypeError("mean / scale must be fp64 CUDA tensors [d]")
+        out = torch.empty_like(x)
+        self._check(self._lib.fx_standardize(self._h, x.data_ptr(), n, d, mean.data_ptr(), scale.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def neighbor_probe(self, x: torch.Tensor, query_rows: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+        """Cosine nearest neighbour (self excluded, first maximum) of each query row: (rows int64 [q], similarities fp32 [q])."""
+        n, d = self._matrix(x)
+        q = np.ascontiguousarray(np.asarray(query_rows, dtype=np.int64))
+        nbr = np.empty(q.size, np.int64)
+        sim = np.empty(q.size, np.float32)
+        self._check(self._lib.fx_neighbor_probe(self._h, x.data_ptr(), n, d, q.ctypes.data, int(q.size), nbr.ctypes.data, sim.ctypes.data,
+                                                self._stream()))
+        return nbr, sim
+
     # -- whole path ---------------------------------------------------------------------------
     def embed_device(self, packed_dev: torch.Tensor, descs, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Preprocess + trunk on device-resident uint8 images -> fp32 [n,512] on the device."""

@@ -92,6 +92,9 @@ class ExtractionResults:
     records: List[ImageRecord]
     failures: List[Path]
     per_file_times: List[float]
+    # extra (defaulted, so the reference's four-field construction still works): the same matrix still on the GPU
+    # when it was assembled there (multi-GPU all-gather), for the on-device post-processing below
+    device_embeddings: Optional[torch.Tensor] = None
 
 
 # --- logging / discovery -------------------------------------------------------------------------
@@ -190,10 +193,19 @@ def resolve_state_dict(spec: Optional[str] = None) -> Dict[str, torch.Tensor]:
     return models.resnet18(weights=models.ResNet18_Weights.IMAGENET1K_V1).state_dict()
 
 
+_NO_WEIGHTS: Dict[str, torch.Tensor] = {}  # sentinel for get_engine: the caller needs no trunk (post-processing kernels only)
+
+
 def get_engine(device: torch.device, min_batch: int = BATCH_SIZE, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                precision: Optional[str] = None) -> Engine:
     """Engine for `device`, created (and its weights loaded) on first use."""
     index = _cuda_index(device)
+    if state_dict is _NO_WEIGHTS:  # post-processing only: any engine of this GPU will do, a bare one otherwise
+        for key, eng in _ENGINES.items():
+            if key[0] == index:
+                return eng
+        eng = _ENGINES[(index, "bare", "")] = Engine(index, max(min_batch, 1), "bf16")
+        return eng
     precision = precision or os.environ.get(PRECISION_ENV, "bf16")
     key = (index, precision, os.environ.get(WEIGHTS_ENV, "") if state_dict is None else f"id{id(state_dict)}")
     eng = _ENGINES.get(key)
@@ -399,7 +411,8 @@ def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_s
         raise RuntimeError("No embeddings were generated; all images failed to decode?")
     matrix = full.cpu().numpy()
     logging.info("Computed embeddings with shape %s", matrix.shape)
-    return ExtractionResults(embeddings=matrix, records=[records[i] for i in kept], failures=failures, per_file_times=times)
+    return ExtractionResults(embeddings=matrix, records=[records[i] for i in kept], failures=failures, per_file_times=times,
+                             device_embeddings=full if full.is_cuda else None)
 
 
 # --- post-processing and artifacts ---------------------------------------------------------------
@@ -415,39 +428,62 @@ def compute_dataset_digest(records: Sequence[ImageRecord]) -> str:
     return h.hexdigest()
 
 
-def run_sanity_checks(embeddings: np.ndarray) -> Dict[str, float]:
-    """NaN/Inf guard + summary statistics (src/feature_extraction.py:334-356)."""
-    if np.isnan(embeddings).any():
-        raise ValueError("Embedding matrix contains NaN values")
-    if np.isinf(embeddings).any():
-        raise ValueError("Embedding matrix contains inf values")
-    stats = {
-        "num_vectors": int(embeddings.shape[0]),
-        "dimension": int(embeddings.shape[1]),
-        "mean_abs_mean": float(np.abs(embeddings.mean(axis=0)).mean()),
-        "mean_std": float(embeddings.std(axis=0).mean()),
-    }
+def run_sanity_checks(embeddings) -> Dict[str, float]:
+    """NaN/Inf guard + summary statistics (src/feature_extraction.py:334-356).
+
+    A numpy matrix is checked with the reference's own numpy expressions; a CUDA tensor is checked where it lives
+    (fx_column_stats: one pass for the counts and the column sums, one for the deviations, fp64 accumulation)."""
+    if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda:
+        eng = get_engine(embeddings.device, min_batch=1, state_dict=_NO_WEIGHTS)
+        with torch.cuda.device(embeddings.device):
+            st, _, _, _ = eng.column_stats(embeddings.contiguous())
+        if st["nan_count"]:
+            raise ValueError("Embedding matrix contains NaN values")
+        if st["inf_count"]:
+            raise ValueError("Embedding matrix contains inf values")
+        stats = {"num_vectors": int(embeddings.shape[0]), "dimension": int(embeddings.shape[1]),
+                 "mean_abs_mean": st["mean_abs_mean"], "mean_std": st["mean_std"]}
+    else:
+        if np.isnan(embeddings).any():
+            raise ValueError("Embedding matrix contains NaN values")
+        if np.isinf(embeddings).any():
+            raise ValueError("Embedding matrix contains inf values")
+        stats = {
+            "num_vectors": int(embeddings.shape[0]),
+            "dimension": int(embeddings.shape[1]),
+            "mean_abs_mean": float(np.abs(embeddings.mean(axis=0)).mean()),
+            "mean_std": float(embeddings.std(axis=0).mean()),
+        }
     logging.info("Embedding stats — vectors: %d, dim: %d, mean(|mean|): %.5f, mean(std): %.5f",
                  stats["num_vectors"], stats["dimension"], stats["mean_abs_mean"], stats["mean_std"])
     return stats
 
 
-def nearest_neighbor_probe(embeddings: np.ndarray, records: Sequence[ImageRecord], sample_size: int = NEIGHBOR_SAMPLE,
+def nearest_neighbor_probe(embeddings, records: Sequence[ImageRecord], sample_size: int = NEIGHBOR_SAMPLE,
                            seed: int = RNG_SEED) -> List[Dict[str, object]]:
-    """Cosine nearest neighbour of a few seeded queries (src/feature_extraction.py:359-398)."""
+    """Cosine nearest neighbour of a few seeded queries (src/feature_extraction.py:359-398); numpy matrix -> numpy as
+    the reference, CUDA tensor -> fx_neighbor_probe (same sampled rows, same tie rule)."""
     n = embeddings.shape[0]
     k = min(sample_size, n - 1)
     if n < 2 or k <= 0:
         return []
     queries = np.random.default_rng(seed).choice(n, size=k, replace=False)
-    unit = embeddings / np.clip(np.linalg.norm(embeddings, axis=1, keepdims=True), a_min=1e-12, a_max=None)
     probe = []
-    for q in queries:
-        sims = unit[q] @ unit.T
-        sims[q] = -np.inf
-        best = int(np.argmax(sims))
-        probe.append({"query": str(records[q].relative_path), "neighbor": str(records[best].relative_path),
-                      "similarity": float(sims[best])})
+    if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda:
+        eng = get_engine(embeddings.device, min_batch=1, state_dict=_NO_WEIGHTS)
+        with torch.cuda.device(embeddings.device):
+            rows, sims = eng.neighbor_probe(embeddings.contiguous(), queries)
+        for q, best, sim in zip(queries, rows, sims):
+            probe.append({"query": str(records[q].relative_path), "neighbor": str(records[int(best)].relative_path),
+                          "similarity": float(sim)})
+    else:
+        unit = embeddings / np.clip(np.linalg.norm(embeddings, axis=1, keepdims=True), a_min=1e-12, a_max=None)
+        for q in queries:
+            sims = unit[q] @ unit.T
+            sims[q] = -np.inf
+            best = int(np.argmax(sims))
+            probe.append({"query": str(records[q].relative_path), "neighbor": str(records[best].relative_path),
+                          "similarity": float(sims[best])})
     logging.info("Nearest-neighbor probe completed for %d samples", len(probe))
     return probe
 
@@ -563,8 +599,12 @@ def main(argv: Optional[Sequence[str]] = None) -> None:
     results = extract_embeddings(records, device=device, batch_size=args.batch_size)
     logging.info("Completed embedding extraction in %.2f seconds", time.perf_counter() - t0)
     if rank == 0:
-        stats = run_sanity_checks(results.embeddings)
-        probe = nearest_neighbor_probe(results.embeddings, results.records)
+        # large gathered matrices are post-processed where they already are (SSIP_B200_DEVICE_POSTPROCESS = 0 | 1 | auto)
+        mode = os.environ.get("SSIP_B200_DEVICE_POSTPROCESS", "auto")
+        on_device = results.device_embeddings is not None and (mode == "1" or (mode == "auto" and results.embeddings.shape[0] >= 100_000))
+        matrix = results.device_embeddings if on_device else results.embeddings
+        stats = run_sanity_checks(matrix)
+        probe = nearest_neighbor_probe(matrix, results.records)
         save_artifacts(results, stats, probe, args.data_dir, device)
         logging.info("Artifacts saved to %s", FEATURE_OUTPUT_DIR)
     if size > 1 and torch.distributed.is_initialized():
