@@ -221,8 +221,9 @@ typedef struct fx_matrix_stats {
 int fx_column_stats(fx_handle h, const float *emb_dev, int64_t n, int d, double *col_mean_dev, double *col_std_dev,
                     double *col_var_dev, fx_matrix_stats *stats, void *stream);
 
-/* StandardScaler.transform as numpy executes it in place on a float32 matrix: t = fp32(x - mean) in fp64 arithmetic,
- * z = fp32(t / scale).  scale_dev is the caller's (std with near-constant columns replaced by 1, sklearn semantics). */
+/* StandardScaler.transform as scikit-learn (>= 1.3; 1.9 installed) executes it on a float32 matrix: mean and scale
+ * rounded to fp32, z = (x - mean) / scale in fp32 IEEE arithmetic, bit for bit.  scale_dev is the caller's (std with
+ * near-constant columns replaced by 1, sklearn's _is_constant_feature rule). */
 int fx_standardize(fx_handle h, const float *emb_dev, int64_t n, int d, const double *col_mean_dev, const double *col_scale_dev,
                    float *out_dev, void *stream);
 

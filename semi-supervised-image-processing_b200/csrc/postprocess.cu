@@ -89,13 +89,15 @@ __global__ void colstd_kernel(const double* __restrict__ part, int blocks, int d
     }
 }
 
-// StandardScaler.transform as numpy executes it: X -= mean_ (fp64 arithmetic, rounded to fp32), X /= scale_ (same)
+// StandardScaler.transform as scikit-learn >= 1.3 executes it on a float32 matrix (sklearn/preprocessing/_data.py:
+// `X -= astype(mean_, X.dtype); X /= astype(scale_, X.dtype)`): mean and scale rounded to fp32, then fp32 IEEE
+// subtraction and division -- reproduced bit for bit.
 __global__ void standardize_kernel(const float* __restrict__ x, long long total, int d, const double* __restrict__ mean,
                                    const double* __restrict__ scale, float* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % d);
-        const float t = (float)((double)x[i] - mean[c]);
-        out[i] = (float)((double)t / scale[c]);
+        const float t = __fsub_rn(x[i], (float)mean[c]);
+        out[i] = __fdiv_rn(t, (float)scale[c]);
     }
 }
 

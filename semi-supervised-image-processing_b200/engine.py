@@ -230,7 +230,7 @@ class Engine:
                  "mean_std": float(st.mean_std)}, mean, std, var)
 
     def standardize(self, x: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
-        """z = fp32(fp32(x - mean) / scale) with fp64 arithmetic, as StandardScaler.transform on a float32 matrix."""
+        """z = (x - fp32(mean)) / fp32(scale) in fp32, as scikit-learn's StandardScaler.transform on a float32 matrix."""
         n, d = self._matrix(x)
         if mean.dtype != torch.float64 or scale.dtype != torch.float64 or mean.numel() != d or scale.numel() != d:
             raise TypeError("mean / scale must be fp64 CUDA tensors [d]")

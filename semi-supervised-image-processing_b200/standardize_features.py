@@ -5,7 +5,7 @@ Same CLI (``--embeddings-npy --embeddings-csv --output-npz --log-level``, src/st
 checks and exceptions (:15-39), same bundle keys ``features, paths, is_labeled, labels, scaler_mean, scaler_scale``
 (:49-58).  The scaler: column mean / variance with fp64 accumulation (fx_column_stats), near-constant columns get
 scale 1 by scikit-learn's own rule (sklearn/preprocessing/_data.py _is_constant_feature / _handle_zeros_in_scale),
-transform = numpy's in-place float32 arithmetic (fx_standardize).  No CPU fallback.
+transform = scikit-learn's float32 arithmetic, bit for bit (fx_standardize).  No CPU fallback.
 """
 from __future__ import annotations
 
