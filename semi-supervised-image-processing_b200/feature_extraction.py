@@ -22,6 +22,7 @@ bench.py use that.  ``SSIP_B200_PRECISION`` = ``bf16`` (default) or ``fp32`` (ti
 from __future__ import annotations
 
 import argparse
+import atexit
 import hashlib
 import json
 import logging
@@ -38,6 +39,7 @@ import torch
 from PIL import Image, UnidentifiedImageError
 
 from . import _native as N
+from ._decode_pool import DecodePool
 from . import dist as fxdist
 from .engine import Engine, pack_images
 
@@ -72,6 +74,7 @@ WEIGHTS_ENV = "SSIP_B200_WEIGHTS"
 PRECISION_ENV = "SSIP_B200_PRECISION"
 GRAY_CARRIAGE_ENV = "SSIP_B200_GRAY_CARRIAGE"  # "1": ship R==G==B files as one plane
 DECODE_THREADS_ENV = "SSIP_B200_DECODE_THREADS"
+DECODE_MODE_ENV = "SSIP_B200_DECODE"  # "process" | "thread" | "auto" (default: worker processes from 512 files up)
 
 
 @dataclass(frozen=True)
@@ -222,20 +225,21 @@ def get_engine(device: torch.device, min_batch: int = BATCH_SIZE, state_dict: Op
 # --- transform / model: same call shapes as the reference ----------------------------------------
 
 
-def _decoded_array(img: Image.Image) -> np.ndarray:
-    """The HWC uint8 array ToTensor would see, with the reference's failure modes.
-
-    The reference never converts modes (src/feature_extraction.py:233-240): anything that is not
-    three 8-bit bands makes Normalize raise.  Same exception types here.
-    """
-    bands = len(img.getbands())
-    if img.mode in ("I", "I;16", "I;16L", "I;16B", "F"):
-        raise TypeError(f"Input tensor should be a float tensor after ToTensor; mode {img.mode!r} images are not 8-bit")
+def _check_mode(mode: str, bands: int) -> None:
+    """The reference never converts modes (src/feature_extraction.py:233-240): anything that is not three 8-bit
+    bands makes ToTensor / Normalize raise.  Same exception types here."""
+    if mode in ("I", "I;16", "I;16L", "I;16B", "F"):
+        raise TypeError(f"Input tensor should be a float tensor after ToTensor; mode {mode!r} images are not 8-bit")
     if bands != 3:
         raise RuntimeError(
             f"output with shape [{bands}, {TARGET_CROP}, {TARGET_CROP}] doesn't match the broadcast shape "
-            f"[3, {TARGET_CROP}, {TARGET_CROP}] (image mode {img.mode!r}; the pipeline does no RGB conversion)"
+            f"[3, {TARGET_CROP}, {TARGET_CROP}] (image mode {mode!r}; the pipeline does no RGB conversion)"
         )
+
+
+def _decoded_array(img: Image.Image) -> np.ndarray:
+    """The HWC uint8 array ToTensor would see, with the reference's failure modes."""
+    _check_mode(img.mode, len(img.getbands()))
     arr = np.asarray(img)
     if arr.dtype != np.uint8:
         raise TypeError(f"unsupported pixel type {arr.dtype} for mode {img.mode!r}")
@@ -320,6 +324,35 @@ def _load_file(path: Path):
         return exc
 
 
+_DECODE_POOL: Optional[DecodePool] = None
+
+
+def _process_pool(workers: int, slots: int) -> DecodePool:
+    """The worker processes are started once per interpreter (about 2 s) and reused by later calls."""
+    global _DECODE_POOL
+    if _DECODE_POOL is None or _DECODE_POOL.workers != workers:
+        if _DECODE_POOL is not None:
+            _DECODE_POOL.close()
+        _DECODE_POOL = DecodePool(workers, slots)
+        atexit.register(_DECODE_POOL.close)
+    return _DECODE_POOL
+
+
+def _pin(t: torch.Tensor) -> torch.Tensor:
+    """Page-lock a shared-memory staging tensor so that its H2D copy is an asynchronous DMA (best effort)."""
+    rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
+    t._fx_pinned = int(rc) == 0  # type: ignore[attr-defined]
+    if not t._fx_pinned:  # type: ignore[attr-defined]
+        logging.warning("cudaHostRegister failed (%s): staging buffer stays pageable, copies will be slower", rc)
+    return t
+
+
+def _unpin(t: Optional[torch.Tensor]) -> None:
+    if t is not None and getattr(t, "_fx_pinned", False):
+        torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+        t._fx_pinned = False  # type: ignore[attr-defined]
+
+
 def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int):
     """Single-GPU pass over `records`: embeddings + bookkeeping.
 
@@ -351,31 +384,93 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
         t_last = now
         pending[slot] = None
 
-    with ThreadPoolExecutor(max_workers=threads) as pool, torch.cuda.device(eng.device):
-        slot = 0
-        for lo in range(0, len(records), batch_size):
-            chunk = records[lo : lo + batch_size]
-            decoded = list(pool.map(_load_file, [r.absolute_path for r in chunk]))
-            arrays, ok = [], []
-            for off, (rec, item) in enumerate(zip(chunk, decoded)):
-                if isinstance(item, BaseException):
-                    logging.error("Failed to decode %s: %s", rec.absolute_path, item)
-                    failures.append(rec.absolute_path)
-                else:
-                    arrays.append(item)
-                    ok.append(lo + off)
-            if not arrays:
+    mode = os.environ.get(DECODE_MODE_ENV, "auto")
+    use_procs = mode == "process" or (mode == "auto" and len(records) >= 512)
+    gray = os.environ.get(GRAY_CARRIAGE_ENV) == "1"
+
+    def fail(rec: ImageRecord, text: str) -> None:
+        logging.error("Failed to decode %s: %s", rec.absolute_path, text)
+        failures.append(rec.absolute_path)
+
+    def stage_with_threads(pool, chunk, lo, slot):
+        """Decode on threads, then pack into the slot's pinned buffer -> (descs, n, total bytes, record indices)."""
+        decoded = list(pool.map(_load_file, [r.absolute_path for r in chunk]))
+        arrays, ok = [], []
+        for off, (rec, item) in enumerate(zip(chunk, decoded)):
+            if isinstance(item, BaseException):
+                fail(rec, str(item))
+            else:
+                arrays.append(item)
+                ok.append(lo + off)
+        if not arrays:
+            return None
+        finish(slot)  # the slot's buffers are free again once its previous batch is out
+        need = sum((a.size + 255) // 256 * 256 for a in arrays)
+        if staging[slot] is None or staging[slot].numel() < need:
+            staging[slot] = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8).pin_memory()
+        _, descs, total = pack_images(arrays, out=staging[slot].numpy())
+        return descs, len(arrays), total, ok
+
+    def stage_with_processes(pool: DecodePool, chunk, lo, slot):
+        """Header pass -> layout -> worker processes decode straight into the slot's shared, page-locked buffer."""
+        metas = pool.probe([str(r.absolute_path) for r in chunk])
+        jobs, ok, off = [], [], 0
+        for k, (rec, m) in enumerate(zip(chunk, metas)):
+            if isinstance(m[0], str):  # failure triple (kind, exception name, text)
+                if m[0] != "decode":
+                    raise RuntimeError(f"{m[1]} while opening {rec.absolute_path}: {m[2]}")
+                fail(rec, m[2])
                 continue
-            finish(slot)  # the slot's buffers are free again once its previous batch is out
-            need = sum((a.size + 255) // 256 * 256 for a in arrays)
-            if staging[slot] is None or staging[slot].numel() < need:
-                staging[slot] = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8).pin_memory()
-            _, descs, total = pack_images(arrays, out=staging[slot].numpy())
-            eng.embed_host_async(slot, staging[slot], descs, len(arrays), total, outs[slot])
-            pending[slot] = (ok, len(arrays))
-            slot = (slot + 1) % nslots
-        for k in range(nslots):  # oldest first
-            finish((slot + k) % nslots)
+            h, w, bands, pil_mode = m
+            _check_mode(pil_mode, bands)
+            jobs.append((str(rec.absolute_path), off, h, w, bands, gray))
+            ok.append(lo + k)
+            off += (h * w * bands + 255) // 256 * 256
+        if not jobs:
+            return None
+        finish(slot)
+        if staging[slot] is None or staging[slot].numel() < off:
+            _unpin(staging[slot])
+            staging[slot] = None
+            shm, _ = pool.buffer(slot, off)
+            staging[slot] = _pin(torch.frombuffer(shm.buf, dtype=torch.uint8))
+        done = pool.decode(slot, jobs)
+        descs = (N.ImageDesc * len(jobs))()
+        n, kept_idx = 0, []
+        for job, idx, res in zip(jobs, ok, done):
+            if not isinstance(res, int):  # pixel data broken although the header parsed
+                if res[0] != "decode":
+                    raise RuntimeError(f"{res[1]} while decoding {job[0]}: {res[2]}")
+                fail(records[idx], res[2])
+                continue
+            descs[n].offset, descs[n].height, descs[n].width, descs[n].channels = job[1], job[2], job[3], res
+            kept_idx.append(idx)
+            n += 1
+        return (descs, n, off, kept_idx) if n else None
+
+    pool_cm = _process_pool(threads, nslots) if use_procs else ThreadPoolExecutor(max_workers=threads)
+    stage = stage_with_processes if use_procs else stage_with_threads
+    try:
+        with torch.cuda.device(eng.device):
+            slot = 0
+            for lo in range(0, len(records), batch_size):
+                staged = stage(pool_cm, records[lo : lo + batch_size], lo, slot)
+                if staged is None:
+                    continue
+                descs, n_ok, total, ok = staged
+                eng.embed_host_async(slot, staging[slot], descs, n_ok, total, outs[slot])
+                pending[slot] = (ok, n_ok)
+                slot = (slot + 1) % nslots
+            for k in range(nslots):  # oldest first
+                finish((slot + k) % nslots)
+    finally:
+        if use_procs:
+            for k in range(nslots):
+                _unpin(staging[k])
+                staging[k] = None
+                pool_cm.release(k)
+        else:
+            pool_cm.shutdown(wait=True)
     order = np.argsort(np.asarray(kept, dtype=np.int64), kind="stable") if kept else np.zeros(0, np.int64)
     local = np.concatenate(blocks, axis=0)[order] if blocks else np.empty((0, 512), np.float32)
     kept = [kept[i] for i in order]

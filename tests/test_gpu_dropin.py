@@ -190,3 +190,35 @@ def test_size_independent_properties_at_scale():
     assert torch.equal(base[1000], base[7]) and torch.equal(base[4095], base[7])
     assert bool(torch.isfinite(base).all())
     assert float((base[0] - base[1]).abs().max()) > 0  # different images do differ
+
+
+def test_process_decode_pool_gives_the_same_result_as_threads(dataset, tmp_path, monkeypatch):
+    """worker processes decoding into the shared page-locked staging buffer change nothing but
+    the speed -- same rows, same failures (incl. a file whose header parses but whose pixel data is truncated), same
+    exception for a channel count the reference cannot normalise."""
+    from PIL import Image
+
+    root, imgs = dataset
+    full = tmp_path / "data"
+    import shutil
+
+    shutil.copytree(root, full)
+    Image.fromarray(imgs[0]).save(full / "sans_label" / "a_good.jpg", quality=90)
+    data = (full / "sans_label" / "a_good.jpg").read_bytes()
+    (full / "sans_label" / "b_truncated.jpg").write_bytes(data[: len(data) // 3])
+    records = fx.discover_image_records(full)
+    monkeypatch.setenv(fx.DECODE_MODE_ENV, "thread")
+    a = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=6)
+    monkeypatch.setenv(fx.DECODE_MODE_ENV, "process")
+    monkeypatch.setenv(fx.DECODE_THREADS_ENV, "4")
+    b = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=6)
+    assert np.array_equal(a.embeddings, b.embeddings)
+    assert [r.relative_path for r in a.records] == [r.relative_path for r in b.records]
+    assert sorted(p.name for p in a.failures) == sorted(p.name for p in b.failures) == ["b_truncated.jpg", "zz_broken.png"]
+    monkeypatch.setenv(fx.GRAY_CARRIAGE_ENV, "1")  # R==G==B files travel as one plane: same embeddings
+    c = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=6)
+    assert np.array_equal(a.embeddings, c.embeddings)
+    monkeypatch.delenv(fx.GRAY_CARRIAGE_ENV)
+    Image.fromarray(imgs[1][..., 0]).save(full / "sans_label" / "c_gray.png")  # true mode "L": the reference raises
+    with pytest.raises(RuntimeError, match="broadcast shape"):
+        fx.extract_embeddings(fx.discover_image_records(full), torch.device("cuda:0"), batch_size=6)

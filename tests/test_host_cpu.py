@@ -297,3 +297,50 @@ def test_inference_drop_ins_keep_the_reference_signatures(have_reference):
     assert params(inference.evaluate_model) == params(ref_common.evaluate_model)
     assert params(inference.compute_probs) == params(ref_sweep.compute_probs)
     assert params(inference.build_transforms) == params(ref_common.build_transforms)
+
+
+def test_decode_pool_processes_write_pillow_pixels_into_shared_memory(tmp_path):
+    """SURVEY.md 8f rank 1 (host decode pool): worker processes decode with the reference's own Pillow call straight
+    into the shared staging buffer; failures come back per file with the reference's two tolerated exception types
+    marked as such (src/feature_extraction.py:281-284)."""
+    from PIL import Image
+
+    from ssip_b200._decode_pool import DecodePool
+
+    imgs = synthetic.ragged_images([(64, 80), (224, 224), (100, 130)], seed=8) + [synthetic.mri_like_images(1, 128, seed=2)[0]]
+    paths = []
+    for i, a in enumerate(imgs):
+        p = tmp_path / f"ok_{i}.{'png' if i % 2 else 'jpg'}"
+        Image.fromarray(a).save(p, quality=92) if p.suffix == ".jpg" else Image.fromarray(a).save(p)
+        paths.append(str(p))
+    (tmp_path / "junk.png").write_bytes(b"not an image")
+    full = (tmp_path / "ok_0.jpg").read_bytes()
+    (tmp_path / "cut.jpg").write_bytes(full[: len(full) // 3])  # header parses, pixel data is truncated
+    Image.fromarray(imgs[0][..., 0]).save(tmp_path / "gray.png")  # mode L: the caller must raise like the reference
+    paths += [str(tmp_path / "junk.png"), str(tmp_path / "cut.jpg"), str(tmp_path / "gray.png"), str(tmp_path / "missing.png")]
+    pool = DecodePool(3, 2)
+    try:
+        metas = pool.probe(paths)
+        assert metas[0] == (64, 80, 3, "RGB") and metas[3] == (128, 128, 3, "RGB")
+        assert metas[4][:2] == ("decode", "UnidentifiedImageError") and metas[7][:2] == ("decode", "FileNotFoundError")
+        assert metas[6] == (64, 80, 1, "L")
+        with pytest.raises(RuntimeError):
+            fx._check_mode("L", 1)
+        jobs, off = [], 0
+        for p, m in zip(paths[:4] + [paths[5]], metas[:4] + [metas[5]]):
+            jobs.append((p, off, m[0], m[1], m[2], p.endswith("ok_3.png")))  # gray carriage for the R==G==B MRI-like image
+            off += (m[0] * m[1] * m[2] + 255) // 256 * 256
+        shm, created = pool.buffer(1, off)
+        assert created and shm.size >= off
+        res = pool.decode(1, jobs)
+        assert res[:3] == [3, 3, 3] and res[3] == 1  # the gray image went over as one plane
+        assert res[4][0] == "decode" and res[4][1] == "OSError"  # truncated JPEG: Pillow raises OSError at load
+        buf = np.frombuffer(shm.buf, dtype=np.uint8)
+        for (p, o, h, w, b, g), r in zip(jobs[:4], res[:4]):
+            want = np.asarray(Image.open(p))
+            want = want[..., 0] if r == 1 else want
+            assert np.array_equal(buf[o : o + want.size].reshape(want.shape), want)
+        del buf
+        assert pool.buffer(1, off // 2)[1] is False  # reused, not re-created
+    finally:
+        pool.close()
