@@ -1,4 +1,12 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_dropin.py -q -m gpu -x > gpurun_out/exp9_pytest.log 2>&1; echo "pytest rc=$?"
-tail -15 gpurun_out/exp9_pytest.log
-timeout 600 python tools/real_files_bench.py 4096 > gpurun_out/r01f_real_files.md 2> gpurun_out/r01f_real_files.err; echo "rc=$?"; cat gpurun_out/r01f_real_files.md; tail -3 gpurun_out/r01f_real_files.err
+timeout 900 python -m pytest tests/test_gpu_trunk.py -q -m gpu -x > gpurun_out/exp11_pytest.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/exp11_pytest.log
+B="python bench.py --steps 60 --warmup 5 --pool 4096 --no-cpu-baseline"
+$B --lanes 1 > gpurun_out/exp11_l1.json 2>/dev/null
+$B > gpurun_out/exp11_l2.json 2>/dev/null
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/exp11_*.json')):
+    d=json.load(open(f))
+    print(f, round(d['value']), 'trunk_ms', round(d['roofline_trunk']['avg_ms'],4), 'layers', [round(x,4) for x in d['layer_ms'][:7]], d['clocks']['sm_mhz'])
+PY
