@@ -309,6 +309,10 @@ void fx_destroy(fx_handle e) {
     }
     for (auto& st : e->lane_stream)
         if (st) cudaStreamDestroy(st);
+    for (auto& g : e->step_graph) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     cudaFree(e->head_w);
     cudaFree(e->head_b);
     cudaFree(e->post_scratch);
@@ -354,6 +358,8 @@ int fx_create(fx_handle* out, int device, int max_batch, int precision) {
     if (rc != FX_OK) return fail(rc);
     if ((err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
+    if (const char* g = getenv("FX_GRAPHS")) e->graphs_on = g[0] != '0';
+    if (const char* g = getenv("FX_GRAPH_MAX_BATCH")) e->graph_max_batch = atoi(g);
     if ((rc = preprocess_init(e)) != FX_OK) return fail(rc);
     if ((rc = tc_init(e)) != FX_OK) return fail(rc);
     *out = e;
@@ -378,6 +384,7 @@ int fx_load_weights(fx_handle e, const fx_conv_bn* layers, int n_layers) {
         if (rc != FX_OK) return rc;
     }
     e->weights_loaded = true;
+    e->weights_epoch++;  // captured step graphs hold the old weight pointers
     return FX_OK;
 }
 
@@ -434,6 +441,10 @@ int fx_load_head(fx_handle e, const float* weight, const float* bias, int num_cl
         return set_error(e, FX_ERR_INVALID, "fx_load_head: null pointer or num_classes outside 1.." + std::to_string(FX_MAX_CLASSES));
     FX_CUDA(e, cudaSetDevice(e->device));
     FX_CUDA(e, cudaDeviceSynchronize());  // a previous head may still be in use
+    for (auto& g : e->step_graph) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     cudaFree(e->head_w);
     cudaFree(e->head_b);
     cudaFree(e->post_scratch);
@@ -461,7 +472,117 @@ int fx_select_lane(fx_handle e, int lane) {
     return select_lane(e, lane);
 }
 
+// ---- CUDA graph of a whole step for launch-bound batch sizes ---------------------------------
+static void graph_destroy(fx_engine::StepGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g = fx_engine::StepGraph();
+}
+
+// Capture fx_preprocess (plan hit: one launch, no upload) + the trunk on `s`; find the two kernel nodes whose
+// parameters depend on the call.  Returns false (and leaves no graph) if anything about the capture fails.
+static bool graph_build(fx_engine* e, fx_engine::StepGraph& g, const uint8_t* src_dev, const fx_image_desc* descs, int n, float* emb_dev,
+                        const void* pre_func, cudaStream_t s) {
+    graph_destroy(g);
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const uint64_t launches = e->launches;
+    e->capturing = true;
+    int rc = fx_preprocess(e, src_dev, descs, n, s);
+    if (rc == FX_OK) rc = fx_forward(e, n, emb_dev, s);
+    e->capturing = false;
+    e->launches = launches;  // nothing has run yet
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(s, &graph);
+    if (rc != FX_OK || end != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return false;
+    }
+    g.graph = graph;
+    size_t count = 0;
+    if (cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess || cudaGraphGetNodes(graph, nullptr, &count) != cudaSuccess) {
+        cudaGetLastError();
+        graph_destroy(g);
+        return false;
+    }
+    std::vector<cudaGraphNode_t> nodes(count);
+    cudaGraphGetNodes(graph, nodes.data(), &count);
+    const void* pool_func = avgpool_kernel_ptr(false);
+    for (cudaGraphNode_t node : nodes) {
+        cudaGraphNodeType type;
+        cudaKernelNodeParams kp;
+        if (cudaGraphNodeGetType(node, &type) != cudaSuccess || type != cudaGraphNodeTypeKernel) continue;
+        if (cudaGraphKernelNodeGetParams(node, &kp) != cudaSuccess) continue;
+        g.kernels++;
+        if (kp.func == pre_func) g.pre_node = node;
+        if (kp.func == pool_func) g.pool_node = node;
+    }
+    if (!g.pre_node || !g.pool_node) {
+        cudaGetLastError();
+        graph_destroy(g);
+        return false;
+    }
+    g.n = n;
+    g.plan_serial = e->pre_plan[e->cur_lane].serial;
+    g.weights_epoch = e->weights_epoch;
+    g.src = src_dev;
+    g.emb = emb_dev;
+    return true;
+}
+
+// Replace kernel parameter `index` of a graph node (the other parameters keep the values captured with the graph).
+static bool graph_patch(fx_engine::StepGraph& g, cudaGraphNode_t node, int index, void* value_ptr, int n_params) {
+    cudaKernelNodeParams kp;
+    if (cudaGraphKernelNodeGetParams(node, &kp) != cudaSuccess) return false;
+    void* args[8];
+    for (int i = 0; i < n_params; ++i) args[i] = kp.kernelParams[i];
+    args[index] = value_ptr;
+    kp.kernelParams = args;
+    return cudaGraphExecKernelNodeSetParams(g.exec, node, &kp) == cudaSuccess;
+}
+
 int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, int n, float* emb_dev, void* stream) {
+    if (!e) return FX_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // Launch-bound regime (19 launches of a few microseconds each at batch <= 64): replay the step as one CUDA graph.
+    // Needs a capturable stream, the lane's preprocess plan to repeat (no descriptor upload inside the graph) and no
+    // per-launch profiling events.
+    if (e->graphs_on && s != nullptr && s != cudaStreamLegacy && !e->prof_on && n > 0 && n <= e->graph_max_batch && n <= e->max_batch &&
+        e->weights_loaded && src_dev && descs && emb_dev) {
+        const PreOut mode = e->precision == FX_PRECISION_BF16 ? PreOut::IN0_BF16 : PreOut::IN0_F32;
+        const void* pre_func = nullptr;
+        if (preprocess_plan_hit(e, descs, n, mode, &pre_func)) {
+            FX_CUDA(e, cudaSetDevice(e->device));
+            FX_CUDA(e, cudaStreamWaitEvent(s, e->img_host_free, 0));  // the plan's upload may be on another stream
+            fx_engine::StepGraph& g = e->step_graph[e->cur_lane];
+            const bool usable = g.exec && g.n == n && g.plan_serial == e->pre_plan[e->cur_lane].serial && g.weights_epoch == e->weights_epoch;
+            if (!usable && !graph_build(e, g, src_dev, descs, n, emb_dev, pre_func, s)) e->graphs_on = false;  // never try again on this handle
+            if (g.exec && e->graphs_on) {
+                bool ok = true;
+                if (g.src != src_dev) {
+                    const void* v = src_dev;
+                    ok = graph_patch(g, g.pre_node, 0, &v, e->pre_plan[e->cur_lane].s2d ? 4 : 7);
+                    g.src = src_dev;
+                }
+                if (ok && g.emb != emb_dev) {
+                    float* v = emb_dev;
+                    ok = graph_patch(g, g.pool_node, 1, &v, 5);
+                    g.emb = emb_dev;
+                }
+                if (ok && cudaGraphLaunch(g.exec, s) == cudaSuccess) {
+                    e->staged = n;
+                    e->launches += g.kernels;
+                    return FX_OK;
+                }
+                cudaGetLastError();
+                graph_destroy(g);
+                e->graphs_on = false;
+            }
+        }
+    }
     int rc = fx_preprocess(e, src_dev, descs, n, stream);
     if (rc != FX_OK) return rc;
     return fx_forward(e, n, emb_dev, stream);

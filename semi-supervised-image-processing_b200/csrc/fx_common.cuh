@@ -146,7 +146,24 @@ struct fx_engine {
         bool valid = false, s2d = false;
         int mode = 0, transform = 0, n = 0, kernel = 0, bands = 0, smem = 0, tmp_bytes = 0, rowbuf = 0;
         std::vector<fx_image_desc> descs;
+        uint64_t serial = 0;  // bumped whenever the plan is rebuilt (CUDA-graph cache key)
     } pre_plan[FX_MAX_LANES];
+    // CUDA graph of one whole step (preprocess + trunk) per lane, for launch-bound batch sizes: captured once the
+    // lane's preprocess plan repeats, replayed with the two call-specific pointers (source images, embedding output)
+    // patched into its first and last kernel node (engine.cu)
+    struct StepGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t pre_node = nullptr, pool_node = nullptr;
+        int n = 0, kernels = 0;
+        uint64_t plan_serial = 0, weights_epoch = 0;
+        const uint8_t* src = nullptr;
+        float* emb = nullptr;
+    } step_graph[FX_MAX_LANES];
+    bool graphs_on = true;     // FX_GRAPHS=0 disables; switched off for the handle if a capture ever fails
+    int graph_max_batch = 64;  // FX_GRAPH_MAX_BATCH: above this a step is GPU-bound and launched directly
+    bool capturing = false;
+    uint64_t weights_epoch = 0;
 
     // host-buffer path (fx_embed_host*): FX_HOST_SLOTS pipelined slots (device copies of one batch's packed images and
     // embeddings); slot s computes on lane s % FX_MAX_LANES, whose stream serialises the slots that share its buffers.
@@ -219,6 +236,9 @@ enum class PreOut : int { NCHW_F32 = 0, IN0_BF16 = 1, IN0_F32 = 2 };
 int preprocess_init(fx_engine* e);
 void preprocess_free(fx_engine* e);
 int preprocess_lane_init(fx_engine* e);  // per-lane descriptor buffers -> the active lane's fields
+// true if `descs` repeats the active lane's previous batch (no upload needed); *kernel = the kernel that would launch
+bool preprocess_plan_hit(fx_engine* e, const fx_image_desc* descs, int n, PreOut mode, const void** kernel);
+const void* avgpool_kernel_ptr(bool in_is_bf16);
 int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode,
                    void* out, cudaStream_t stream);
 int stage_nchw_run(fx_engine* e, const float* in_dev, int n, cudaStream_t stream);

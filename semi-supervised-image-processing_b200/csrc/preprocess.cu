@@ -904,6 +904,14 @@ static int preprocess_launch(fx_engine* e, const fx_engine::PrePlan& plan, const
     return FX_OK;
 }
 
+bool preprocess_plan_hit(fx_engine* e, const fx_image_desc* descs, int n, PreOut mode, const void** kernel) {
+    const fx_engine::PrePlan& plan = e->pre_plan[e->cur_lane];
+    const bool hit = n > 0 && plan.valid && plan.mode == (int)mode && plan.transform == e->transform && plan.n == n &&
+                     std::memcmp(plan.descs.data(), descs, sizeof(fx_image_desc) * n) == 0;
+    if (hit && kernel) *kernel = plan.s2d ? reinterpret_cast<const void*>(s2d_kernels()[plan.kernel]) : reinterpret_cast<const void*>(pre_kernels()[plan.kernel]);
+    return hit;
+}
+
 int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode, void* out,
                    cudaStream_t stream) {
     if (n == 0) return FX_OK;
@@ -913,10 +921,13 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     const bool hit = plan.valid && plan.mode == (int)mode && plan.transform == e->transform && plan.n == n &&
                      std::memcmp(plan.descs.data(), descs, sizeof(fx_image_desc) * n) == 0;
     if (hit) {
-        FX_CUDA(e, cudaStreamWaitEvent(stream, e->img_host_free, 0));  // the upload may have been queued on another stream
+        // the upload may have been queued on another stream (while capturing a graph the caller has already waited)
+        if (!e->capturing) FX_CUDA(e, cudaStreamWaitEvent(stream, e->img_host_free, 0));
         return preprocess_launch(e, plan, src_dev, n, mode, out, stream);
     }
+    if (e->capturing) return set_error(e, FX_ERR_STATE, "preprocess: descriptor upload inside a graph capture");
     plan.valid = false;
+    plan.serial++;
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
     int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
     bool all_s2d = mode == PreOut::IN0_BF16 && !e->pre_force_banded && e->norm_fma_ok;  // every image can take the column-walk kernel

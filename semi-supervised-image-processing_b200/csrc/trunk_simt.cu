@@ -236,6 +236,10 @@ __global__ void avgpool_kernel(const void* __restrict__ in_, float* __restrict__
     out[i] = s / (float)hw;
 }
 
+const void* avgpool_kernel_ptr(bool in_is_bf16) {
+    return in_is_bf16 ? reinterpret_cast<const void*>(avgpool_kernel<true>) : reinterpret_cast<const void*>(avgpool_kernel<false>);
+}
+
 int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n, int hw, int c, cudaStream_t stream) {
     const int total = n * c;
     if (in_is_bf16)

@@ -9,6 +9,8 @@ Floating-point work, so the comparison is against a plain PyTorch fp32 evaluatio
     cosine >= 0.999 and relative L2 <= 1e-2.
 Reference lines: src/feature_extraction.py:210-227,289-294; torchvision/models/resnet.py:89-105,266-282.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -294,3 +296,44 @@ def test_lanes_are_independent_and_give_identical_rows(eng_bf16):
         assert np.array_equal(ob.cpu().numpy(), want_b)
     with pytest.raises(N.FxError):
         eng_bf16.select_lane(2)
+
+
+def test_step_graph_replay_is_byte_identical_to_direct_launches(eng_bf16):
+    """Launch-bound batch sizes (<= 64 images) replay the whole step as one CUDA graph once the lane's preprocess plan
+    repeats; the source / output pointers are patched per call.  Same bytes as the direct launches, on both lanes,
+    across a weight reload and a geometry change."""
+    os.environ["FX_GRAPHS"] = "0"
+    try:
+        ref_eng = Engine(0, max_batch=64, precision="bf16")  # graphs disabled for this handle: direct launches only
+    finally:
+        os.environ.pop("FX_GRAPHS")
+    side = torch.cuda.Stream()
+    xs = [torch.from_numpy(synthetic.noise_images(24, 224, 224, seed=50 + i).reshape(-1)).cuda() for i in range(4)]
+    descs = uniform_descs(24, 224, 224)
+    for randbn in (False, True):
+        state = rp.make_backbone(randomize_bn=randbn).state_dict()
+        eng_bf16.load_state_dict(state)
+        ref_eng.load_state_dict(state)
+        want = [ref_eng.embed_device(x, descs, 24).cpu().numpy() for x in xs]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            before = eng_bf16.launch_count
+            outs = []
+            for i, x in enumerate(xs * 2):  # call 1 uploads the plan, call 2 captures, calls 3.. replay with new pointers
+                eng_bf16.select_lane(i & 1)
+                outs.append(eng_bf16.embed_device(x, descs, 24))
+            eng_bf16.select_lane(0)
+            side.synchronize()
+            assert eng_bf16.launch_count - before == 8 * 19  # replays are counted kernel by kernel
+        for i, o in enumerate(outs):
+            assert np.array_equal(o.cpu().numpy(), want[i % 4]), (randbn, i)
+    # a different geometry invalidates the plan and with it the graph
+    big = synthetic.mri_like_images(24, 512, seed=3)
+    d = torch.from_numpy(big.reshape(-1)).cuda()
+    want = ref_eng.embed_device(d, uniform_descs(24, 512, 512), 24).cpu().numpy()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            got = eng_bf16.embed_device(d, uniform_descs(24, 512, 512), 24)
+        side.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+    ref_eng.close()
