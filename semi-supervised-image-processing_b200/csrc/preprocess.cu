@@ -625,6 +625,25 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
     const size_t pitch = (size_t)img.w * 3;
     const uint8_t* base = src + img.src_off;
 
+    // stage the source rows (only the byte range the crop touches) with cp.async: the copies are in flight while the
+    // tables and this thread's taps are fetched below (a third of the kernel's warp time used to be spent waiting here).
+    // The images are never written by a kernel of this library, so this may overlap the previous kernel's tail (PDL).
+    const int nvec_max = src_pitch >> 4;
+    const unsigned div_magic = (1u << 24) / (unsigned)nvec_max + 1;  // idx / nvec_max == (idx * magic) >> 24 for idx < 4096
+    const uint32_t s_src_addr = (uint32_t)__cvta_generic_to_shared(s_src);
+    for (int idx = tid; idx < nrows * nvec_max; idx += kS2dThreads) {
+        const int r = (int)(((unsigned)idx * div_magic) >> 24), j = idx - r * nvec_max;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(base + (size_t)(rlo + r) * pitch + (size_t)img.col_lo * 3);
+        const uintptr_t a0 = ga & ~(uintptr_t)15;
+        const int shift = (int)(ga - a0);
+        if (j == 0) s_rowoff[r] = r * src_pitch + shift;
+        // every 16-byte chunk read holds at least one byte of this row (see the generic path)
+        if (j * 16 < shift + span_bytes)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_src_addr + (uint32_t)(r * src_pitch + 16 * j)),
+                         "l"(a0 + 16 * (uintptr_t)j)
+                         : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // vertical table of the band's output rows: field 0 = how many staged rows enter the ring before this row
     for (int i = tid; i < nout * 8; i += kS2dThreads) {
         const int j = i >> 3, f = i & 7, y = yfirst + j;
@@ -640,20 +659,6 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
             v = __ldg(vk + yc * img.ksv + (f - 1)) << 2;
         }
         s_vt[i] = v;
-    }
-    // stage the source rows (only the byte range the crop touches); the images are never written by a kernel of
-    // this library, so this may overlap the previous kernel's tail (PDL)
-    const int nvec_max = src_pitch >> 4;
-    const unsigned div_magic = (1u << 24) / (unsigned)nvec_max + 1;  // idx / nvec_max == (idx * magic) >> 24 for idx < 4096
-    for (int idx = tid; idx < nrows * nvec_max; idx += kS2dThreads) {
-        const int r = (int)(((unsigned)idx * div_magic) >> 24), j = idx - r * nvec_max;
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(base + (size_t)(rlo + r) * pitch + (size_t)img.col_lo * 3);
-        const uintptr_t a0 = ga & ~(uintptr_t)15;
-        const int shift = (int)(ga - a0);
-        if (j == 0) s_rowoff[r] = r * src_pitch + shift;
-        // every 16-byte chunk read holds at least one byte of this row (see the generic path)
-        if (j * 16 < shift + span_bytes)
-            reinterpret_cast<uint4*>(s_src + (size_t)r * src_pitch)[j] = ldg_stream16(reinterpret_cast<const void*>(a0 + 16 * (uintptr_t)j));
     }
     if (tid < NTV) s_rowoff[nrows + tid] = (nrows + tid) * src_pitch;  // rows only zero-weight taps reach
 
@@ -679,6 +684,7 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
         // keep them in registers: ptxas otherwise re-derives the selects from tid inside the row loop
         asm volatile("" : "+f"(na0[c]), "+f"(nb0[c]), "+f"(na1[c]), "+f"(nb1[c]));
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     pdl_wait();  // the staging tensor may still be read by the previous batch's stem kernel
     if (!active) return;
