@@ -564,7 +564,7 @@ int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, in
                 bool ok = true;
                 if (g.src != src_dev) {
                     const void* v = src_dev;
-                    ok = graph_patch(g, g.pre_node, 0, &v, e->pre_plan[e->cur_lane].s2d ? 4 : 7);
+                    ok = graph_patch(g, g.pre_node, 0, &v, e->pre_plan[e->cur_lane].s2d ? 5 : 7);
                     g.src = src_dev;
                 }
                 if (ok && g.emb != emb_dev) {

@@ -56,7 +56,7 @@ struct GeomTableHost {
     int max_rows;            // source rows a band touches (upper bound)
     int col_lo, col_hi;      // source pixel columns touched by the crop [lo, hi)
     int cnt_h, cnt_v;        // largest tap count actually used inside the crop, per axis
-    int s2d_rows;            // source rows a band of the s2d kernel touches (upper bound)
+    int s2d_rows[2];         // source rows a band of the s2d kernel touches (upper bound), bands of 8 / 16 row pairs
     bool noclip;             // all taps >= 0 and sums small enough that clip8 never clips
     std::vector<int32_t> blob;  // packed device image, layout in preprocess.cu
 };
@@ -64,7 +64,7 @@ struct GeomTableHost {
 struct GeomEntry {
     int32_t* dev = nullptr;  // device copy of blob
     int ksh = 0, ksv = 0, band = 0, max_rows = 0, col_lo = 0, col_hi = 0, cnt_h = 0, cnt_v = 0;
-    int s2d_rows = 0;
+    int s2d_rows[2] = {0, 0};
     bool noclip = false;
 };
 
@@ -111,6 +111,7 @@ struct fx_engine {
     cudaEvent_t img_host_free = nullptr; // img_host may be rewritten once this has fired
     float norm_a[3] = {}, norm_b[3] = {};  // Normalize o ToTensor as one FMA per value (preprocess.cu, NormFma)
     bool norm_fma_ok = false;            // ... proven equal to the bf16 table for all 768 inputs at start-up
+    bool s2d_ppb16 = false;              // FX_DEBUG_S2D_PPB=16: bands of 16 row pairs instead of 8 (slower; measurement knob)
     bool pre_force_banded = false;       // FX_DEBUG_PRE_BANDED=1: measurement knob (preprocess.cu)
 
     // trunk
@@ -144,7 +145,7 @@ struct fx_engine {
     // preprocess launch plan of each lane's last batch; reused when the next batch has the same descriptor table
     struct PrePlan {
         bool valid = false, s2d = false;
-        int mode = 0, transform = 0, n = 0, kernel = 0, bands = 0, smem = 0, tmp_bytes = 0, rowbuf = 0;
+        int mode = 0, transform = 0, n = 0, kernel = 0, bands = 0, smem = 0, tmp_bytes = 0, rowbuf = 0, ppb = 8;
         std::vector<fx_image_desc> descs;
         uint64_t serial = 0;  // bumped whenever the plan is rebuilt (CUDA-graph cache key)
     } pre_plan[FX_MAX_LANES];

@@ -100,7 +100,8 @@ int crop_offset(int size) {
 //   [.., +224*ksv)      vertical taps
 constexpr int kGeomHdr = 4 * kCrop;
 constexpr int kMaxTmpRows = 48;
-constexpr int kS2dBands = 14;     // s2d kernel: 13 bands of 8 row pairs + one of 9 (113 pairs carry data)
+constexpr int kS2dPairs = kCrop / 2 + 1;  // 113 s2d row pairs carry data; a band is 8 or 16 of them (the last one more)
+constexpr int kS2dVtRows = 34;           // output rows of the largest band (17 pairs)
 constexpr int kS2dThreads = 128;  // one thread per s2d column X = 1 .. 113
 
 static void axis_for_crop(int in_size, int out_size, int crop_off, std::vector<int32_t>& mn, std::vector<int32_t>& ct,
@@ -165,11 +166,14 @@ static bool build_geom(int h, int w, int transform, GeomTableHost& g) {
             const int y0 = std::max(0, 16 * k - 1), y1 = std::min(kCrop, 16 * k + 15) - 1;
             g.max_rows = std::max(g.max_rows, vmn[y1] + vct[y1] - vmn[y0]);
         }
-    // s2d kernel: band b = crop rows [16b-1, 16b+15), the last (b = 13) up to row 223
-    g.s2d_rows = 0;
-    for (int b = 0; b < kS2dBands; ++b) {
-        const int y0 = std::max(0, 16 * b - 1), y1 = (b == kS2dBands - 1 ? kCrop : 16 * b + 15) - 1;
-        g.s2d_rows = std::max(g.s2d_rows, vmn[y1] + vct[y1] - vmn[y0]);
+    // s2d kernel: band b = ppb row pairs = crop rows [2*ppb*b - 1, 2*ppb*(b+1) - 1), the last band up to row 223
+    for (int v = 0; v < 2; ++v) {
+        const int ppb = v ? 16 : 8, nb = (kCrop / 2 + 1) / ppb;  // 14 bands of 8 pairs (+1), or 7 of 16 (+1)
+        g.s2d_rows[v] = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int y0 = std::max(0, 2 * ppb * b - 1), y1 = (b == nb - 1 ? kCrop : 2 * ppb * (b + 1) - 1) - 1;
+            g.s2d_rows[v] = std::max(g.s2d_rows[v], vmn[y1] + vct[y1] - vmn[y0]);
+        }
     }
     // clip8 is the identity when every tap is >= 0 and the taps of an output sample sum to at most 2^22 + 4096:
     // 2^21 + 255 * (2^22 + 4096) < 256 * 2^22 (and the s2d kernel's x4-scaled accumulator stays below 2^32).  True for Pillow's normalised triangle filter; checked, not assumed.
@@ -597,17 +601,17 @@ struct NormFma {
 
 template <int NTH, int NTV>
 __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8_t* __restrict__ src, const ImgDev* __restrict__ imgs,
-                                                                     __nv_bfloat16* __restrict__ out, const NormFma nf) {
+                                                                     __nv_bfloat16* __restrict__ out, const NormFma nf, const int ppb) {
     extern __shared__ __align__(16) uint8_t smem[];
     const ImgDev img = imgs[blockIdx.y];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int npair = b == kS2dBands - 1 ? 9 : 8;
-    const int yfirst = 16 * b - 1;  // crop row of output row j = 0 of this band (row -1 / 224 = conv padding)
+    const int npair = b == (int)gridDim.x - 1 ? kS2dPairs - ppb * b : ppb;  // ppb = 8 or 16 row pairs per band
+    const int yfirst = 2 * ppb * b - 1;  // crop row of output row j = 0 of this band (row -1 / 224 = conv padding)
     const int nout = 2 * npair;
     const int ya = max(0, yfirst), yb = min(kCrop, yfirst + nout);
 
-    int32_t* s_vt = reinterpret_cast<int32_t*>(smem);  // [18][8]: new source rows, k0..k4 (x4), -, row valid
-    int32_t* s_rowoff = s_vt + 18 * 8;                 // [kMaxTmpRows + 8] byte offset of staged row r
+    int32_t* s_vt = reinterpret_cast<int32_t*>(smem);  // [kS2dVtRows][8]: new source rows, k0..k4 (x4), -, row valid
+    int32_t* s_rowoff = s_vt + kS2dVtRows * 8;         // [kMaxTmpRows + 8] byte offset of staged row r
     uint8_t* s_src = reinterpret_cast<uint8_t*>(s_rowoff + kMaxTmpRows + 8);
 
     pdl_launch_dependents();
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
 #pragma unroll
         for (int c = 0; c < 3; ++c) h0[i][c] = h1[i][c] = 0;
     const int32_t* rowoff = s_rowoff;  // next staged row to enter the ring
-    uint4* optr = reinterpret_cast<uint4*>(out + (((size_t)blockIdx.y * kS2dH + (8 * b + 1)) * kS2dW + X) * kS2dC);
+    uint4* optr = reinterpret_cast<uint4*>(out + (((size_t)blockIdx.y * kS2dH + (ppb * b + 1)) * kS2dW + X) * kS2dC);
     for (int pj = 0; pj < npair; ++pj) {
         unsigned w[6];
 #pragma unroll
@@ -799,7 +803,7 @@ static PreKernel* pre_kernels() {
     return table;
 }
 
-using S2dKernel = void (*)(const uint8_t*, const ImgDev*, __nv_bfloat16*, NormFma);
+using S2dKernel = void (*)(const uint8_t*, const ImgDev*, __nv_bfloat16*, NormFma, int);
 
 // [NTH class 2/4/5][NTV class 2/4/5]
 static S2dKernel* s2d_kernels() {
@@ -809,7 +813,7 @@ static S2dKernel* s2d_kernels() {
     return table;
 }
 
-static int s2d_smem_bytes(int rows, int src_pitch) { return 18 * 8 * 4 + (kMaxTmpRows + 8) * 4 + (rows + kFastTaps) * src_pitch + 16; }
+static int s2d_smem_bytes(int rows, int src_pitch) { return kS2dVtRows * 8 * 4 + (kMaxTmpRows + 8) * 4 + (rows + kFastTaps) * src_pitch + 16; }
 
 int preprocess_init(fx_engine* e) {
     // ToTensor + Normalize as torch computes them (fp32 division by 255, fp32 subtract, fp32
@@ -847,6 +851,10 @@ int preprocess_init(fx_engine* e) {
         FX_CUDA(e, cudaFuncSetAttribute(s2d_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     const char* old = getenv("FX_DEBUG_PRE_BANDED");  // measurement knob: force the banded kernel for the bf16 staging output
     e->pre_force_banded = old && old[0] == '1';
+    // bands of 16 row pairs halve the per-band set-up but leave too few blocks in flight: 39.6 us against 37.2 us at
+    // batch 256 (measured), so 8 is the default; FX_DEBUG_S2D_PPB=16 is the measurement knob
+    const char* ppb = getenv("FX_DEBUG_S2D_PPB");
+    e->s2d_ppb16 = ppb && atoi(ppb) == 16;
     return FX_OK;
 }
 
@@ -882,7 +890,8 @@ static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
         ent.col_hi = g.col_hi;
         ent.cnt_h = g.cnt_h;
         ent.cnt_v = g.cnt_v;
-        ent.s2d_rows = g.s2d_rows;
+        ent.s2d_rows[0] = g.s2d_rows[0];
+        ent.s2d_rows[1] = g.s2d_rows[1];
         ent.noclip = g.noclip;
         FX_CUDA(e, cudaMalloc(&ent.dev, sizeof(int32_t) * g.blob.size()));
         FX_CUDA(e, cudaMemcpy(ent.dev, g.blob.data(), sizeof(int32_t) * g.blob.size(), cudaMemcpyHostToDevice));
@@ -899,7 +908,7 @@ static int preprocess_launch(fx_engine* e, const fx_engine::PrePlan& plan, const
         std::memcpy(nf.a, e->norm_a, sizeof(nf.a));
         std::memcpy(nf.b, e->norm_b, sizeof(nf.b));
         FX_CUDA(e, launch_pdl(s2d_kernels()[plan.kernel], dim3(plan.bands, n), dim3(kS2dThreads), plan.smem, stream, src_dev,
-                              static_cast<const ImgDev*>(e->img_dev), static_cast<__nv_bfloat16*>(out), nf));
+                              static_cast<const ImgDev*>(e->img_dev), static_cast<__nv_bfloat16*>(out), nf, plan.ppb));
         FX_LAUNCH_CHECK(e, "preprocess_s2d_kernel");
         return FX_OK;
     }
@@ -937,7 +946,8 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
     int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
     bool all_s2d = mode == PreOut::IN0_BF16 && !e->pre_force_banded && e->norm_fma_ok;  // every image can take the column-walk kernel
-    int s2d_smem = 0, s2d_nth = 2, s2d_ntv = 2;
+    int s2d_smem = 0, s2d_smem16 = 0, s2d_nth = 2, s2d_ntv = 2;
+    bool s2d_ppb16 = e->s2d_ppb16;
     for (int i = 0; i < n; ++i) {
         const fx_image_desc& d = descs[i];
         if (d.channels != 3 && d.channels != 1)
@@ -968,10 +978,14 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
             nth = std::max(nth, ge->cnt_h);
             ntv = std::max(ntv, ge->cnt_v);
         }
-        const int s2d_need = s2d_smem_bytes(ge->s2d_rows, src_pitch);
-        if (d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->noclip && ge->s2d_rows <= kMaxTmpRows &&
-            s2d_need <= 100 * 1024) {
-            s2d_smem = std::max(s2d_smem, s2d_need);
+        if (d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->noclip && ge->s2d_rows[0] <= kMaxTmpRows &&
+            s2d_smem_bytes(ge->s2d_rows[0], src_pitch) <= 100 * 1024) {
+            s2d_smem = std::max(s2d_smem, s2d_smem_bytes(ge->s2d_rows[0], src_pitch));
+            // (optional) bands of 16 row pairs: only while the staged rows stay small (up-scales)
+            if (ge->s2d_rows[1] <= kMaxTmpRows && s2d_smem_bytes(ge->s2d_rows[1], src_pitch) <= 32 * 1024)
+                s2d_smem16 = std::max(s2d_smem16, s2d_smem_bytes(ge->s2d_rows[1], src_pitch));
+            else
+                s2d_ppb16 = false;
             s2d_nth = std::max(s2d_nth, ge->cnt_h);
             s2d_ntv = std::max(s2d_ntv, ge->cnt_v);
         } else {
@@ -990,8 +1004,9 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     if (all_s2d) {
         const int ih = s2d_nth <= 2 ? 0 : (s2d_nth <= 4 ? 1 : 2), iv = s2d_ntv <= 2 ? 0 : (s2d_ntv <= 4 ? 1 : 2);
         plan.kernel = ih * 3 + iv;
-        plan.smem = s2d_smem;
-        plan.bands = kS2dBands;
+        plan.ppb = s2d_ppb16 ? 16 : 8;
+        plan.smem = s2d_ppb16 ? s2d_smem16 : s2d_smem;
+        plan.bands = kS2dPairs / plan.ppb;
     } else {
         plan.tmp_bytes = (max_tmp + 15) & ~15;
         plan.rowbuf = std::min(kRowBufCap, (max_span + 15) & ~15);
