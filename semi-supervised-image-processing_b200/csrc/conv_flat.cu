@@ -488,6 +488,291 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// flat2: the layer-1 kernel (3x3 / stride 1, Cin = Cout = 64) as a CTA PAIR (cta_group::2).
+//
+// Why: flat_conv_kernel's N = 64 MMAs are bound by the 128 B/clk shared-memory pipe -- every M128 x N64 x K16 MMA
+// fetches 4 KB of A and 2 KB of B.  With one M = 256 MMA per CTA pair each CTA supplies its own 128 A
+// rows (its own work tile) but only HALF of B (32 of the 64 output channels): 5 KB per MMA instead of 6, and only
+// half of the folded weights (36 KB instead of 72 KB) resident per CTA, which buys a third A stage.
+// Protocol (as tc2_conv_kernel): the even CTA of the pair issues every MMA; its `full` / weight barriers count the TMA
+// bytes of both CTAs; `tcgen05.commit` multicasts `empty` / accumulator-ready to both; the epilogue warps of both CTAs
+// arrive on the leader's accumulator-free barriers.  Unit u of a pair = work tiles 2u (leader) and 2u + 1 (peer).
+// Warp roles per CTA: 0 = TMA producer, 1 = MMA issuer (leader only), 2 = TMEM allocator, 3 = bias, 4..11 = epilogue.
+// ------------------------------------------------------------------------------------------
+constexpr int kFlat2Threads = 384;
+
+struct Flat2Params {
+    int P, W, H, R, tiles_per_img, n_work, batch, cout;
+    int nstages, stage_bytes, box_bytes, slack_bytes;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    int relu;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlat2Threads, 1)
+flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Flat2Params p) {
+    constexpr int TAPS = 9, KW = 3, ROWB = 128, KSTEPS = 4;
+    constexpr int WTILE = 32 * ROWB;  // one tap's weights of THIS CTA's 32 output channels
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sW = sbase;
+    const uint32_t sA = sbase + TAPS * WTILE;
+    const uint32_t stage0 = sA + p.nstages * p.stage_bytes + p.slack_bytes;  // epilogue staging: 8 warps x 4 KB
+    const uint32_t bias0 = stage0 + 8 * 4096;
+    const uint32_t bars = bias0 + 256;
+    const uint32_t full0 = bars, empty0 = full0 + 8 * p.nstages, tfull0 = empty0 + 8 * p.nstages;
+    const uint32_t tempty0 = tfull0 + 8 * kFlatSlots, wbar = tempty0 + 8 * kFlatSlots, tslot = wbar + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_units = (p.n_work + 1) >> 1;
+    const int u_first = (int)((long long)n_units * pair / n_pairs), u_last = (int)((long long)n_units * (pair + 1) / n_pairs);
+    const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;  // every tile is issued at full height (rows past H are zero fill)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.nstages; ++i) {
+            mbar_init(full0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
+            mbar_init(empty0 + 8 * i, 1);  // multicast commit
+        }
+        for (int i = 0; i < kFlatSlots; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);     // multicast commit
+            mbar_init(tempty0 + 8 * i, 256);  // one epilogue group (128 threads) of each CTA
+        }
+        mbar_init(wbar, 2);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tslot, 512);
+    if (warp == 3) {
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        bs[lane] = __ldg(p.bias + lane);
+        bs[lane + 32] = __ldg(p.bias + lane + 32);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    // this CTA's half of the folded weights is constant data: fetch it before waiting for the previous kernel (PDL)
+    if (warp == 0 && elect_one_sync()) {
+        if (leader) mbar_expect_tx(wbar, 2 * TAPS * WTILE);
+        for (int tap = 0; tap < TAPS; ++tap) tma_load_2d_2cta(sW + tap * WTILE, &map_b, wbar, tap * 64, (int)rank * 32);
+        if (!leader) mbar_arrive_leader(wbar);
+    }
+    __syncwarp();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): the halo box of this CTA's tile of the unit =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int u = u_first; u < u_last; ++u) {
+                const int w = 2 * u + (int)rank;
+                const int img = w < p.n_work ? w / p.tiles_per_img : p.batch;  // the odd leftover: out of bounds -> zeros
+                const int y0 = w < p.n_work ? (w - img * p.tiles_per_img) * p.R : 0;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * p.box_bytes);
+                tma_load_4d_2cta(sA + stage * p.stage_bytes, &map_a, full0 + 8 * stage, 0, -1, y0 - 1, img);
+                if (!leader) mbar_arrive_leader(full0 + 8 * stage);
+                if (++stage == (uint32_t)p.nstages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only): M = 256 (both CTAs' tiles), N = 64 =====
+        if (leader) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            constexpr uint64_t desc_hi = make_smem_desc_rowb<ROWB>(0) & 0xFFFFFFFF00000000ull;
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, g_base = 0;
+            const uint32_t w_lo = sW >> 4;
+            const uint32_t row_units = ROWB / 16;
+            for (int u = u_first; u < u_last; ++u) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_lo_stage = (sA + stage * p.stage_bytes) >> 4;
+                for (int mt = 0; mt < n_mt; mt += 2) {
+                    const bool two = mt + 1 < n_mt;
+                    const uint32_t g0 = g_base + mt, slot0 = g0 & (kFlatSlots - 1), use0 = g0 / kFlatSlots;
+                    const uint32_t g1 = g0 + 1, slot1 = g1 & (kFlatSlots - 1), use1 = g1 / kFlatSlots;
+                    mbar_wait(tempty0 + 8 * slot0, (use0 & 1) ^ 1);
+                    if (two) mbar_wait(tempty0 + 8 * slot1, (use1 & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t d0 = tmem_base + slot0 * 64, d1 = tmem_base + slot1 * 64;
+                        const uint32_t a_lo_mt = a_lo_stage + (uint32_t)(mt * 128) * row_units;
+#pragma unroll
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            const uint32_t a_lo = a_lo_mt + (uint32_t)((tap / KW) * p.P + (tap % KW)) * row_units;
+                            const uint32_t b_lo = w_lo + (uint32_t)tap * (WTILE / 16);
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k)
+                                umma_bf16_2cta(d0, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (tap | k) != 0);
+                            if (two) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; ++k)
+                                    umma_bf16_2cta(d1, desc_hi | (uint64_t)(a_lo + 128 * row_units + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k),
+                                                   idesc, (tap | k) != 0);
+                            }
+                        }
+                        umma_commit_2cta(tfull0 + 8 * slot0);
+                        if (two) umma_commit_2cta(tfull0 + 8 * slot1);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one_sync()) umma_commit_2cta(empty0 + 8 * stage);
+                __syncwarp();
+                if (++stage == (uint32_t)p.nstages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                g_base += n_mt;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): as flat_conv_kernel, on this CTA's tile of every unit =====
+        const int q = warp & 3;
+        const int grp = (warp - 4) >> 2;
+        const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        const int rr0 = lane >> 3, ch = lane & 7;
+        const bool has_res = p.residual != nullptr;
+
+        int u = u_first, mt = 0, img = 0, y0 = 0, rows_valid = 0;
+        uint32_t g = 0;
+        auto tile_setup = [&]() {
+            const int w = 2 * u + (int)rank;
+            if (w < p.n_work) {
+                img = w / p.tiles_per_img;
+                y0 = (w - img * p.tiles_per_img) * p.R;
+                rows_valid = min(p.R, p.H - y0);
+            } else {
+                rows_valid = 0;  // the odd leftover: nothing to store
+            }
+        };
+        auto advance = [&]() {
+            ++g;
+            if (++mt == n_mt) {
+                mt = 0;
+                if (++u >= u_last) return false;
+                tile_setup();
+            }
+            return true;
+        };
+        auto my_pix = [&]() {
+            const int m = mt * 128 + q * 32 + lane;
+            const int i = m / p.P, x = m - i * p.P;
+            return (x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+        };
+        auto prefetch_res = [&](int pix) {
+            if (has_res) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rr0;
+                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                    if (pr >= 0) cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + ch * 8);
+                }
+            }
+            cp_async_commit();
+        };
+
+        bool live = u < u_last;
+        if (live) {
+            tile_setup();
+            if (grp == 1) live = advance();
+        }
+        int pix = live ? my_pix() : -1;
+        if (live) prefetch_res(pix);
+        while (live) {
+            const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
+            cp_async_wait_all();
+            __syncwarp();
+            mbar_wait(tfull0 + 8 * slot, use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + slot * 64 + ((uint32_t)(q * 32) << 16);
+            const uint32_t srow = stg + lane * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
+                tmem_ld_wait();
+                if (h == 1) {
+                    tc_fence_before();
+                    mbar_arrive_leader(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back to the leader
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
+                    float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                  __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                  __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                  __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                    if (has_res && pix >= 0) {
+                        const uint4 rv = lds128(sa);
+                        const unsigned uu[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            f[2 * k] += __uint_as_float(uu[k] << 16);
+                            f[2 * k + 1] += __uint_as_float(uu[k] & 0xffff0000u);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                    }
+                    uint4 o;
+                    unsigned* ou = &o.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                        ou[k] = *reinterpret_cast<const unsigned*>(&h2);
+                    }
+                    sts128(sa, o);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rr0;
+                const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                if (pr >= 0) {
+                    const uint4 val = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    *reinterpret_cast<uint4*>(p.out + (size_t)pr * p.cout + ch * 8) = val;
+                }
+            }
+            __syncwarp();
+            live = advance();
+            if (live) live = advance();
+            if (live) {
+                pix = my_pix();
+                prefetch_res(pix);
+            }
+        }
+        cp_async_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory / barriers stay alive until both CTAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // flat128: the same halo-tile / shifted-view A operand, but 128 output channels per MMA (N=128 issues at
 // the tensor floor, 64 cycles, where two N=64 MMAs cost 96) and the weights STREAMED per (tap, chunk)
 // K-block through a ring, because a 128-channel slice of a 3x3x128 filter bank (288 KB) does not fit in
@@ -846,6 +1131,72 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     return FX_OK;
 }
 
+// Layer 1 on CTA pairs (flat2_conv_kernel): measured 78 -> 62 us per launch for the convs WITHOUT a residual (batch 256);
+// the ones with a residual are HBM-bound at ~3.5 TB/s either way and stay on flat_conv_kernel (85 vs 87 us).
+// FX_FLAT2 = 0 disables it, = 2 also routes the residual convs through it (measurement knob).
+static int flat2_mode() {
+    static const int mode = [] {
+        const char* v = getenv("FX_FLAT2");
+        return v ? atoi(v) : 1;
+    }();
+    return mode;
+}
+
+static int flat2_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                      int n, int relu, cudaStream_t stream) {
+    const LayerGeom& g = L.g;
+    Flat2Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.bias = L.bias;
+    p.residual = residual;
+    p.out = out;
+    p.relu = relu;
+    p.cout = g.cout;
+    p.batch = n;
+    p.W = g.wout;
+    p.H = g.hout;
+    p.P = g.win + 2;
+    p.R = std::max(1, std::min(g.hout, 256 / p.P));
+    p.tiles_per_img = (p.H + p.R - 1) / p.R;
+    p.n_work = n * p.tiles_per_img;
+    p.box_bytes = (p.R + 2) * p.P * 128;
+    p.stage_bytes = (p.box_bytes + 1023) & ~1023;
+    const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
+    const int reach_rows = n_mt * 128 + 2 * p.P + 2;
+    p.slack_bytes = (std::max(0, reach_rows * 128 - p.stage_bytes) + 1023) & ~1023;
+    const int bar_bytes = 8 * (2 * 8 + 2 * kFlatSlots + 2) + 64;
+    const int fixed = 1024 + 9 * 32 * 128 + p.slack_bytes + kEpiBytes + bar_bytes;
+    p.nstages = std::min(4, (kSmemMax - fixed) / p.stage_bytes);
+    if (p.nstages < 2 || n_mt > kFlatSlots) return set_error(e, FX_ERR_UNSUPPORTED, "flat2_conv: tile does not fit");
+    const int smem = fixed + p.nstages * p.stage_bytes;
+    CUtensorMap ma, mb;
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.P, (uint32_t)(p.R + 2), 1};
+    int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat2 A");
+    if (rc != FX_OK) return rc;
+    const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+    const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+    const uint32_t bbox[2] = {64, 32};  // one tap's K-block of HALF of the output channels
+    rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat2 B");
+    if (rc != FX_OK) return rc;
+    static bool attr_done[16] = {};
+    if (!attr_done[e->device & 15]) {
+        FX_CUDA(e, cudaFuncSetAttribute(flat2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_done[e->device & 15] = true;
+    }
+    const int n_units = (p.n_work + 1) / 2;
+    const int pairs = std::max(1, std::min(e->sm_count / 2, n_units));
+    FX_CUDA(e, launch_pdl(flat2_conv_kernel, dim3(2 * pairs), dim3(kFlat2Threads), smem, stream, ma, mb, p));  // cluster dims are a kernel attribute
+    FX_LAUNCH_CHECK(e, "flat2_conv_kernel");
+    return FX_OK;
+}
+
+static bool flat2_supported(const LayerGeom& g, bool has_residual) {
+    return flat2_mode() >= (has_residual ? 2 : 1) && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin == 64 && g.cout == 64 && g.win + 2 <= 128 && g.win >= 8;
+}
+
 static bool flat128_supported(const LayerGeom& g) {
     return g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin % 64 == 0 && g.cout % 128 == 0 && g.win + 2 <= 64 &&
            g.win >= 16;
@@ -909,6 +1260,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     }
     if (pool) return set_error(e, FX_ERR_INVALID, "flat_conv: only the stem has a fused max-pool");
     if (flat128_supported(g)) return flat128_conv(e, L, in, residual, out, n, relu, stream);
+    if (flat2_supported(g, residual != nullptr)) return flat2_conv(e, L, in, residual, out, n, relu, stream);
     p.P = g.win + 2;
     p.chunks = g.cin / 64;
     p.x0 = -1;
