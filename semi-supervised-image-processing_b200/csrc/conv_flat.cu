@@ -785,7 +785,7 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 constexpr int kFlat128Threads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps
 
 struct Flat128Params {
-    int P, W, H, R, tiles_per_img, n_work, chunks, ns, cout;
+    int P, W, H, R, tiles_per_img, n_work, chunks, ns, cout, batch;
     int a_stages, a_stage_bytes, a_box_bytes, b_stages, slack_bytes;
     const float* bias;
     const __nv_bfloat16* residual;
@@ -1041,6 +1041,271 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
+// flat128x2: flat128_conv_kernel as a CTA PAIR (cta_group::2), as flat2_conv_kernel is to flat_conv_kernel: one
+// M = 256 x N = 128 MMA per pair; each CTA brings its own work tile (A) and HALF of every weight K-block (64 of the
+// 128 output channels of the slice).  Per MMA and CTA 4 KB of A + 2 KB of B leave the shared-memory pipe (the math
+// takes 64 cycles, the single-CTA form's 8 KB took 64 cycles of fetch), and the streamed weights -- the larger part
+// of this kernel's L2 -> SM traffic, 288 KB per work tile -- are halved.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlat128Threads, 1)
+flat128x2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Flat128Params p) {
+    constexpr int TAPS = 9, KW = 3, ROWB = 128, KSTEPS = 4;
+    constexpr int BTILE = 64 * ROWB;  // THIS CTA's half of a weight K-block: 64 of the 128 cout rows x 64 k
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sB = sbase;
+    const uint32_t sA = sB + p.b_stages * BTILE;
+    const uint32_t stage0 = sA + p.a_stages * p.a_stage_bytes + p.slack_bytes;  // 16 epilogue warps x 4 KB
+    const uint32_t bias0 = stage0 + 16 * 4096;                                 // 128 fp32
+    const uint32_t bars = bias0 + 512;
+    const uint32_t afull0 = bars, aempty0 = afull0 + 8 * p.a_stages;
+    const uint32_t bfull0 = aempty0 + 8 * p.a_stages, bempty0 = bfull0 + 8 * p.b_stages;
+    const uint32_t tfull0 = bempty0 + 8 * p.b_stages, tempty0 = tfull0 + 16, tslot = tempty0 + 16;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int nslice = pair % p.ns;
+    // contiguous run of UNITS per pair; unit u = (image pair j = u / tiles_per_img, tile t = u % tiles_per_img): the leader
+    // CTA works on tile t of image 2j, the peer on tile t of image 2j + 1 -- both tiles have the same height, so the
+    // short last tile of an image (one M-tile instead of two) stays short for the whole M = 256 MMA
+    const int n_pair = (gridDim.x >> 1) / p.ns, pidx = pair / p.ns;
+    const int n_units = ((p.batch + 1) >> 1) * p.tiles_per_img;
+    const int w_first = (int)((long long)n_units * pidx / n_pair), w_last = (int)((long long)n_units * (pidx + 1) / n_pair);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.a_stages; ++i) {
+            mbar_init(afull0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
+            mbar_init(aempty0 + 8 * i, 1);  // multicast commit
+        }
+        for (int i = 0; i < p.b_stages; ++i) {
+            mbar_init(bfull0 + 8 * i, 2);
+            mbar_init(bempty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);        // multicast commit
+            mbar_init(tempty0 + 8 * i, 2 * 512);  // the 16 epilogue warps of both CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tslot, 512);
+    if (warp == 3) {
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        for (int i = lane; i < 128; i += 32) bs[i] = __ldg(p.bias + nslice * 128 + i);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== A producer: one halo box per (tile, chunk) =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int u = w_first; u < w_last; ++u) {
+                const int j = u / p.tiles_per_img;
+                const int img = 2 * j + (int)rank;  // == batch for the odd leftover: out of bounds -> zeros
+                const int y0 = (u - j * p.tiles_per_img) * p.R;
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(aempty0 + 8 * stage, phase ^ 1);
+                    if (leader) mbar_expect_tx(afull0 + 8 * stage, 2 * p.a_box_bytes);
+                    tma_load_4d_2cta(sA + stage * p.a_stage_bytes, &map_a, afull0 + 8 * stage, c * 64, -1, y0 - 1, img);
+                    if (!leader) mbar_arrive_leader(afull0 + 8 * stage);
+                    if (++stage == (uint32_t)p.a_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===== B producer: the weight K-blocks in the order the MMA warp consumes them =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int u = w_first; u < w_last; ++u)
+                for (int c = 0; c < p.chunks; ++c)
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        mbar_wait(bempty0 + 8 * stage, phase ^ 1);
+                        if (leader) mbar_expect_tx(bfull0 + 8 * stage, 2 * BTILE);
+                        tma_load_2d_2cta(sB + stage * BTILE, &map_b, bfull0 + 8 * stage, (tap * p.chunks + c) * 64, nslice * 128 + (int)rank * 64);
+                        if (!leader) mbar_arrive_leader(bfull0 + 8 * stage);
+                        if (++stage == (uint32_t)p.b_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+        }
+    } else if (warp == 1 && leader) {
+        // ===== MMA issuer (leader CTA only): M = 256 (both CTAs' tiles), N = 128 =====
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        constexpr uint64_t desc_hi = make_smem_desc_rowb<ROWB>(0) & 0xFFFFFFFF00000000ull;
+        uint32_t astage = 0, aphase = 0, bstage = 0, bphase = 0;
+        int it = 0;
+        for (int u = w_first; u < w_last; ++u, ++it) {
+            const int y0 = (u % p.tiles_per_img) * p.R;
+            const int rows_valid = min(p.R, p.H - y0);
+            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+            const uint32_t set = it & 1, sphase = (it >> 1) & 1;
+            mbar_wait(tempty0 + 8 * set, sphase ^ 1);
+            tc_fence_after();
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(afull0 + 8 * astage, aphase);
+                tc_fence_after();
+                const uint32_t a_lo_stage = (sA + astage * p.a_stage_bytes) >> 4;
+                const uint32_t d0 = tmem_base + set * 256;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    mbar_wait(bfull0 + 8 * bstage, bphase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t b_lo = (sB + bstage * BTILE) >> 4;
+                        const uint32_t a_lo = a_lo_stage + (uint32_t)((tap / KW) * p.P + (tap % KW)) * (ROWB / 16);
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                            umma_bf16_2cta(d0, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (c | tap | k) != 0);
+                        if (n_mt > 1) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k)
+                                umma_bf16_2cta(d0 + 128, desc_hi | (uint64_t)(a_lo + 128 * (ROWB / 16) + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                                               (c | tap | k) != 0);
+                        }
+                        umma_commit_2cta(bempty0 + 8 * bstage);
+                    }
+                    __syncwarp();
+                    if (++bstage == (uint32_t)p.b_stages) {
+                        bstage = 0;
+                        bphase ^= 1;
+                    }
+                }
+                if (elect_one_sync()) {
+                    umma_commit_2cta(aempty0 + 8 * astage);
+                    if (c == p.chunks - 1) umma_commit_2cta(tfull0 + 8 * set);
+                }
+                __syncwarp();
+                if (++astage == (uint32_t)p.a_stages) {
+                    astage = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int q = warp & 3;
+        const int mt = ((warp - 4) >> 2) & 1;  // which M-tile of the work tile this warp handles
+        const int pass = (warp - 4) >> 3;      // which 64 of the 128 output channels
+        const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        const int cbase = nslice * 128;
+        const int rr0 = lane >> 3, ch = lane & 7;
+        const bool has_res = p.residual != nullptr;
+        int it = 0;
+        for (int u = w_first; u < w_last; ++u, ++it) {
+            const int j = u / p.tiles_per_img;
+            const int img = 2 * j + (int)rank;
+            const int y0 = (u - j * p.tiles_per_img) * p.R;
+            const int rows_valid = min(p.R, p.H - y0);
+            const int n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+            const bool real = img < p.batch;  // the odd leftover image stores nothing
+            const uint32_t set = it & 1, sphase = (it >> 1) & 1;
+            const int m = mt * 128 + q * 32 + lane;
+            const int i = m / p.P, x = m - i * p.P;
+            const int pix = (real && mt < n_mt && x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+            mbar_wait(tfull0 + 8 * set, sphase);
+            tc_fence_after();
+            if (mt >= n_mt) {  // nothing of ours in this (short) tile
+                tc_fence_before();
+                mbar_arrive_leader(tempty0 + 8 * set);
+                continue;
+            }
+            const uint32_t taddr = tmem_base + set * 256 + mt * 128 + ((uint32_t)(q * 32) << 16);
+            const uint32_t srow = stg + lane * 128;
+            {
+                if (has_res) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int rr = t * 4 + rr0;
+                        const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                        if (pr >= 0)
+                            cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
+                    }
+                    cp_async_commit();
+                    cp_async_wait_all();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + pass * 64 + h * 32, v);
+                    tmem_ld_wait();
+                    if (h == 1) {
+                        tc_fence_before();
+                        mbar_arrive_leader(tempty0 + 8 * set);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + pass * 64 + h * 32 + j * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + pass * 64 + h * 32 + j * 8 + 4);
+                        float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                      __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                      __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                      __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                        if (has_res && pix >= 0) {
+                            const uint4 rv = lds128(sa);
+                            const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                f[2 * k] += __uint_as_float(u[k] << 16);
+                                f[2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                        }
+                        uint4 o;
+                        unsigned* ou = &o.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                            ou[k] = *reinterpret_cast<const unsigned*>(&h2);
+                        }
+                        sts128(sa, o);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = t * 4 + rr0;
+                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                    if (pr >= 0) {
+                        const uint4 val = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                        *reinterpret_cast<uint4*>(p.out + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8) = val;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory / barriers stay alive until both CTAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemMax = 227 * 1024;
@@ -1079,6 +1344,15 @@ static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& m
     return FX_OK;
 }
 
+// flat128 on CTA pairs (flat128x2_conv_kernel); FX_FLAT128X2=0 keeps the single-CTA kernel.
+static bool flat128x2_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("FX_FLAT128X2");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
 static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                         int n, int relu, cudaStream_t stream) {
     const LayerGeom& g = L.g;
@@ -1103,9 +1377,12 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     p.slack_bytes = (std::max(0, reach_rows * 128 - p.a_stage_bytes) + 1023) & ~1023;
     p.a_stages = 2;  // chunk granularity: the next tile's chunk c loads as soon as this tile's chunk c is consumed
     const int fixed = 1024 + p.a_stages * p.a_stage_bytes + p.slack_bytes + 16 * 4096 + 512 + 8 * (2 * 3 + 2 * 8 + 4) + 64;
-    p.b_stages = std::min(6, (kSmemMax - fixed) / (128 * 128));
+    const bool pair = flat128x2_enabled();
+    const int btile = pair ? 64 * 128 : 128 * 128;  // the CTA-pair kernel streams half a weight K-block per CTA
+    p.batch = n;
+    p.b_stages = std::min(pair ? 10 : 6, (kSmemMax - fixed) / btile);
     if (p.b_stages < 2) return set_error(e, FX_ERR_UNSUPPORTED, "flat128_conv: tile does not fit in shared memory");
-    const int smem = fixed + p.b_stages * 128 * 128;
+    const int smem = fixed + p.b_stages * btile;
     CUtensorMap ma, mb;
     const uint32_t ones[4] = {1, 1, 1, 1};
     const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
@@ -1115,13 +1392,23 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     if (rc != FX_OK) return rc;
     const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
     const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
-    const uint32_t bbox[2] = {64, 128};
+    const uint32_t bbox[2] = {64, (uint32_t)(pair ? 64 : 128)};
     rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat128 B");
     if (rc != FX_OK) return rc;
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
         FX_CUDA(e, cudaFuncSetAttribute(flat128_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        FX_CUDA(e, cudaFuncSetAttribute(flat128x2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_done[e->device & 15] = true;
+    }
+    if (pair) {
+        const int n_units = ((n + 1) / 2) * p.tiles_per_img;
+        int pairs = std::min(e->sm_count / 2, n_units * p.ns);
+        pairs -= pairs % p.ns;
+        if (pairs < p.ns) pairs = p.ns;
+        FX_CUDA(e, launch_pdl(flat128x2_conv_kernel, dim3(2 * pairs), dim3(kFlat128Threads), smem, stream, ma, mb, p));  // cluster dims are a kernel attribute
+        FX_LAUNCH_CHECK(e, "flat128x2_conv_kernel");
+        return FX_OK;
     }
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
