@@ -42,6 +42,7 @@ struct FlatParams {
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     int relu;
+    int sched;             // tile walk: bit 0 = descending, bit 1 = strided over the CTAs (see TileWalk)
 };
 
 constexpr int kFlatThreads = 384;
@@ -69,6 +70,14 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// Read-once global data (no L1 allocation).  Deliberately unpredicated: behind a predicated load -- a `live ? load : 0`
+// select, or a guarded in/out asm operand -- ptxas copies the value out of a scratch register at once, i.e. waits for
+// the load right there, which defeats a prefetch.  Callers clamp the address instead.
+__device__ __forceinline__ uint4 ldg_stream128(const void* gptr) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(gptr));
+    return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
@@ -77,6 +86,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+
+// Which work items a CTA (or CTA pair) processes, and in which order.  The activations of the stem and of layer 1 at
+// batch 256 (103 MB per tensor) do not fit in L2 next to the tensors written meanwhile, so a kernel that walks its
+// input in the order the previous kernel wrote it finds nothing of it in L2 (LRU: the oldest lines went first).
+// Consecutive launches therefore walk in OPPOSITE directions: what the previous kernel touched last is read first.
+//   sched bit 1 clear: a contiguous run of items per CTA (item = begin + i);   set: items strided over the CTAs, so
+//   that the whole grid sweeps the tensor front to back in time;   bit 0: the same items in descending order.
+struct TileWalk {
+    int begin, step, count;
+    __device__ __forceinline__ TileWalk(int n_items, int cta, int n_cta, int sched) {
+        if (sched & 2) {
+            count = cta < n_items ? (n_items - cta + n_cta - 1) / n_cta : 0;
+            begin = (sched & 1) ? n_items - 1 - cta : cta;
+            step = (sched & 1) ? -n_cta : n_cta;
+        } else {
+            const int first = (int)((long long)n_items * cta / n_cta), last = (int)((long long)n_items * (cta + 1) / n_cta);
+            count = last - first;
+            begin = (sched & 1) ? last - 1 : first;
+            step = (sched & 1) ? -1 : 1;
+        }
+    }
+};
 
 // POOL (stem only): the epilogue keeps the ReLU'd conv rows of the tile in a shared-memory ring and
 // writes the 3x3 / stride-2 / pad-1 max-pooled rows (torchvision/models/resnet.py:200) instead of the
@@ -104,7 +135,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int nslice = blockIdx.x % p.ns;
     // contiguous run of work tiles per CTA (balances the short last tile of each image, keeps halo rows in L2)
     const int n_cta = gridDim.x / p.ns, cta = blockIdx.x / p.ns;
-    const int w_first = (int)((long long)p.n_work * cta / n_cta), w_last = (int)((long long)p.n_work * (cta + 1) / n_cta);
+    const TileWalk walk(p.n_work, cta, n_cta, p.sched);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -147,7 +178,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===== TMA producer: one halo box per (tile, chunk) =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int w = w_first; w < w_last; ++w) {
+            for (int wi = 0, w = walk.begin; wi < walk.count; ++wi, w += walk.step) {
                 const int img = w / p.tiles_per_img;
                 const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
                 for (int c = 0; c < p.chunks; ++c) {
@@ -170,7 +201,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t stage = 0, phase = 0, g_base = 0;
         const uint32_t w_lo = sW >> 4;
         const uint32_t row_units = ROWB / 16;  // descriptor address units (16 B) per smem row
-        for (int w = w_first; w < w_last; ++w) {
+        for (int wi = 0, w = walk.begin; wi < walk.count; ++wi, w += walk.step) {
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             const int rows_valid = min(p.R, p.H - y0);
@@ -241,7 +272,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
         uint32_t g = 0;
         int tile_idx = 0;
-        for (int w = w_first; w < w_last; ++w, ++tile_idx) {
+        for (int w = walk.begin; tile_idx < walk.count; w += walk.step, ++tile_idx) {
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             for (int mt = 0; mt < n_mt; ++mt, ++g) {
@@ -304,7 +335,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;
         uint32_t g = 0;
         int tile_idx = 0;
-        for (int w = w_first; w < w_last; ++w, ++tile_idx) {
+        for (int w = walk.begin; tile_idx < walk.count; w += walk.step, ++tile_idx) {
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
             int jnext = 0;
@@ -365,52 +396,66 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const bool has_res = p.residual != nullptr;
 
         // this group's M-tile sequence
-        int w = w_first, mt = 0, n_mt = 0, img = 0, y0 = 0, rows_valid = 0;
-        uint32_t g = 0;
-        auto tile_setup = [&]() {
-            img = w / p.tiles_per_img;
-            y0 = (w - img * p.tiles_per_img) * p.rstep + p.yfirst;
-            rows_valid = min(p.R, p.H - y0);
-            n_mt = ((rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+        struct Cursor {
+            int w, wi, mt, n_mt, img, y0, rows_valid;
+            uint32_t g;
         };
-        auto advance = [&]() {  // next M-tile in schedule order; returns false at the end
-            ++g;
-            if (++mt == n_mt) {
-                mt = 0;
-                ++w;
-                if (w >= w_last) return false;
-                tile_setup();
+        auto tile_setup = [&](Cursor& c) {
+            c.img = c.w / p.tiles_per_img;
+            c.y0 = (c.w - c.img * p.tiles_per_img) * p.rstep + p.yfirst;
+            c.rows_valid = min(p.R, p.H - c.y0);
+            c.n_mt = ((c.rows_valid - 1) * p.P + p.W - 1) / 128 + 1;
+        };
+        auto advance = [&](Cursor& c) {  // next M-tile in schedule order; returns false at the end
+            ++c.g;
+            if (++c.mt == c.n_mt) {
+                c.mt = 0;
+                c.w += walk.step;
+                if (++c.wi >= walk.count) return false;
+                tile_setup(c);
             }
             return true;
         };
-        auto my_pix = [&]() {  // output pixel index of this lane's accumulator row, or -1
-            const int m = mt * 128 + q * 32 + lane;
+        auto pix_of = [&](const Cursor& c) {  // output pixel index of this lane's accumulator row, or -1
+            const int m = c.mt * 128 + q * 32 + lane;
             const int i = m / p.P, x = m - i * p.P;
-            return (x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+            return (x < p.W && i < c.rows_valid) ? ((c.img * p.H + c.y0 + i) * p.W + x) : -1;
         };
-        auto prefetch_res = [&](int pix) {
-            if (has_res) {
+        // The residual of the group's NEXT M-tile is fetched into registers (coalesced: 8 lanes x 16 B per pixel row)
+        // BEFORE the current tile is processed and moved to the staging block when that tile's store-out is done: a whole
+        // tile period hides the load (a cp.async into the staging block could only start after the store-out and was
+        // waited for at once: the epilogue, not the tensor pipe, then paced the convs with a residual).
+        uint4 rres[8];
+        auto load_res = [&](int px) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + rr0;
-                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                    if (pr >= 0)
-                        cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + ch * 8);
-                }
+            for (int it = 0; it < 8; ++it) {
+                const int pr = __shfl_sync(0xffffffffu, px, it * 4 + rr0);
+                rres[it] = ldg_stream128(p.residual + (size_t)max(pr, 0) * p.cout + cbase + ch * 8);  // junk rows read pixel 0, unused
             }
-            cp_async_commit();
+        };
+        auto stash_res = [&]() {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rr0;
+                sts128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), rres[it]);
+            }
         };
 
-        bool live = w < w_last;
+        Cursor cur;
+        cur.w = walk.begin, cur.wi = 0, cur.mt = 0, cur.g = 0;
+        bool live = walk.count > 0;
         if (live) {
-            tile_setup();
-            if (grp == 1) live = advance();
+            tile_setup(cur);
+            if (grp == 1) live = advance(cur);
         }
-        int pix = live ? my_pix() : -1;
-        if (live) prefetch_res(pix);
+        int pix = live ? pix_of(cur) : -1;
+        if (live && has_res) load_res(pix);
         while (live) {
-            const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
-            cp_async_wait_all();
+            Cursor nxt = cur;
+            const bool nlive = advance(nxt) && advance(nxt);
+            const int npix = nlive ? pix_of(nxt) : -1;
+            if (has_res) stash_res();
+            const uint32_t slot = cur.g & (kFlatSlots - 1), use = cur.g / kFlatSlots;
             __syncwarp();
             mbar_wait(tfull0 + 8 * slot, use & 1);
             tc_fence_after();
@@ -421,6 +466,9 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 uint32_t v[32];
                 tmem_ld32(taddr + h * 32, v);
                 tmem_ld_wait();
+                // issued here, while v[] occupies the registers the TMEM load needs: ptxas then loads straight into rres
+                // (issued before the TMEM load it used scratch registers and copied -- waited -- at once)
+                if (h == 0 && has_res && nlive) load_res(npix);
                 if (h == 1) {
                     tc_fence_before();
                     mbar_arrive(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back
@@ -469,14 +517,10 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
             __syncwarp();
-            live = advance();
-            if (live) live = advance();
-            if (live) {
-                pix = my_pix();
-                prefetch_res(pix);
-            }
+            cur = nxt;
+            live = nlive;
+            pix = npix;
         }
-        cp_async_wait_all();
     }
 
     tc_fence_before();
@@ -508,6 +552,7 @@ struct Flat2Params {
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     int relu;
+    int sched;  // tile walk over the pair's units (TileWalk)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlat2Threads, 1)
@@ -531,7 +576,7 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int n_units = (p.n_work + 1) >> 1;
-    const int u_first = (int)((long long)n_units * pair / n_pairs), u_last = (int)((long long)n_units * (pair + 1) / n_pairs);
+    const TileWalk walk(n_units, pair, n_pairs, p.sched);
     const int n_mt = ((p.R - 1) * p.P + p.W - 1) / 128 + 1;  // every tile is issued at full height (rows past H are zero fill)
 
     if (warp == 0 && lane == 0) {
@@ -574,7 +619,7 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer (both CTAs): the halo box of this CTA's tile of the unit =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int u = u_first; u < u_last; ++u) {
+            for (int ui = 0, u = walk.begin; ui < walk.count; ++ui, u += walk.step) {
                 const int w = 2 * u + (int)rank;
                 const int img = w < p.n_work ? w / p.tiles_per_img : p.batch;  // the odd leftover: out of bounds -> zeros
                 const int y0 = w < p.n_work ? (w - img * p.tiles_per_img) * p.R : 0;
@@ -598,7 +643,7 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             uint32_t stage = 0, phase = 0, g_base = 0;
             const uint32_t w_lo = sW >> 4;
             const uint32_t row_units = ROWB / 16;
-            for (int u = u_first; u < u_last; ++u) {
+            for (int ui = 0, u = walk.begin; ui < walk.count; ++ui, u += walk.step) {
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t a_lo_stage = (sA + stage * p.stage_bytes) >> 4;
@@ -649,54 +694,67 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int rr0 = lane >> 3, ch = lane & 7;
         const bool has_res = p.residual != nullptr;
 
-        int u = u_first, mt = 0, img = 0, y0 = 0, rows_valid = 0;
-        uint32_t g = 0;
-        auto tile_setup = [&]() {
-            const int w = 2 * u + (int)rank;
+        struct Cursor {
+            int u, ui, mt, img, y0, rows_valid;
+            uint32_t g;
+        };
+        auto tile_setup = [&](Cursor& c) {
+            const int w = 2 * c.u + (int)rank;
             if (w < p.n_work) {
-                img = w / p.tiles_per_img;
-                y0 = (w - img * p.tiles_per_img) * p.R;
-                rows_valid = min(p.R, p.H - y0);
+                c.img = w / p.tiles_per_img;
+                c.y0 = (w - c.img * p.tiles_per_img) * p.R;
+                c.rows_valid = min(p.R, p.H - c.y0);
             } else {
-                rows_valid = 0;  // the odd leftover: nothing to store
+                c.rows_valid = 0;  // the odd leftover: nothing to store
             }
         };
-        auto advance = [&]() {
-            ++g;
-            if (++mt == n_mt) {
-                mt = 0;
-                if (++u >= u_last) return false;
-                tile_setup();
+        auto advance = [&](Cursor& c) {
+            ++c.g;
+            if (++c.mt == n_mt) {
+                c.mt = 0;
+                c.u += walk.step;
+                if (++c.ui >= walk.count) return false;
+                tile_setup(c);
             }
             return true;
         };
-        auto my_pix = [&]() {
-            const int m = mt * 128 + q * 32 + lane;
+        auto pix_of = [&](const Cursor& c) {
+            const int m = c.mt * 128 + q * 32 + lane;
             const int i = m / p.P, x = m - i * p.P;
-            return (x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+            return (x < p.W && i < c.rows_valid) ? ((c.img * p.H + c.y0 + i) * p.W + x) : -1;
         };
-        auto prefetch_res = [&](int pix) {
-            if (has_res) {
+        // residual of the group's next M-tile: registers first, staging block after this tile's store-out (flat_conv_kernel)
+        uint4 rres[8];
+        auto load_res = [&](int px) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + rr0;
-                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                    if (pr >= 0) cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + ch * 8);
-                }
+            for (int it = 0; it < 8; ++it) {
+                const int pr = __shfl_sync(0xffffffffu, px, it * 4 + rr0);
+                rres[it] = ldg_stream128(p.residual + (size_t)max(pr, 0) * p.cout + ch * 8);  // junk rows read pixel 0, unused
             }
-            cp_async_commit();
+        };
+        auto stash_res = [&]() {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rr0;
+                sts128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), rres[it]);
+            }
         };
 
-        bool live = u < u_last;
+        Cursor cur;
+        cur.u = walk.begin, cur.ui = 0, cur.mt = 0, cur.img = 0, cur.y0 = 0, cur.rows_valid = 0, cur.g = 0;
+        bool live = walk.count > 0;
         if (live) {
-            tile_setup();
-            if (grp == 1) live = advance();
+            tile_setup(cur);
+            if (grp == 1) live = advance(cur);
         }
-        int pix = live ? my_pix() : -1;
-        if (live) prefetch_res(pix);
+        int pix = live ? pix_of(cur) : -1;
+        if (live && has_res) load_res(pix);
         while (live) {
-            const uint32_t slot = g & (kFlatSlots - 1), use = g / kFlatSlots;
-            cp_async_wait_all();
+            Cursor nxt = cur;
+            const bool nlive = advance(nxt) && advance(nxt);
+            const int npix = nlive ? pix_of(nxt) : -1;
+            if (has_res) stash_res();
+            const uint32_t slot = cur.g & (kFlatSlots - 1), use = cur.g / kFlatSlots;
             __syncwarp();
             mbar_wait(tfull0 + 8 * slot, use & 1);
             tc_fence_after();
@@ -707,6 +765,7 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 uint32_t v[32];
                 tmem_ld32(taddr + h * 32, v);
                 tmem_ld_wait();
+                if (h == 0 && has_res && nlive) load_res(npix);  // see flat_conv_kernel
                 if (h == 1) {
                     tc_fence_before();
                     mbar_arrive_leader(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back to the leader
@@ -754,14 +813,10 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
             __syncwarp();
-            live = advance();
-            if (live) live = advance();
-            if (live) {
-                pix = my_pix();
-                prefetch_res(pix);
-            }
+            cur = nxt;
+            live = nlive;
+            pix = npix;
         }
-        cp_async_wait_all();
     }
 
     tc_fence_before();
@@ -1430,10 +1485,11 @@ static int flat2_mode() {
 }
 
 static int flat2_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                      int n, int relu, cudaStream_t stream) {
+                      int n, int relu, cudaStream_t stream, int sched) {
     const LayerGeom& g = L.g;
     Flat2Params p;
     std::memset(&p, 0, sizeof(p));
+    p.sched = sched;
     p.bias = L.bias;
     p.residual = residual;
     p.out = out;
@@ -1498,10 +1554,11 @@ bool flat_supported(const LayerGeom& g) {
 }
 
 int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, int n,
-              int relu, bool pool, cudaStream_t stream) {
+              int relu, bool pool, cudaStream_t stream, int sched) {
     const LayerGeom& g = L.g;
     FlatParams p;
     std::memset(&p, 0, sizeof(p));
+    p.sched = sched;
     p.bias = L.bias;
     p.residual = residual;
     p.out = out;
@@ -1547,7 +1604,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     }
     if (pool) return set_error(e, FX_ERR_INVALID, "flat_conv: only the stem has a fused max-pool");
     if (flat128_supported(g)) return flat128_conv(e, L, in, residual, out, n, relu, stream);
-    if (flat2_supported(g, residual != nullptr)) return flat2_conv(e, L, in, residual, out, n, relu, stream);
+    if (flat2_supported(g, residual != nullptr)) return flat2_conv(e, L, in, residual, out, n, relu, stream, sched);
     p.P = g.win + 2;
     p.chunks = g.cin / 64;
     p.x0 = -1;

@@ -138,6 +138,20 @@ struct ProfScope {
     }
 };
 
+// Tile walk of launch `li` (conv_flat.cu TileWalk).  The stem's and layer 1's tensors (103 MB each at batch 256) do not
+// fit in L2, so consecutive launches sweep them in opposite directions: the preprocess kernel and the strided conv of
+// layer 2 ascend, hence stem descending, layer1.0.conv1 ascending, ... layer1.1.conv2 descending.  Results do not
+// depend on the walk.  FX_SCHED: 0 = every kernel ascending over contiguous runs, 1 = alternate over contiguous runs,
+// 2 = alternate, tiles strided over the CTAs (the grid sweeps the tensor in time).
+static int tile_sched(int li) {
+    static const int mode = [] {
+        const char* v = getenv("FX_SCHED");
+        return v ? atoi(v) : 2;
+    }();
+    if (mode == 0 || li > 4) return 0;
+    return ((li & 1) ? 0 : 1) | (mode == 2 ? 2 : 0);
+}
+
 // One conv layer on NHWC activations in the engine's precision.  Layer 0 reads the staging tensor.
 static int run_conv(fx_engine* e, int li, const void* in, const void* residual, void* out, float* out_f32, int n, int relu,
                     cudaStream_t stream) {
@@ -146,7 +160,7 @@ static int run_conv(fx_engine* e, int li, const void* in, const void* residual, 
     if (e->precision == FX_PRECISION_BF16) {
         if (!out_f32 && flat_supported(L.g))
             return flat_conv(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
-                             static_cast<__nv_bfloat16*>(out), n, relu, false, stream);
+                             static_cast<__nv_bfloat16*>(out), n, relu, false, stream, tile_sched(li));
         return tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(residual),
                               static_cast<__nv_bfloat16*>(out), out_f32, n, relu, stream);
     }
@@ -167,7 +181,7 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
     if (bf16) {  // one kernel: the max-pool runs in the conv epilogue
         ProfScope ps(e, 0, stream);
         if ((rc = flat_conv(e, e->layers[0], static_cast<const __nv_bfloat16*>(e->in0), nullptr, static_cast<__nv_bfloat16*>(A), n, 1,
-                            true, stream)) != FX_OK)
+                            true, stream, tile_sched(0))) != FX_OK)
             return rc;
     } else {
         ProfScope ps(e, 0, stream);

@@ -279,7 +279,8 @@ int tc_conv(fx_engine* e, int li, const __nv_bfloat16* in, const __nv_bfloat16* 
 // conv_flat.cu (bf16 tcgen05 weight-stationary halo-tile path: stem, layer1, layer2 3x3/s1)
 bool flat_supported(const LayerGeom& g);
 // pool (stem only): also apply the 3x3/s2/p1 max-pool in the epilogue; out is then [n][56][56][64].
+// sched: tile walk of the stem / layer-1 kernels (conv_flat.cu TileWalk: bit 0 descending, bit 1 strided over the CTAs).
 int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out, int n,
-              int relu, bool pool, cudaStream_t stream);
+              int relu, bool pool, cudaStream_t stream, int sched = 0);
 
 }  // namespace fx
