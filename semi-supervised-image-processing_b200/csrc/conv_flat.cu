@@ -421,10 +421,10 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int i = m / p.P, x = m - i * p.P;
             return (x < p.W && i < c.rows_valid) ? ((c.img * p.H + c.y0 + i) * p.W + x) : -1;
         };
-        // The residual of the group's NEXT M-tile is fetched into registers (coalesced: 8 lanes x 16 B per pixel row)
-        // BEFORE the current tile is processed and moved to the staging block when that tile's store-out is done: a whole
-        // tile period hides the load (a cp.async into the staging block could only start after the store-out and was
-        // waited for at once: the epilogue, not the tensor pipe, then paced the convs with a residual).
+        // The residual of the group's NEXT M-tile is fetched into registers (coalesced: 8 lanes x 16 B per pixel row) BEFORE
+        // the current tile is processed, and moved to the staging block once that tile's store-out is done: a whole tile
+        // period hides the load.  (A cp.async into the staging block could only start after the store-out and was waited
+        // for at once: the epilogue, not the tensor pipe, paced the convs with a residual -- 85 -> 76 us per launch.)
         uint4 rres[8];
         auto load_res = [&](int px) {
 #pragma unroll
@@ -454,7 +454,10 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             Cursor nxt = cur;
             const bool nlive = advance(nxt) && advance(nxt);
             const int npix = nlive ? pix_of(nxt) : -1;
-            if (has_res) stash_res();
+            if (has_res) {
+                stash_res();
+                if (nlive) load_res(npix);
+            }
             const uint32_t slot = cur.g & (kFlatSlots - 1), use = cur.g / kFlatSlots;
             __syncwarp();
             mbar_wait(tfull0 + 8 * slot, use & 1);
@@ -468,7 +471,6 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 tmem_ld_wait();
                 // issued here, while v[] occupies the registers the TMEM load needs: ptxas then loads straight into rres
                 // (issued before the TMEM load it used scratch registers and copied -- waited -- at once)
-                if (h == 0 && has_res && nlive) load_res(npix);
                 if (h == 1) {
                     tc_fence_before();
                     mbar_arrive(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back
@@ -753,7 +755,10 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             Cursor nxt = cur;
             const bool nlive = advance(nxt) && advance(nxt);
             const int npix = nlive ? pix_of(nxt) : -1;
-            if (has_res) stash_res();
+            if (has_res) {
+                stash_res();
+                if (nlive) load_res(npix);
+            }
             const uint32_t slot = cur.g & (kFlatSlots - 1), use = cur.g / kFlatSlots;
             __syncwarp();
             mbar_wait(tfull0 + 8 * slot, use & 1);
@@ -765,7 +770,6 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 uint32_t v[32];
                 tmem_ld32(taddr + h * 32, v);
                 tmem_ld_wait();
-                if (h == 0 && has_res && nlive) load_res(npix);  // see flat_conv_kernel
                 if (h == 1) {
                     tc_fence_before();
                     mbar_arrive_leader(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back to the leader
