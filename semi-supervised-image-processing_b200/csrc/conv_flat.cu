@@ -38,7 +38,10 @@ struct FlatParams {
     int x0, ypad;          // TMA box origin: x = x0, y = y0 - ypad
     int cout;
     int nstages, stage_bytes, box_bytes, w_bytes, slack_bytes;
-    const float* bias;
+    // The folded bias travels IN the kernel parameters (constant bank): the epilogue's FADDs take it as a constant operand.
+    // Read from shared memory it cost 32 of the epilogue's 92 (153 with a residual) shared-memory wavefronts per warp and
+    // M-tile (a broadcast LDS.128 is two wavefronts), on the data pipe the MMA operand fetch saturates.  Needs cout == 64.
+    float bias_v[64];
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     int relu;
@@ -157,9 +160,11 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 2) tmem_alloc(tslot, 512);
     if (warp == 3) {
         if (POOL && lane == 0) *reinterpret_cast<int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw))) = 0;
-        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
-        bs[lane] = __ldg(p.bias + nslice * 64 + lane);
-        bs[lane + 32] = __ldg(p.bias + nslice * 64 + lane + 32);
+        if (POOL) {  // the pooled stem keeps its bias in shared memory (constant operands measured 4 us slower there)
+            float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+            bs[lane] = p.bias_v[lane];
+            bs[lane + 32] = p.bias_v[lane + 32];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -390,7 +395,6 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int q = warp & 3;           // TMEM lane quarter this warp may read
         const int grp = (warp - 4) >> 2;  // which M-tiles (g & 1) this warp handles
         const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
-        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         const int cbase = nslice * 64;
         const int rr0 = lane >> 3, ch = lane & 7;  // store-out role: row (it*4 + rr0), 16-byte chunk ch
         const bool has_res = p.residual != nullptr;
@@ -478,8 +482,9 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
+                    const float* bv = p.bias_v + h * 32 + j * 8;  // compile-time offsets: constant-bank operands
+                    const float4 b0 = make_float4(bv[0], bv[1], bv[2], bv[3]);
+                    const float4 b1 = make_float4(bv[4], bv[5], bv[6], bv[7]);
                     float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
                                   __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                                   __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
@@ -550,7 +555,7 @@ constexpr int kFlat2Threads = 384;
 struct Flat2Params {
     int P, W, H, R, tiles_per_img, n_work, batch, cout;
     int nstages, stage_bytes, box_bytes, slack_bytes;
-    const float* bias;
+    float bias_v[64];  // folded bias as constant operands (FlatParams)
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     int relu;
@@ -598,11 +603,6 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2cta(tslot, 512);
-    if (warp == 3) {
-        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
-        bs[lane] = __ldg(p.bias + lane);
-        bs[lane + 32] = __ldg(p.bias + lane + 32);
-    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -692,7 +692,6 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int q = warp & 3;
         const int grp = (warp - 4) >> 2;
         const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
-        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
         const int rr0 = lane >> 3, ch = lane & 7;
         const bool has_res = p.residual != nullptr;
 
@@ -777,8 +776,9 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 32 + j * 8 + 4);
+                    const float* bv = p.bias_v + h * 32 + j * 8;  // compile-time offsets: constant-bank operands
+                    const float4 b0 = make_float4(bv[0], bv[1], bv[2], bv[3]);
+                    const float4 b1 = make_float4(bv[4], bv[5], bv[6], bv[7]);
                     float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
                                   __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
                                   __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
@@ -1494,7 +1494,8 @@ static int flat2_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
     Flat2Params p;
     std::memset(&p, 0, sizeof(p));
     p.sched = sched;
-    p.bias = L.bias;
+    if (g.cout != 64 || L.host_b.size() != 64) return set_error(e, FX_ERR_UNSUPPORTED, "flat2_conv: cout must be 64");
+    std::memcpy(p.bias_v, L.host_b.data(), sizeof(p.bias_v));
     p.residual = residual;
     p.out = out;
     p.relu = relu;
@@ -1553,7 +1554,7 @@ static bool flat128_supported(const LayerGeom& g) {
 bool flat_supported(const LayerGeom& g) {
     if (flat128_supported(g)) return true;
     if (g.cin == 3) return g.kh == 7 && g.kw == 7 && g.stride == 2 && g.pad == 3 && g.hin == kCrop && g.win == kCrop && g.cout == 64;
-    return g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin % 64 == 0 && g.cin <= 128 && g.cout % 64 == 0 &&
+    return g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin % 64 == 0 && g.cin <= 128 && g.cout == 64 &&
            g.win + 2 <= 128 && g.win >= 8;
 }
 
@@ -1563,7 +1564,10 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     FlatParams p;
     std::memset(&p, 0, sizeof(p));
     p.sched = sched;
-    p.bias = L.bias;
+    if (!flat128_supported(g)) {  // stem and layer 1: the bias is part of the kernel parameters
+        if (g.cout != 64 || L.host_b.size() != 64) return set_error(e, FX_ERR_UNSUPPORTED, "flat_conv: cout must be 64");
+        std::memcpy(p.bias_v, L.host_b.data(), sizeof(p.bias_v));
+    }
     p.residual = residual;
     p.out = out;
     p.relu = relu;
