@@ -81,15 +81,6 @@ __device__ __forceinline__ uint4 ldg_stream128(const void* gptr) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(gptr));
     return r;
 }
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
-    return r;
-}
-__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 // Which work items a CTA (or CTA pair) processes, and in which order.  The activations of the stem and of layer 1 at
 // batch 256 (103 MB per tensor) do not fit in L2 next to the tensors written meanwhile, so a kernel that walks its
 // input in the order the previous kernel wrote it finds nothing of it in L2 (LRU: the oldest lines went first).

@@ -53,6 +53,11 @@ struct TcConvParams {
     const float* ds_bias;
     __nv_bfloat16* ds_out;
     int split_full, split_tail;  // CTA-pair kernel only: see the work-unit comment in tc2_conv_kernel
+    // CTA-pair kernel, stride-2 layers: the input is addressed through two 5-D maps [cin][W/2][row parity][H/2][n], one
+    // per COLUMN parity (base + cin elements), so that every tap is a plain unit-stride box of one parity plane.  A box
+    // with elementStrides = 2 costs the TMA unit a walk over its whole bounding box (measured: ~1000 cycles per
+    // 128-pixel box, four times the MMAs it feeds; the traffic itself was never the problem).
+    int s2planes;
 };
 
 constexpr int kTcThreads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps (4 TMEM lane quarters x 4 column groups)
@@ -286,20 +291,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // rows), so the weight bytes per SM halve (64 B/clk/SM at the floor).  Barriers: the leader's `full`
 // barrier counts the bytes of both CTAs' TMA loads; tcgen05.commit multicasts `empty` / `tmem full` to both.
 // ------------------------------------------------------------------------------------------
-template <int BN, int BK, int STAGES>
+// RESB (layer2.0 conv1 + downsample: 3x3 x 64 -> 128, ten K-blocks): this CTA's half of EVERY weight K-block stays
+// resident in shared memory (80 KB), loaded once before the previous kernel has finished (PDL); the ring then carries
+// activations only.  That kernel is bound by L2 -> SM delivery (24 KB per K-block and CTA against 256 MMA cycles);
+// without the weight reloads it is 16 KB.
+constexpr int kResKb = 10;
+template <int BN, int BK, int STAGES, bool RESB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_bh, const TcConvParams p) {
+tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b2,
+                const __grid_constant__ CUtensorMap map_bh, const TcConvParams p) {
     constexpr int kA = 128 * BK * 2, kB = (BN / 2) * BK * 2;
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sA = sbase, sB = sbase + STAGES * kA;
-    const uint32_t bars = sB + STAGES * kB;
+    const uint32_t sA = sbase, sB = sbase + STAGES * kA;  // RESB: sB = kResKb resident K-blocks, not a ring
+    const uint32_t bars = sB + (RESB ? kResKb : STAGES) * kB;
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
-    const uint32_t tslot = tempty0 + 16;
+    const uint32_t tslot = tempty0 + 16, wbar = tslot + 8;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
+    // RESB: 2 KB per epilogue warp (32 rows x 64 B) to turn the accumulator layout (one pixel per lane) into whole
+    // 64-byte pieces of pixel rows before they go to global memory
+    const uint32_t stage_out0 = (tslot + 16 + 2 * 512 * 4 + 127u) & ~127u;
     for (int i = threadIdx.x; i < p.cout; i += kTcThreads) {
         bias_s[i] = __ldg(p.bias + i);
         if (p.ds_tiles) bias_s[512 + i] = __ldg(p.ds_bias + i);
@@ -313,6 +327,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_b);
     }
     if (warp == 1 && lane == 0) {
@@ -324,6 +339,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_init(tfull0 + 8 * i, 1);                       // multicast commit
             mbar_init(tempty0 + 8 * i, 2 * (kTcThreads - 128));  // every epilogue thread of both CTAs
         }
+        if (RESB) mbar_init(wbar, 2);  // leader's arrive.expect_tx + the peer producer's arrive
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2cta(tslot, kTmemCols);
@@ -331,9 +347,18 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tslot_ptr;
+    const int num_kb = p.kh * p.kw * p.cchunks;
+    if (RESB && warp == 0 && elect_one_sync()) {  // constant data: fetched before waiting for the previous kernel
+        const int n_res = num_kb + (p.ds_tiles ? p.cchunks : 0);
+        if (leader) mbar_expect_tx(wbar, 2 * n_res * kB);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d_2cta(sB + kb * kB, &map_b, wbar, kb * BK, (int)rank * (BN / 2));
+        if (p.ds_tiles)
+            for (int cc = 0; cc < p.cchunks; ++cc) tma_load_2d_2cta(sB + (num_kb + cc) * kB, &map_b2, wbar, cc * BK, (int)rank * (BN / 2));
+        if (!leader) mbar_arrive_leader(wbar);
+    }
+    __syncwarp();
     pdl_wait();
 
-    const int num_kb = p.kh * p.kw * p.cchunks;
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles_n;
     // Work units.  Normally one unit = one 256 x BN pair tile (+ the grouped downsample tiles).  With a SPLIT TAIL
@@ -366,9 +391,19 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int s = 0; s < kw; ++s)
                         for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                            if (leader) mbar_expect_tx(full0 + 8 * stage, half >= 0 ? 2 * (kA + kB / 2) : 2 * (kA + kB));
-                            tma_load_4d_2cta(sA + stage * kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            if (half >= 0)
+                            if (leader) mbar_expect_tx(full0 + 8 * stage, RESB ? 2 * kA : (half >= 0 ? 2 * (kA + kB / 2) : 2 * (kA + kB)));
+                            if (p.s2planes) {
+                                // input pixel = 2 * output pixel + (tap - pad): parity plane (tap - pad) & 1, plane index
+                                // shifted by floor((tap - pad) / 2); negative / too large indices are zero fill = padding
+                                const int dw = ds ? 0 : s - p.pad_w, dh = ds ? 0 : r - p.pad_h;
+                                const int pw = dw & 1, ph = dh & 1;
+                                tma_load_5d_2cta(sA + stage * kA, pw ? &map_a1 : &map_a, full0 + 8 * stage, cc * BK,
+                                                 (tw << p.wt_log2) + (dw - pw) / 2, ph, (th << p.ht_log2) + (dh - ph) / 2, n0);
+                            } else {
+                                tma_load_4d_2cta(sA + stage * kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                            }
+                            if (RESB) {
+                            } else if (half >= 0)
                                 tma_load_2d_2cta(sB + stage * kB, &map_bh, full0 + 8 * stage, kb * BK,
                                                  n_tile * BN + half * (BN / 2) + (int)rank * (BN / 4));
                             else
@@ -388,19 +423,25 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
             uint32_t stage = 0, phase = 0;
             int it = 0;
+            if (RESB) {
+                mbar_wait(wbar, 0);
+                tc_fence_after();
+            }
             constexpr uint32_t idesc_half = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 4) << 17) | ((uint32_t)(256 >> 4) << 24);
             for (int t0 = pair; t0 < n_units; t0 += n_pairs, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * as, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                const int nkb = (!p.split_tail && t0 >= pair_tiles) ? p.cchunks : num_kb;
+                const bool ds_unit = !p.split_tail && t0 >= pair_tiles;
+                const int nkb = ds_unit ? p.cchunks : num_kb;
                 const uint32_t idesc_u = (p.split_tail && t0 >= p.split_full) ? idesc_half : idesc;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        const uint32_t a_lo = (sA + stage * kA) >> 4, b_lo = (sB + stage * kB) >> 4;
+                        const uint32_t a_lo = (sA + stage * kA) >> 4;
+                        const uint32_t b_lo = (RESB ? sB + ((ds_unit ? num_kb : 0) + kb) * kB : sB + stage * kB) >> 4;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc_u, (kb | k) != 0);
@@ -459,6 +500,12 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+            // Short-K units (nine K-blocks, or ONE for the grouped downsample) are paced by this epilogue, and a store in
+            // which every lane writes 16 bytes of a different pixel row is 32 separate line requests.  RESB: stage the
+            // warp's 32 rows x 64 B in shared memory (16-byte chunk c of row r at ((c ^ (r >> 1)) & 3), conflict-free
+            // both ways) and store 8 rows x 64 contiguous bytes per instruction.
+            const bool staged = RESB && BN == 128 && !(p.out_f32 && !ds);
+            const uint32_t stg = stage_out0 + (uint32_t)(warp - 4) * 2048;
 #pragma unroll
             for (int ci = 0; ci < BN / 64; ++ci) {
                 if (ci >= nci) break;
@@ -508,13 +555,28 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
                                 u[k] = *reinterpret_cast<const unsigned*>(&h2);
                             }
-                            op[j] = o;
+                            if (staged)
+                                sts128(stg + lane * 64 + ((((ci * 2 + j) ^ (lane >> 1)) & 3) << 4), o);
+                            else
+                                op[j] = o;
                         }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive_leader(tempty0 + 8 * as);
+            if (staged) {
+                __syncwarp();
+                const int mypix = valid ? (int)pix : -1;
+                __nv_bfloat16* obuf = (ds ? p.ds_out : p.out) + (size_t)n_tile * BN + ch0 + (lane & 3) * 8;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const int r = i4 * 8 + (lane >> 2);
+                    const int pr = __shfl_sync(0xffffffffu, mypix, r);
+                    if (pr >= 0) *reinterpret_cast<uint4*>(obuf + (size_t)pr * p.cout) = lds128(stg + r * 64 + ((((lane & 3) ^ (r >> 1)) & 3) << 4));
+                }
+                __syncwarp();
+            }
         }
     }
 
@@ -649,13 +711,16 @@ static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb,
     return FX_OK;
 }
 
-template <int BN, int BK, int STAGES>
-static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const CUtensorMap& mbh,
-                      TcConvParams p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4;
+template <int BN, int BK, int STAGES, bool RESB = false>
+static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma1, const CUtensorMap& mb, const CUtensorMap& mb2,
+                      const CUtensorMap& mbh, TcConvParams p, cudaStream_t stream) {
+    constexpr int kBBytes = (BN / 2) * BK * 2;
+    constexpr int kSmem = 1024 + STAGES * 128 * BK * 2 + (RESB ? kResKb : STAGES) * kBBytes + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4 +
+                          (RESB ? 128 + 16 * 2048 : 0);
+    static_assert(kSmem <= 232448, "tc2_conv_kernel: shared memory");
     static bool attr_done[16] = {};
     if (!attr_done[e->device & 15]) {
-        FX_CUDA(e, cudaFuncSetAttribute(tc2_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        FX_CUDA(e, cudaFuncSetAttribute(tc2_conv_kernel<BN, BK, STAGES, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_done[e->device & 15] = true;
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
@@ -664,12 +729,12 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb
     int pairs = std::max(1, std::min(pair_tiles + p.ds_tiles, e->sm_count / 2));
     // split the tail wave into half-N units when it would leave more than half of the pairs idle
     const int tail = pair_tiles % pairs;
-    if (!p.ds_tiles && pair_tiles > pairs && tail > 0 && 2 * tail <= pairs && !getenv("FX_DEBUG_NO_SPLIT")) {
+    if (!RESB && !p.ds_tiles && pair_tiles > pairs && tail > 0 && 2 * tail <= pairs && !getenv("FX_DEBUG_NO_SPLIT")) {
         p.split_tail = tail;
         p.split_full = pair_tiles - tail;
     }
     if (const char* dbg = getenv("FX_DEBUG_TC_PAIRS")) pairs = std::max(1, std::min(pairs, atoi(dbg)));  // fabric experiments only
-    FX_CUDA(e, launch_pdl(tc2_conv_kernel<BN, BK, STAGES>, dim3(2 * pairs), dim3(kTcThreads), kSmem, stream, ma, mb, mb2, mbh, p));  // cluster dims are a kernel attribute
+    FX_CUDA(e, launch_pdl(tc2_conv_kernel<BN, BK, STAGES, RESB>, dim3(2 * pairs), dim3(kTcThreads), kSmem, stream, ma, ma1, mb, mb2, mbh, p));  // cluster dims are a kernel attribute
     FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
     return FX_OK;
 }
@@ -739,15 +804,36 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     p.tiles_g = (n + (1 << p.nt_log2) - 1) >> p.nt_log2;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_g * p.n_tiles_n;
 
-    CUtensorMap ma, mb;
+    CUtensorMap ma, ma1, mb;
     if (g.cin % 64 != 0) return set_error(e, FX_ERR_UNSUPPORTED, "tc_conv: cin must be a multiple of 64 (the stem runs on the flat kernel)");
+    static const bool planes_on = [] {
+        const char* v = getenv("FX_TC_S2PLANES");
+        return !(v && v[0] == '0');
+    }();
+    // stride-2 layers on the CTA-pair kernel: parity-plane maps (TcConvParams::s2planes)
+    p.s2planes = planes_on && bn >= 128 && g.stride == 2 && g.hin % 2 == 0 && g.win % 2 == 0 && g.kh == 3 && g.kw == 3 && g.pad == 1;
+    if (p.s2planes) {
+        const uint64_t rowb = (uint64_t)g.win * g.cin * 2;
+        const uint64_t dims[5] = {(uint64_t)g.cin, (uint64_t)g.win / 2, 2, (uint64_t)g.hin / 2, (uint64_t)n};
+        const uint64_t strides[4] = {(uint64_t)g.cin * 4, rowb, 2 * rowb, (uint64_t)g.hin * rowb};
+        const uint32_t box[5] = {64, 1u << p.wt_log2, 1, 1u << p.ht_log2, 1u << p.nt_log2};
+        const uint32_t estr[5] = {1, 1, 1, 1, 1};
+        int rc = tc_encode_map(e, &ma, in, 5, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A (even columns)");
+        if (rc != FX_OK) return rc;
+        rc = tc_encode_map(e, &ma1, in + g.cin, 5, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A (odd columns)");
+        if (rc != FX_OK) return rc;
+    }
     {
         const uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)g.win, (uint64_t)g.hin, (uint64_t)n};
         const uint64_t strides[3] = {(uint64_t)g.cin * 2, (uint64_t)g.win * g.cin * 2, (uint64_t)g.hin * g.win * g.cin * 2};
         const uint32_t box[4] = {64, (uint32_t)g.stride << p.wt_log2, (uint32_t)g.stride << p.ht_log2, 1u << p.nt_log2};
         const uint32_t estr[4] = {1, (uint32_t)g.stride, (uint32_t)g.stride, 1};
-        int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A");
-        if (rc != FX_OK) return rc;
+        int rc = FX_OK;
+        if (!p.s2planes) {
+            rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "conv A");
+            if (rc != FX_OK) return rc;
+            ma1 = ma;
+        }
         const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
         const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
         const uint32_t bbox[2] = {64, (uint32_t)(bn >= 128 ? bn / 2 : bn)};  // the CTA-pair kernel loads half a K-block per CTA
@@ -785,8 +871,17 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     }
     switch (bn) {
         case 64: return launch_tc<64, 64, 8>(e, ma, mb, mb2, p, stream);
-        case 128: return launch_tc2<128, 64, 8>(e, ma, mb, mb2, mbh, p, stream);
-        default: return launch_tc2<256, 64, 6>(e, ma, mb, mb2, mbh, p, stream);
+        case 128: {
+            // few K-blocks (layer2.0 conv1 + its downsample): weights resident in shared memory; FX_TC_RESB=0 streams them
+            static const bool resb_on = [] {
+                const char* v = getenv("FX_TC_RESB");
+                return !(v && v[0] == '0');
+            }();
+            const int n_res = p.kh * p.kw * p.cchunks + (p.ds_tiles ? p.cchunks : 0);
+            if (resb_on && p.n_tiles_n == 1 && n_res <= kResKb) return launch_tc2<128, 64, 6, true>(e, ma, ma1, mb, mb2, mbh, p, stream);
+            return launch_tc2<128, 64, 8>(e, ma, ma1, mb, mb2, mbh, p, stream);
+        }
+        default: return launch_tc2<256, 64, 6>(e, ma, ma1, mb, mb2, mbh, p, stream);
     }
 }
 
