@@ -23,7 +23,6 @@ from __future__ import annotations
 
 import argparse
 import atexit
-import hashlib
 import json
 import logging
 import os
@@ -38,6 +37,7 @@ import numpy as np
 import torch
 from PIL import Image, UnidentifiedImageError
 
+from . import _artifacts
 from . import _native as N
 from ._decode_pool import DecodePool
 from . import dist as fxdist
@@ -515,12 +515,7 @@ def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_s
 
 def compute_dataset_digest(records: Sequence[ImageRecord]) -> str:
     """sha256 over (relative path, size, int(mtime)) in path order (src/feature_extraction.py:316-331)."""
-    h = hashlib.sha256()
-    for rec in sorted(records, key=lambda r: str(r.relative_path)):
-        st = rec.absolute_path.stat()
-        for piece in (str(rec.relative_path), str(st.st_size), str(int(st.st_mtime))):
-            h.update(piece.encode("utf-8"))
-    return h.hexdigest()
+    return _artifacts.dataset_digest(records)
 
 
 def run_sanity_checks(embeddings) -> Dict[str, float]:
@@ -628,21 +623,11 @@ def _summary_markdown(results: ExtractionResults, stats: Dict[str, float], probe
 def save_artifacts(results: ExtractionResults, stats: Dict[str, float], neighbor_probe: List[Dict[str, object]], data_dir: Path,
                    device: torch.device) -> None:
     """embeddings.npy / embeddings.csv / metadata.json / feature_summary.md (src/feature_extraction.py:401-502)."""
-    import pandas as pd
-
     FEATURE_OUTPUT_DIR.mkdir(parents=True, exist_ok=True)
     NOTE_OUTPUT_DIR.mkdir(parents=True, exist_ok=True)
-    np.save(EMBEDDING_ARRAY_PATH, results.embeddings.astype(np.float32))
-    frame = pd.DataFrame(
-        {
-            "index": list(range(len(results.records))),
-            "path": [str(r.relative_path) for r in results.records],
-            "bucket": [r.bucket for r in results.records],
-            "label": [r.label for r in results.records],
-        },
-        columns=["index", "path", "bucket", "label"],
-    )
-    frame.to_csv(EMBEDDING_CSV_PATH, index=False)
+    # same bytes as np.save(astype(float32)) / DataFrame.to_csv(index=False), without the second 2 GB buffer and the
+    # DataFrame of the reference; the .npy stream, the CSV and the dataset digest run side by side (SURVEY.md 8f rank 4)
+    digest = _artifacts.save_parallel(EMBEDDING_ARRAY_PATH, EMBEDDING_CSV_PATH, results.embeddings, results.records)
     metadata = {
         "backbone": BACKBONE_NAME,
         "weights": BACKBONE_WEIGHTS,
@@ -658,7 +643,7 @@ def save_artifacts(results: ExtractionResults, stats: Dict[str, float], neighbor
         "failed_images": len(results.failures),
         "device": str(device),
         "dataset_dir": str(data_dir),
-        "dataset_digest": compute_dataset_digest(results.records),
+        "dataset_digest": digest,
         "sanity_checks": stats,
         "neighbor_probe": neighbor_probe,
     }

@@ -166,3 +166,18 @@ def test_large_matrix_known_answers(eng):
     z = eng.standardize(x, mean, torch.where(var == 0, torch.ones_like(std), std))
     assert abs(z[:, 5].mean().item()) < 1e-5 and abs(z[:, 5].std(unbiased=False).item() - 1.0) < 1e-5
     assert z[:, 0].abs().max().item() == 0.0
+
+
+def test_device_streamed_npy_is_np_save_byte_for_byte(tmp_path):
+    """embeddings.npy written from the gathered matrix while it is still on the GPU (two page-locked
+    buffers, copy of chunk k+1 under the write of chunk k) == np.save(matrix.astype(float32)), src/feature_extraction.py:416."""
+    from ssip_b200 import _artifacts as A
+
+    for n, chunk in ((0, 1 << 20), (1, 1 << 20), (700, 64 * 2048), (700, 1 << 30), (4099, 3 * 2048 + 100)):
+        x = post_matrix(max(n, 1))[:n] if n <= 700 else np.random.default_rng(n).random((n, 512), dtype=np.float32)
+        dev = torch.from_numpy(x).to(DEV)
+        A.write_npy(tmp_path / "dev.npy", dev, chunk_bytes=chunk)
+        np.save(tmp_path / "ref.npy", x.astype(np.float32))
+        assert (tmp_path / "dev.npy").read_bytes() == (tmp_path / "ref.npy").read_bytes(), (n, chunk)
+    with pytest.raises(ValueError):
+        A.write_npy(tmp_path / "bad.npy", torch.zeros(4, 512, dtype=torch.float16, device=DEV))

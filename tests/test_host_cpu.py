@@ -344,3 +344,65 @@ def test_decode_pool_processes_write_pillow_pixels_into_shared_memory(tmp_path):
         assert pool.buffer(1, off // 2)[1] is False  # reused, not re-created
     finally:
         pool.close()
+
+
+# ---- artifact writers at scale: same bytes as the reference's np.save / pandas / serial stat ----
+def test_streamed_npy_is_np_save_byte_for_byte(tmp_path):
+    from ssip_b200 import _artifacts as A
+
+    rng = np.random.default_rng(5)
+    cases = [rng.random((0, 512), dtype=np.float32), rng.random((1, 512), dtype=np.float32), rng.random((1000, 512), dtype=np.float32),
+             rng.random((37, 512)).astype(np.float64), np.asfortranarray(rng.random((64, 512), dtype=np.float32)),
+             rng.random((130, 512), dtype=np.float32)[::2]]
+    for k, emb in enumerate(cases):
+        ours, ref = tmp_path / f"o{k}.npy", tmp_path / f"r{k}.npy"
+        A.write_npy(ours, emb, chunk_bytes=(1 << 16) + 12)  # a chunk size that does not divide a row
+        np.save(ref, emb.astype(np.float32))                # src/feature_extraction.py:416
+        assert ours.read_bytes() == ref.read_bytes(), k
+    A.write_npy(tmp_path / "t.npy", torch.from_numpy(cases[2]))
+    assert (tmp_path / "t.npy").read_bytes() == (tmp_path / "r2.npy").read_bytes()
+
+
+def test_csv_writer_is_pandas_to_csv_byte_for_byte(tmp_path):
+    import pandas as pd
+
+    from ssip_b200 import _artifacts as A
+
+    names = ["plain.jpg", "with,comma.png", 'quote"inside.jpg', "new\nline.jpg", "  spaces  .jpg", "ünï/cödé.jpg", "'single'.jpg", "semi;colon.jpg",
+             "tab\there.jpg", "cr\rhere.jpg", "", "None", "nan"]
+    recs = [fx.ImageRecord(tmp_path / n, Path("avec_labels") / "cancer" / n if i % 3 else Path(n), "labeled" if i % 2 else "unlabeled",
+                           ("cancer" if i % 4 else 'odd,"label"') if i % 2 else None) for i, n in enumerate(names)]
+    for rows in (recs, recs[:1], [r for r in recs if r.label is None], []):
+        ours, ref = tmp_path / "o.csv", tmp_path / "r.csv"
+        A.write_embeddings_csv(ours, rows)
+        # the reference's construction, src/feature_extraction.py:418-431
+        frame = pd.DataFrame([{"index": i, "path": str(r.relative_path), "bucket": r.bucket, "label": r.label} for i, r in enumerate(rows)])
+        if rows:
+            frame.to_csv(ref, index=False)
+            assert ours.read_bytes() == ref.read_bytes()
+        else:  # the reference raises before it gets here (no embeddings); only the header makes sense
+            assert ours.read_text() == "index,path,bucket,label\n"
+
+
+def test_digest_equals_the_reference_loop(tmp_path):
+    import hashlib
+
+    from ssip_b200 import _artifacts as A
+
+    recs = []
+    for i in range(300):
+        f = tmp_path / f"f{i:04d}.bin"
+        f.write_bytes(b"x" * (i % 17))
+        os.utime(f, (1_700_000_000 + i, 1_700_000_000 + i * 3 + 0.75))
+        recs.append(fx.ImageRecord(f, Path("sans_label") / f.name, "unlabeled", None))
+    recs = recs[::-1]  # the digest sorts by relative path itself
+    h = hashlib.sha256()
+    for r in sorted(recs, key=lambda r: str(r.relative_path)):  # src/feature_extraction.py:326-330
+        st = r.absolute_path.stat()
+        h.update(str(r.relative_path).encode("utf-8"))
+        h.update(str(st.st_size).encode("utf-8"))
+        h.update(str(int(st.st_mtime)).encode("utf-8"))
+    assert A.dataset_digest(recs) == h.hexdigest() == fx.compute_dataset_digest(recs)
+    (tmp_path / "f0007.bin").unlink()
+    with pytest.raises(FileNotFoundError):  # as the reference: a vanished file aborts the run
+        A.dataset_digest(recs)
