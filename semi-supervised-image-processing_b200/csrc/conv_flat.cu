@@ -1004,6 +1004,18 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int m = mt * 128 + q * 32 + lane;
             const int i = m / p.P, x = m - i * p.P;
             const int pix = (mt < n_mt && x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+            // the residual does not depend on the accumulator: its cp.async runs under the wait for the tile's MMAs (the
+            // staging block is free: the previous tile's store-out is complete)
+            if (has_res) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = t * 4 + rr0;
+                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                    if (pr >= 0)
+                        cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
+                }
+                cp_async_commit();
+            }
             mbar_wait(tfull0 + 8 * set, sphase);
             tc_fence_after();
             if (mt >= n_mt) {  // nothing of ours in this (short) tile
@@ -1015,14 +1027,6 @@ flat128_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t srow = stg + lane * 128;
             {
                 if (has_res) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int rr = t * 4 + rr0;
-                        const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                        if (pr >= 0)
-                            cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
-                    }
-                    cp_async_commit();
                     cp_async_wait_all();
                     __syncwarp();
                 }
@@ -1269,6 +1273,18 @@ flat128x2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int m = mt * 128 + q * 32 + lane;
             const int i = m / p.P, x = m - i * p.P;
             const int pix = (real && mt < n_mt && x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
+            // the residual does not depend on the accumulator: its cp.async runs under the wait for the tile's MMAs (the
+            // staging block is free: the previous tile's store-out is complete)
+            if (has_res) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = t * 4 + rr0;
+                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
+                    if (pr >= 0)
+                        cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
+                }
+                cp_async_commit();
+            }
             mbar_wait(tfull0 + 8 * set, sphase);
             tc_fence_after();
             if (mt >= n_mt) {  // nothing of ours in this (short) tile
@@ -1280,14 +1296,6 @@ flat128x2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const uint32_t srow = stg + lane * 128;
             {
                 if (has_res) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int rr = t * 4 + rr0;
-                        const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                        if (pr >= 0)
-                            cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
-                    }
-                    cp_async_commit();
                     cp_async_wait_all();
                     __syncwarp();
                 }
