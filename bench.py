@@ -49,12 +49,12 @@ WEIGHT_SEED = 1234
 _M = 115_605_504
 LAYER_MACS = [118_013_952, _M, _M, _M, _M, _M // 2, _M, 6_422_528, _M, _M, _M // 2, _M, 6_422_528, _M, _M, _M // 2, _M, 6_422_528, _M, _M]
 assert sum(LAYER_MACS) == 1_813_561_344
-LAYER_FAMILY = (["flat_conv_kernel<32,4,4,pool> (stem conv1+bn+relu+maxpool, s2d 4x4, N=64)"] + ["flat2_conv_kernel<cta_group::2> (convs without residual) + flat_conv_kernel<128,3,3> (with residual): layer1 3x3/s1, N=64"] * 4 +
+LAYER_FAMILY = (["flat_conv_kernel<32,4,4,pool> (stem conv1+bn+relu+maxpool, s2d 4x4, N=64)"] + ["flat2_conv_kernel<cta_group::2> (layer1 3x3/s1, N=64; residual prefetched into registers)"] * 4 +
                 ["tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128x2_conv_kernel<cta_group::2> (layer2 3x3/s1, N=128)",
                  "tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128x2_conv_kernel<cta_group::2> (layer2 3x3/s1, N=128)",
                  "flat128x2_conv_kernel<cta_group::2> (layer2 3x3/s1, N=128)"] + ["tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)"] * 10)
 EXEC_ORDER = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 13, 14, 15, 16, 18, 19]  # launch order of the slots inside fx_forward (the 1x1 downsample slots 7, 12, 17 ride in the launches of slots 5, 10, 15)
-LAUNCH_PROFILE = ROOT / "profiles" / "r01_launches_v12.csv"  # ncu launch list (batch 256) used for the DRAM-traffic column
+LAUNCH_PROFILE = ROOT / "profiles" / "r01_launches_v13.csv"  # ncu launch list (batch 256) used for the DRAM-traffic column
 
 
 def profiled_traffic():

@@ -1476,13 +1476,14 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     return FX_OK;
 }
 
-// Layer 1 on CTA pairs (flat2_conv_kernel): measured 78 -> 62 us per launch for the convs WITHOUT a residual (batch 256);
-// the ones with a residual are HBM-bound at ~3.5 TB/s either way and stay on flat_conv_kernel (85 vs 87 us).
-// FX_FLAT2 = 0 disables it, = 2 also routes the residual convs through it (measurement knob).
+// Layer 1 on CTA pairs (flat2_conv_kernel): measured 78 -> 62 us per launch for the convs WITHOUT a residual (batch 256).
+// With the residual prefetched into registers and the bias in the constant bank the convs WITH a residual are faster on
+// it as well (74.3 -> 72.7 us; with the old cp.async residual they were HBM-latency-bound either way, 85 vs 87 us).
+// FX_FLAT2 = 0 disables it, = 1 keeps the residual convs on flat_conv_kernel (measurement knobs).
 static int flat2_mode() {
     static const int mode = [] {
         const char* v = getenv("FX_FLAT2");
-        return v ? atoi(v) : 1;
+        return v ? atoi(v) : 2;
     }();
     return mode;
 }
