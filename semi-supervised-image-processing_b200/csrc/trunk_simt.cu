@@ -220,7 +220,10 @@ int maxpool_3x3s2(fx_engine* e, const void* in, void* out, int n, int h, int w, 
 // ------------------------------------------------------------------------------------------
 // global average pool: [n][hw][c] -> fp32 [n][c]; fixed summation order (deterministic)
 // ------------------------------------------------------------------------------------------
-template <bool BF16>
+// HW > 0: the plane size is a compile-time constant (49 for ResNet-18 at 224 x 224), all HW loads of a thread are issued
+// before the first add -- the runtime loop kept ~4 loads per thread in flight and ran at 2.4 TB/s on a 25.7 MB input.
+// The additions happen in the same order (p ascending) either way: the results are bit-identical.
+template <bool BF16, int HW>
 __global__ void avgpool_kernel(const void* __restrict__ in_, float* __restrict__ out, int n, int hw, int c) {
     pdl_launch_dependents();
     pdl_wait();
@@ -228,24 +231,42 @@ __global__ void avgpool_kernel(const void* __restrict__ in_, float* __restrict__
     if (i >= n * c) return;
     const int img = i / c, ch = i - img * c;
     float s = 0.f;
-    for (int p = 0; p < hw; ++p) {
-        const size_t off = ((size_t)img * hw + p) * c + ch;
-        s += BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in_)[off])
-                  : reinterpret_cast<const float*>(in_)[off];
+    if (HW > 0) {
+        float v[HW > 0 ? HW : 1];
+#pragma unroll
+        for (int p = 0; p < HW; ++p) {
+            const size_t off = ((size_t)img * HW + p) * c + ch;
+            v[p] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in_)[off]) : reinterpret_cast<const float*>(in_)[off];
+        }
+#pragma unroll
+        for (int p = 0; p < HW; ++p) s += v[p];
+    } else {
+        for (int p = 0; p < hw; ++p) {
+            const size_t off = ((size_t)img * hw + p) * c + ch;
+            s += BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in_)[off])
+                      : reinterpret_cast<const float*>(in_)[off];
+        }
     }
     out[i] = s / (float)hw;
 }
 
 const void* avgpool_kernel_ptr(bool in_is_bf16) {
-    return in_is_bf16 ? reinterpret_cast<const void*>(avgpool_kernel<true>) : reinterpret_cast<const void*>(avgpool_kernel<false>);
+    return in_is_bf16 ? reinterpret_cast<const void*>(avgpool_kernel<true, 49>) : reinterpret_cast<const void*>(avgpool_kernel<false, 49>);
 }
 
 int avgpool_7x7(fx_engine* e, const void* in, bool in_is_bf16, float* out, int n, int hw, int c, cudaStream_t stream) {
     const int total = n * c;
-    if (in_is_bf16)
-        FX_CUDA(e, launch_pdl(avgpool_kernel<true>, dim3((total + 127) / 128), dim3(128), 0, stream, in, out, n, hw, c));
-    else
-        FX_CUDA(e, launch_pdl(avgpool_kernel<false>, dim3((total + 127) / 128), dim3(128), 0, stream, in, out, n, hw, c));
+    const dim3 grid((total + 127) / 128), block(128);
+    if (hw == 49) {
+        if (in_is_bf16)
+            FX_CUDA(e, launch_pdl(avgpool_kernel<true, 49>, grid, block, 0, stream, in, out, n, hw, c));
+        else
+            FX_CUDA(e, launch_pdl(avgpool_kernel<false, 49>, grid, block, 0, stream, in, out, n, hw, c));
+    } else if (in_is_bf16) {
+        FX_CUDA(e, launch_pdl(avgpool_kernel<true, 0>, grid, block, 0, stream, in, out, n, hw, c));
+    } else {
+        FX_CUDA(e, launch_pdl(avgpool_kernel<false, 0>, grid, block, 0, stream, in, out, n, hw, c));
+    }
     FX_LAUNCH_CHECK(e, "avgpool_kernel");
     return FX_OK;
 }
