@@ -337,3 +337,55 @@ def test_step_graph_replay_is_byte_identical_to_direct_launches(eng_bf16):
         side.synchronize()
     assert np.array_equal(got.cpu().numpy(), want)
     ref_eng.close()
+
+
+# ---- kernel-selection knobs: alternate paths stay correct -----------------------------------------
+_KNOB_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import reference_path as rp
+from ssip_b200 import synthetic
+from ssip_b200.engine import Engine, pack_images
+eng = Engine(0, max_batch=64, precision="bf16")
+eng.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+imgs = list(synthetic.noise_images(40, 224, 224, seed=21))
+buf, descs, total = pack_images(imgs)
+np.save(sys.argv[2], eng.embed_host(buf, descs, len(imgs), total))
+eng.close()
+"""
+_KNOBS = [{}, {"FX_SCHED": "0"}, {"FX_SCHED": "1"}, {"FX_FLAT2": "0"}, {"FX_FLAT2": "1"}, {"FX_FLAT128X2": "0"}, {"FX_TC_RESB": "0"},
+          {"FX_TC_S2PLANES": "0"}, {"FX_GRAPHS": "0"}]
+
+
+def test_kernel_selection_knobs_do_not_change_the_embeddings(tmp_path):
+    """The knobs are read once per process, so every setting runs in its own interpreter (all at once: they share the GPU).
+    The tile walk (FX_SCHED) and graph replay only reorder work: byte-identical rows.  The other knobs swap kernels
+    (single CTA <-> CTA pair, streamed <-> resident weights, strided boxes <-> parity planes): identical operands and
+    per-element accumulation order: byte-identical rows as well (measured on B200: every knob, max difference 0)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = str(Path(__file__).resolve().parents[1])
+    script = tmp_path / "knob.py"
+    script.write_text(_KNOB_SCRIPT)
+    procs = []
+    for k, env in enumerate(_KNOBS):
+        e = dict(os.environ)
+        for name in ("FX_SCHED", "FX_FLAT2", "FX_FLAT128X2", "FX_TC_RESB", "FX_TC_S2PLANES", "FX_GRAPHS"):
+            e.pop(name, None)
+        e.update(env)
+        procs.append(subprocess.Popen([sys.executable, str(script), root, str(tmp_path / f"emb{k}.npy")], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, env, out in zip(procs, _KNOBS, outs):
+        assert p.returncode == 0, f"{env}: {out[-2000:]}"
+    base = np.load(tmp_path / "emb0.npy")
+    assert np.isfinite(base).all() and base.shape == (40, 512)
+    report = []
+    for k, env in enumerate(_KNOBS[1:], start=1):
+        got = np.load(tmp_path / f"emb{k}.npy")
+        exact = bool(np.array_equal(got, base))
+        report.append((env, exact, float(np.abs(got - base).max())))
+        assert exact, f"{env}: rows differ by up to {np.abs(got - base).max():.3e}"
+    print("knob report:", report)
