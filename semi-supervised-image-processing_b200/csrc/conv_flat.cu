@@ -19,7 +19,9 @@
 //     TMA-written tile is a valid operand -- pinned by tests via fx_debug_umma_shift.)  No im2col,
 //     no per-tap loads; x >= W positions are junk rows that are never stored (W/P efficiency);
 //   * accumulators are 64-column TMEM slots in a ring of 8, so the epilogue of one 128-pixel
-//     M-tile overlaps the MMAs of the next ones; 8 epilogue warps (+bias, +residual, ReLU, bf16).
+//     M-tile overlaps the MMAs of the next ones; 8 epilogue warps (+bias, +residual, ReLU, bf16);
+//   * consecutive launches walk their tiles in opposite directions (TileWalk), the residual of the next M-tile is
+//     fetched into registers while the current one is processed, the layer-1 bias is a constant-bank operand.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue.
 #include <algorithm>
 #include <cstring>
@@ -382,7 +384,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // Two groups of four warps take alternate M-tiles (g even / odd).  A warp owns 32 accumulator
         // rows x 64 channels = 4 KB, staged in a private swizzled smem block so that global traffic is
         // whole 128-byte pixel rows (8 lanes x 16 B) instead of one 16-byte piece per lane per line.
-        // The residual of the warp's NEXT tile is prefetched into the same block with cp.async.
+        // The residual of the warp's NEXT tile travels in registers until this block is free (see rres below).
         const int q = warp & 3;           // TMEM lane quarter this warp may read
         const int grp = (warp - 4) >> 2;  // which M-tiles (g & 1) this warp handles
         const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
@@ -539,7 +541,7 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // Protocol (as tc2_conv_kernel): the even CTA of the pair issues every MMA; its `full` / weight barriers count the TMA
 // bytes of both CTAs; `tcgen05.commit` multicasts `empty` / accumulator-ready to both; the epilogue warps of both CTAs
 // arrive on the leader's accumulator-free barriers.  Unit u of a pair = work tiles 2u (leader) and 2u + 1 (peer).
-// Warp roles per CTA: 0 = TMA producer, 1 = MMA issuer (leader only), 2 = TMEM allocator, 3 = bias, 4..11 = epilogue.
+// Warp roles per CTA: 0 = TMA producer, 1 = MMA issuer (leader only), 2 = TMEM allocator, 4..11 = epilogue (bias: kernel parameters).
 // ------------------------------------------------------------------------------------------
 constexpr int kFlat2Threads = 384;
 
