@@ -35,6 +35,23 @@ def test_c_oracle_matches_installed_torchvision(shape):
     assert torch.equal(want, got)
 
 
+def test_c_oracle_matches_installed_torchvision_on_seeded_random_geometries():
+    """48 seeded (H, W) pairs: extreme aspect ratios, sides of 1..3 pixels, up- and down-scales up to 13x, odd crops.
+    The reference path is Image -> Resize(256) -> CenterCrop(224) -> ToTensor -> Normalize (src/feature_extraction.py:200-205)."""
+    rng = np.random.default_rng(20261018)
+    shapes = [(1, 1), (1, 700), (700, 1), (2, 3), (3, 2), (223, 225), (255, 257), (257, 255), (256, 3000), (3000, 256)]
+    while len(shapes) < 48:
+        h, w = int(rng.integers(4, 1400)), int(rng.integers(4, 1400))
+        if h * w <= 1_200_000:
+            shapes.append((h, w))
+    transform = rp.port_transform()
+    for h, w in shapes:
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = transform(Image.fromarray(arr))
+        got = torch.from_numpy(rp.c_preprocess_rgb(arr))
+        assert torch.equal(want, got), (h, w)
+
+
 def test_c_oracle_resize_is_pillow_exact_on_gray_and_rgb():
     rng = np.random.default_rng(3)
     for (h, w, oh, ow) in [(512, 512, 256, 256), (224, 224, 256, 256), (300, 500, 256, 426), (100, 100, 256, 256), (512, 512, 224, 224)]:
