@@ -205,7 +205,8 @@ def run_reference(args, rank: int, json_fd: int):
         step(k)
     dt = time.perf_counter() - t0
     value = args.steps * k / dt
-    sample = f"{k} synthetic 224x224x3 images per step x {args.steps} steps, fp32, torch threads={cores} (first call {first:.2f}s untimed)"
+    sample = (f"{k} synthetic 224x224x3 images per step x {args.steps} steps, fp32, torch threads={cores} (first call {first:.2f}s untimed); "
+              "decoded arrays in memory, no PNG/JPEG decode (the GPU arm also starts from decoded bytes)")
     line = {
         "impl": "reference", "metric": "ResNet-18 embed images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -305,7 +306,8 @@ def main():
         torch.cuda.synchronize()
 
     B, K, W = args.batch, args.steps, args.warmup
-    eng = Engine(local_rank, max_batch=B, precision=args.precision)
+    B512 = 512  # per-GPU batch of the N > 1 runs (BASELINE.json configs[2]); also timed at N = 1 for a like-for-like scaling base
+    eng = Engine(local_rank, max_batch=max(B, B512) if world == 1 else B, precision=args.precision)
     eng.load_state_dict(_seeded_backbone(WEIGHT_SEED, False).state_dict())
 
     # resident synthetic pool (seeded, generated on the device): C2 keeps 50k images = 7.5 GB in HBM
@@ -466,6 +468,85 @@ def main():
     e2e_value = world * k_e2e * B / float(t.item())
     finite = bool(torch.isfinite(out_local).all().item()) and all(bool(np.isfinite(h.numpy()).all()) for h in host_out)
 
+    # ---- parity of the timed rows (outside the timed region): a seeded subsample of this rank's rows of the timed
+    # steps against the CPU port of the reference path on the same pool images; max over ranks -----------------------
+    from oracle import reference_path as rp  # the checker, never the thing measured
+
+    prng = np.random.default_rng(4242 + rank)
+    n_par = 32
+    rows = sorted(prng.choice(K * B, size=min(n_par, K * B), replace=False).tolist())
+    imgs = []
+    for r in rows:
+        step, j = divmod(r, B)
+        img = ((W + step) % n_batches) * B + j
+        imgs.append(pool[img * IMG_BYTES : (img + 1) * IMG_BYTES].cpu().numpy().reshape(IMG_H, IMG_W, 3))
+    torch.set_num_threads(max(1, len(all_cpus) // world))
+    want = rp.port_embed_arrays(imgs, seed=WEIGHT_SEED, randomize_bn=False)
+    got = out_local[rows].cpu().numpy()
+    rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+    cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
+    par = torch.tensor([float(rel.max()), -float(cos.min())], dtype=torch.float64, device=dev)
+    # the gathered matrix must hold every rank's rows, bit for bit: checksum of the int32 view per block
+    gather_ok = None
+    if world > 1:
+        dist.all_reduce(par, op=dist.ReduceOp.MAX)
+        mine = out_local.view(torch.int32).to(torch.int64).sum().reshape(1)
+        sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, mine)
+        blocks = gathered.view(world, K * B * 512).view(torch.int32).to(torch.int64).sum(dim=1)
+        gather_ok = bool(torch.equal(blocks, sums)) and bool(torch.equal(gathered[rank * K * B : (rank + 1) * K * B], out_local))
+    parity_max_rel_l2, parity_min_cos = float(par[0].item()), -float(par[1].item())
+
+    # ---- N = 1 only: the same device-resident pass at batch 512 (the per-GPU batch of the N > 1 runs), so that scaling
+    # efficiency can be computed like for like -----------------------------------------------------------------------
+    value_b512 = None
+    if world == 1 and B != B512 and pool_n >= 2 * B512:
+        d512 = uniform_descs(B512, IMG_H, IMG_W)
+        nb512 = pool_n // B512
+        o512 = torch.empty((2 * B512, 512), dtype=torch.float32, device=dev)
+
+        def steps512(k):
+            for i in range(k):
+                lane = i % n_lanes
+                eng.select_lane(lane)
+                with torch.cuda.stream(lane_streams[lane]):
+                    j = i % nb512
+                    eng.embed_device(pool[j * B512 * IMG_BYTES : (j + 1) * B512 * IMG_BYTES], d512, B512, out=o512[lane * B512 : (lane + 1) * B512])
+            eng.select_lane(0)
+            for st in lane_streams[1:]:
+                lane_streams[0].wait_stream(st)
+
+        steps512(4)
+        torch.cuda.synchronize()
+        k512 = max(10, K // 2)
+        a512, b512 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a512.record()
+        steps512(k512)
+        b512.record()
+        b512.synchronize()
+        value_b512 = k512 * B512 / (a512.elapsed_time(b512) / 1e3)
+
+    # ---- the host leg of e2e: what the pinned-host -> device copies alone can deliver, all ranks copying at once
+    # (plain cudaMemcpyAsync of one batch per call on one stream; CUDA events) ---------------------------------------
+    h2d_dst = torch.empty(B * IMG_BYTES, dtype=torch.uint8, device=dev)
+    for j in range(2):
+        h2d_dst.copy_(host_in[j % n_host], non_blocking=True)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_copies = 24
+    h0.record()
+    for j in range(n_copies):
+        h2d_dst.copy_(host_in[j % n_host], non_blocking=True)
+    h1.record()
+    h1.synchronize()
+    h2d = torch.tensor([n_copies * B * IMG_BYTES / (h0.elapsed_time(h1) / 1e3) / 1e9], dtype=torch.float64, device=dev)
+    h2d_min = h2d.clone()
+    if world > 1:
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+        dist.all_reduce(h2d_min, op=dist.ReduceOp.MIN)
+    h2d_mean_gbs, h2d_min_gbs = float(h2d.item()) / world, float(h2d_min.item())
+    e2e_bytes_per_image = IMG_BYTES + 512 * 4
+
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -474,7 +555,7 @@ def main():
         sample = synth_host(512, 5)
         rate, done, secs = cpu_port_rate(list(sample), 32, args.cpu_budget, cores)
         cpu_baseline = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"{done} synthetic 224x224x3 images, batch 32, fp32, {secs:.1f}s, oracle port of src/feature_extraction.py:272-300"}
+                        "sample": f"{done} synthetic 224x224x3 images, batch 32, fp32, {secs:.1f}s, oracle port of src/feature_extraction.py:272-300 on decoded arrays (no PNG/JPEG decode)"}
 
     if rank == 0:
         line = {
@@ -504,6 +585,17 @@ def main():
             "roofline_preprocess": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                                     "traffic": traffic["preprocess"] if traffic else None, "kernel": "preprocess_s2d_kernel (bf16 space-to-depth staging)", "bytes_per_image": PRE_BYTES_BF16,
                                     "avg_ms": pre_b2b, "avg_ms_single_launch_with_events": pre_avg, "peak_src": peaks["src"]},
+            # the host-side ceiling of e2e: every image costs 150,528 B of H2D (+ 2 KB of D2H); `peak` is what plain pinned copies
+            # deliver per GPU with all ranks copying at once, `achieved` what the pipelined e2e pass moved per GPU
+            "roofline_e2e": {"bound": "pcie-h2d", "achieved": e2e_value / world * IMG_BYTES / 1e9, "peak": h2d_mean_gbs, "unit": "GB/s per GPU",
+                             "frac": (e2e_value / world * IMG_BYTES / 1e9) / h2d_mean_gbs, "peak_min_over_ranks": h2d_min_gbs,
+                             "images_per_s_ceiling": world * h2d_mean_gbs * 1e9 / IMG_BYTES, "bytes_per_image": e2e_bytes_per_image,
+                             "how": f"{n_copies} cudaMemcpyAsync of {B * IMG_BYTES} B from pinned host memory per rank, all ranks at once, CUDA events"},
+            "value_b512_n1": value_b512,
+            "parity_max_rel_l2": parity_max_rel_l2, "parity_min_cos": parity_min_cos,
+            "parity": {"rows_per_rank": len(rows), "against": "oracle port of src/feature_extraction.py:272-300 (CPU fp32) on the same pool images, "
+                       "rows of the timed steps, max over ranks", "tolerance": "relL2 <= 1e-2, cos >= 0.999 (bf16); 1e-5 (fp32)",
+                       "gathered_blocks_equal_rank_rows": gather_ok},
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "finite": finite,

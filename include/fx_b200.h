@@ -204,6 +204,16 @@ int fx_embed_host_async(fx_handle h, int slot, const uint8_t *src_host, size_t t
 int fx_embed_host_wait(fx_handle h, int slot);
 
 /*
+ * fx_embed_host_async with the embeddings left ON THE DEVICE: the trunk's last kernel writes the n rows straight to
+ * emb_dev, no device->host copy.  Multi-GPU extraction points emb_dev into the rank's slot of the all-gather buffer
+ * (buf + (rank * rows_per_rank + rows_done) * 512), so that ONE in-place ncclAllGather assembles [N,512] and only the
+ * rank that writes the artifacts copies it to the host (replaces the per-batch `.cpu().numpy()` of
+ * src/feature_extraction.py:293-294 and the concatenation at :305).  Pair with fx_embed_host_wait(slot).
+ */
+int fx_embed_host_async_dev(fx_handle h, int slot, const uint8_t *src_host, size_t total_bytes,
+                            const fx_image_desc *descs_host, int n, float *emb_dev);
+
+/*
  * ---- on-device post-processing of an [n][d] fp32 embedding matrix ----
  * At N = 1M the reference's numpy / scikit-learn post-processing scans 2 GB on the host several times; these are the
  * same reductions as single HBM-bound passes over the (gathered) device buffer.  d <= 4096.  Column statistics

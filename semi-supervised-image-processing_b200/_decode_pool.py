@@ -32,6 +32,45 @@ from PIL import Image, UnidentifiedImageError
 
 _ATTACHED: Dict[str, shared_memory.SharedMemory] = {}
 
+# The preprocess kernel stages the source rows one output band needs in shared memory, which bounds the down-scaling
+# factor it can take (csrc/preprocess.cu build_geom: about 23x, a short side near 5900 px).  Larger files are resized
+# to the Resize(256) size right after the decode with the very call the reference's transform makes (torchvision
+# functional.resize -> PIL Image.resize(BILINEAR)); the kernel then sees a 256-short-side image, for which Resize(256)
+# is the identity, so the result is the reference's, bit for bit, for any size.
+HOST_RESIZE_SHORT_SIDE = 4096
+_RESIZE = 256
+
+
+def resized_size(h: int, w: int) -> Tuple[int, int]:
+    """(height, width) torchvision's Resize(256) gives an h x w image (transforms/functional.py:353-384)."""
+    short, long = (w, h) if w <= h else (h, w)
+    new_long = int(_RESIZE * long / short)
+    return (new_long, _RESIZE) if w <= h else (_RESIZE, new_long)
+
+
+def host_resize_if_oversized(img: Image.Image) -> Image.Image:
+    if min(img.height, img.width) <= HOST_RESIZE_SHORT_SIDE:
+        return img
+    oh, ow = resized_size(img.height, img.width)
+    return img.resize((ow, oh), Image.BILINEAR)
+
+
+def rebuild_exception(name: str, text: str) -> BaseException:
+    """The exception a worker reported as (class name, text), as an instance of the same class when it is a builtin
+    or a Pillow one (so that process mode raises what thread mode and the reference raise), else RuntimeError."""
+    import builtins
+
+    import PIL
+
+    for ns in (builtins, PIL, Image):
+        cls = getattr(ns, name, None)
+        if isinstance(cls, type) and issubclass(cls, BaseException):
+            try:
+                return cls(text)
+            except Exception:  # noqa: BLE001 - constructor with another signature
+                break
+    return RuntimeError(f"{name}: {text}")
+
 
 def _failure(exc: BaseException) -> Tuple[str, str, str]:
     kind = "decode" if isinstance(exc, (UnidentifiedImageError, OSError)) else "other"
@@ -44,7 +83,10 @@ def _probe_chunk(paths: Sequence[str]):
     for p in paths:
         try:
             with Image.open(p) as img:
-                out.append((img.height, img.width, len(img.getbands()), img.mode))
+                h, w = img.height, img.width
+                if min(h, w) > HOST_RESIZE_SHORT_SIDE:  # the decode pass resizes these on the host (see above)
+                    h, w = resized_size(h, w)
+                out.append((h, w, len(img.getbands()), img.mode))
         except BaseException as exc:  # noqa: BLE001 - reported to the parent, which re-raises what the reference would
             out.append(_failure(exc))
     return out
@@ -69,7 +111,7 @@ def _decode_chunk(shm_name: str, jobs: Sequence[Tuple[str, int, int, int, int, b
     for path, off, h, w, bands, gray in jobs:
         try:
             with Image.open(path) as img:
-                arr = np.asarray(img)
+                arr = np.asarray(host_resize_if_oversized(img))
             if arr.dtype != np.uint8 or arr.shape != ((h, w, bands) if bands > 1 else (h, w)):
                 raise OSError(f"decoded array {arr.dtype}{arr.shape} does not match the header ({h}, {w}, {bands})")
             c = bands

@@ -27,7 +27,7 @@ HOST_SLOTS = 4
 # every symbol include/fx_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "fx_version", "fx_abi_version", "fx_last_error", "fx_create", "fx_destroy", "fx_load_weights",
-    "fx_preprocess_nchw_f32", "fx_preprocess", "fx_forward", "fx_stage_nchw_f32", "fx_select_lane", "fx_set_transform", "fx_load_head", "fx_classify", "fx_embed", "fx_embed_host", "fx_embed_host_async", "fx_embed_host_wait",
+    "fx_preprocess_nchw_f32", "fx_preprocess", "fx_forward", "fx_stage_nchw_f32", "fx_select_lane", "fx_set_transform", "fx_load_head", "fx_classify", "fx_embed", "fx_embed_host", "fx_embed_host_async", "fx_embed_host_async_dev", "fx_embed_host_wait",
     "fx_column_stats", "fx_standardize", "fx_neighbor_probe", "fx_launch_count", "fx_profile_enable", "fx_profile_read", "fx_debug_conv", "fx_debug_folded", "fx_debug_tma_probe", "fx_debug_umma_shift", "fx_debug_stem_pool", "fx_debug_mma_rate", "fx_debug_staging",
     "fx_host_resized_size", "fx_host_crop_offset", "fx_host_coeffs",
 )
@@ -91,6 +91,7 @@ def lib() -> ctypes.CDLL:
     L.fx_embed.argtypes = [c_void_p, c_void_p, POINTER(ImageDesc), c_int, c_void_p, c_void_p]
     L.fx_embed_host.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(ImageDesc), c_int, c_void_p]
     L.fx_embed_host_async.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(ImageDesc), c_int, c_void_p]
+    L.fx_embed_host_async_dev.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(ImageDesc), c_int, c_void_p]
     L.fx_embed_host_wait.argtypes = [c_void_p, c_int]
     L.fx_column_stats.argtypes = [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p, c_void_p, POINTER(MatrixStats), c_void_p]
     L.fx_standardize.argtypes = [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -1391,10 +1391,10 @@ static int plan_flat(FlatParams& p, bool pool = false) {
 
 template <int ROWB, int KH, int KW, bool POOL>
 static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, FlatParams& p, int smem, cudaStream_t stream) {
-    static bool attr_done[16] = {};
-    if (!attr_done[e->device & 15]) {
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(flat_conv_kernel<ROWB, KH, KW, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_done[e->device & 15] = true;
+        attr_done[e->device & 255] = true;
     }
     int grid = std::min(e->sm_count, p.n_work * p.ns);
     grid -= grid % p.ns;
@@ -1455,11 +1455,11 @@ static int flat128_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16*
     const uint32_t bbox[2] = {64, (uint32_t)(pair ? 64 : 128)};
     rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat128 B");
     if (rc != FX_OK) return rc;
-    static bool attr_done[16] = {};
-    if (!attr_done[e->device & 15]) {
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(flat128_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         FX_CUDA(e, cudaFuncSetAttribute(flat128x2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_done[e->device & 15] = true;
+        attr_done[e->device & 255] = true;
     }
     if (pair) {
         const int n_units = ((n + 1) / 2) * p.tiles_per_img;
@@ -1531,10 +1531,10 @@ static int flat2_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
     const uint32_t bbox[2] = {64, 32};  // one tap's K-block of HALF of the output channels
     rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat2 B");
     if (rc != FX_OK) return rc;
-    static bool attr_done[16] = {};
-    if (!attr_done[e->device & 15]) {
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(flat2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_done[e->device & 15] = true;
+        attr_done[e->device & 255] = true;
     }
     const int n_units = (p.n_work + 1) / 2;
     const int pairs = std::max(1, std::min(e->sm_count / 2, n_units));

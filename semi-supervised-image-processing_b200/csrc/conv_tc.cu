@@ -920,10 +920,10 @@ template <int BN, int BK, int STAGES>
 static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const TcConvParams& p,
                      cudaStream_t stream) {
     using L = TcSmem<BN, BK, STAGES>;
-    static bool attr_done[16] = {};
-    if (!attr_done[e->device & 15]) {
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(tc_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_done[e->device & 15] = true;
+        attr_done[e->device & 255] = true;
     }
     const int grid = std::min(p.total_tiles + p.ds_tiles, e->sm_count);
     FX_CUDA(e, launch_pdl(tc_conv_kernel<BN, BK, STAGES>, dim3(grid), dim3(kTcThreads), L::kTotal, stream, ma, mb, mb2, p));
@@ -938,10 +938,10 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma
     constexpr int kSmem = 1024 + STAGES * 128 * BK * 2 + (RESB ? kResKb : STAGES) * kBBytes + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4 +
                           (RESB ? 128 + 16 * 2048 : 0);
     static_assert(kSmem <= 232448, "tc2_conv_kernel: shared memory");
-    static bool attr_done[16] = {};
-    if (!attr_done[e->device & 15]) {
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(tc2_conv_kernel<BN, BK, STAGES, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_done[e->device & 15] = true;
+        attr_done[e->device & 255] = true;
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
@@ -963,10 +963,10 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma
 template <int BN, int BK, int STAGES>
 static int launch_tc4(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mbq, const TcConvParams& p, cudaStream_t stream) {
     constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4;
-    static bool attr_done[16] = {};
-    if (!attr_done[e->device & 15]) {
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(tc4_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_done[e->device & 15] = true;
+        attr_done[e->device & 255] = true;
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int n_units = ((((m_tiles + 1) / 2) + 1) / 2) * p.n_tiles_n;

@@ -455,13 +455,10 @@ int fx_load_head(fx_handle e, const float* weight, const float* bias, int num_cl
         return set_error(e, FX_ERR_INVALID, "fx_load_head: null pointer or num_classes outside 1.." + std::to_string(FX_MAX_CLASSES));
     FX_CUDA(e, cudaSetDevice(e->device));
     FX_CUDA(e, cudaDeviceSynchronize());  // a previous head may still be in use
-    for (auto& g : e->step_graph) {
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-        if (g.graph) cudaGraphDestroy(g.graph);
-    }
+    // (the captured step graphs end at the average pool and the post-processing scratch has nothing to do with the
+    // head: neither is touched here)
     cudaFree(e->head_w);
     cudaFree(e->head_b);
-    cudaFree(e->post_scratch);
     e->head_w = e->head_b = nullptr;
     e->head_classes = 0;
     FX_CUDA(e, cudaMalloc(&e->head_w, sizeof(float) * kEmbed * num_classes));
@@ -604,10 +601,12 @@ int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, in
 
 // Host-buffer path, pipelined over FX_HOST_SLOTS slots: the H2D copy of a batch (copy stream) overlaps the kernels
 // of the earlier ones (two lane streams); the D2H of the embeddings follows the kernels on the lane's stream.
-int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
-                        float* emb_host) {
+// emb_host: rows are copied back to the host (fx_embed_host_async); emb_dev_out: rows are written straight to that device
+// address, e.g. the rank's slot of an all-gather buffer (fx_embed_host_async_dev).  Exactly one of them is given.
+static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
+                             float* emb_host, float* emb_dev_out) {
     if (!e) return FX_ERR_INVALID;
-    if (slot < 0 || slot >= FX_HOST_SLOTS || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || !emb_host)))
+    if (slot < 0 || slot >= FX_HOST_SLOTS || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || (!emb_host && !emb_dev_out))))
         return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: bad arguments");
     for (int i = 0; i < n; ++i) {
         const size_t need = descs[i].offset + (size_t)descs[i].height * descs[i].width * descs[i].channels;
@@ -643,14 +642,25 @@ int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t t
     FX_CUDA(e, cudaStreamWaitEvent(s, hs.copied, 0));
     const int caller_lane = e->cur_lane;  // the caller's selection is restored afterwards
     int rc = select_lane(e, lane);
-    if (rc == FX_OK) rc = fx_embed(e, hs.src_dev, descs, n, hs.emb_dev, s);
+    if (rc == FX_OK) rc = fx_embed(e, hs.src_dev, descs, n, emb_dev_out ? emb_dev_out : hs.emb_dev, s);
     const int rc2 = select_lane(e, caller_lane);
     if (rc != FX_OK) return rc;
     if (rc2 != FX_OK) return rc2;
-    FX_CUDA(e, cudaMemcpyAsync(emb_host, hs.emb_dev, sizeof(float) * kEmbed * n, cudaMemcpyDeviceToHost, s));
+    if (!emb_dev_out) FX_CUDA(e, cudaMemcpyAsync(emb_host, hs.emb_dev, sizeof(float) * kEmbed * n, cudaMemcpyDeviceToHost, s));
     FX_CUDA(e, cudaEventRecord(hs.done, s));
     hs.busy = true;
     return FX_OK;
+}
+
+int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
+                        float* emb_host) {
+    return embed_host_submit(e, slot, src_host, total_bytes, descs, n, emb_host, nullptr);
+}
+
+int fx_embed_host_async_dev(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
+                            float* emb_dev) {
+    if (e && n > 0 && !emb_dev) return set_error(e, FX_ERR_INVALID, "fx_embed_host_async_dev: null output");
+    return embed_host_submit(e, slot, src_host, total_bytes, descs, n, nullptr, emb_dev);
 }
 
 int fx_embed_host_wait(fx_handle e, int slot) {

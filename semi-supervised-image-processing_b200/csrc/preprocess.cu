@@ -100,6 +100,7 @@ int crop_offset(int size) {
 //   [.., +224*ksv)      vertical taps
 constexpr int kGeomHdr = 4 * kCrop;
 constexpr int kMaxTmpRows = 48;
+constexpr size_t kGeomCacheCap = 2048;  // distinct (height, width) coefficient tables kept on the device (about 10-60 KB each)
 constexpr int kS2dPairs = kCrop / 2 + 1;  // 113 s2d row pairs carry data; a band is 8 or 16 of them (the last one more)
 constexpr int kS2dVtRows = 34;           // output rows of the largest band (17 pairs)
 constexpr int kS2dThreads = 128;  // one thread per s2d column X = 1 .. 113
@@ -943,6 +944,18 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     if (e->capturing) return set_error(e, FX_ERR_STATE, "preprocess: descriptor upload inside a graph capture");
     plan.valid = false;
     plan.serial++;
+    // The coefficient tables are cached per (height, width, transform) and a ragged dataset can hold any number of
+    // sizes: once the cache is full it is dropped as a whole (the tables of running kernels and of the other lane's
+    // plan go with it, hence the device-wide wait and the invalidated plans) and refills from this batch on.
+    if (e->geoms.size() > kGeomCacheCap) {
+        FX_CUDA(e, cudaDeviceSynchronize());
+        for (auto& kv : e->geoms) cudaFree(kv.second.dev);
+        e->geoms.clear();
+        for (auto& p : e->pre_plan) {
+            p.valid = false;
+            p.serial++;
+        }
+    }
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
     int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
     bool all_s2d = mode == PreOut::IN0_BF16 && !e->pre_force_banded && e->norm_fma_ok;  // every image can take the column-walk kernel

@@ -73,6 +73,32 @@ def allgather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([gathered[r * cap : r * cap + c] for r, c in enumerate(counts_host)], dim=0)
 
 
+def allgather_inplace(buf: torch.Tensor, cap: int, count: int, group=None) -> Tuple[torch.Tensor, List[int]]:
+    """The all-gather of SURVEY.md 8e without staging copies.  `buf` is [world * cap, D] on every rank and this rank's
+    `count` (<= cap) rows already sit at buf[rank * cap : rank * cap + count] -- the trunk's last kernel wrote them there.
+    ONE collective moves the payload: on NCCL it runs in place (send buffer = receive buffer + rank * cap rows, which is
+    NCCL's in-place all-gather).  Returns (matrix [sum(counts), D], counts): a view of `buf` when the shards are full
+    (always, unless files failed to decode), else the compacted rows in rank order."""
+    rank, size = world()
+    if buf.dim() != 2 or buf.shape[0] != size * cap or not buf.is_contiguous() or not 0 <= count <= cap:
+        raise ValueError("allgather_inplace: buf must be a contiguous [world * cap, D] tensor and 0 <= count <= cap")
+    if size == 1:
+        return buf[:count], [count]
+    counts = torch.zeros(size, dtype=torch.int64, device=buf.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([count], dtype=torch.int64, device=buf.device), group=group)
+    counts_host = [int(c) for c in counts.cpu()]
+    if cap > 0 and max(counts_host) > 0:
+        mine = buf[rank * cap : (rank + 1) * cap]
+        if dist.get_backend(group) != "nccl":
+            mine = mine.clone()  # only NCCL documents the aliased form
+        dist.all_gather_into_tensor(buf, mine, group=group)
+    total = sum(counts_host)
+    last = max((r for r, c in enumerate(counts_host) if c), default=-1)
+    if all(c == cap for c in counts_host[:last]):  # every shard before the last non-empty one is full: rows are contiguous
+        return buf[:total], counts_host
+    return torch.cat([buf[r * cap : r * cap + c] for r, c in enumerate(counts_host)], dim=0), counts_host
+
+
 def allgather_objects(obj, group=None) -> List:
     """Small host-side metadata (kept record indices, failure paths, timings)."""
     _, size = world()

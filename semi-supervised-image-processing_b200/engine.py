@@ -244,8 +244,10 @@ class Engine:
         q = np.ascontiguousarray(np.asarray(query_rows, dtype=np.int64))
         nbr = np.empty(q.size, np.int64)
         sim = np.empty(q.size, np.float32)
-        self._check(self._lib.fx_neighbor_probe(self._h, x.data_ptr(), n, d, q.ctypes.data, int(q.size), nbr.ctypes.data, sim.ctypes.data,
-                                                self._stream()))
+        for lo in range(0, q.size, 32):  # fx_neighbor_probe keeps at most 32 queries in shared memory per pass
+            qc, nc, sc = q[lo : lo + 32], nbr[lo : lo + 32], sim[lo : lo + 32]
+            self._check(self._lib.fx_neighbor_probe(self._h, x.data_ptr(), n, d, qc.ctypes.data, int(qc.size), nc.ctypes.data,
+                                                    sc.ctypes.data, self._stream()))
         return nbr, sim
 
     # -- whole path ---------------------------------------------------------------------------
@@ -278,6 +280,15 @@ class Engine:
         dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
         self._slot_keep[slot] = (packed_host, descs, out)  # the library reads/writes them until the wait
         self._check(self._lib.fx_embed_host_async(self._h, slot, src_ptr, total_bytes, descs, n, dst_ptr))
+
+    def embed_host_async_dev(self, slot: int, packed_host, descs, n: int, total_bytes: int, out_dev: torch.Tensor) -> None:
+        """embed_host_async with the rows left on the device: written straight at `out_dev` (a contiguous fp32 CUDA view
+        with room for [n,512], e.g. this rank's slot of the all-gather buffer); no device->host copy."""
+        if out_dev.dtype != torch.float32 or not out_dev.is_cuda or not out_dev.is_contiguous() or out_dev.numel() < n * N.EMBED_DIM:
+            raise TypeError("out_dev must be a contiguous fp32 CUDA tensor with room for [n,512]")
+        src_ptr = packed_host.data_ptr() if isinstance(packed_host, torch.Tensor) else packed_host.ctypes.data
+        self._slot_keep[slot] = (packed_host, descs, out_dev)
+        self._check(self._lib.fx_embed_host_async_dev(self._h, slot, src_ptr, total_bytes, descs, n, out_dev.data_ptr()))
 
     def embed_host_wait(self, slot: int) -> None:
         self._check(self._lib.fx_embed_host_wait(self._h, slot))

@@ -4,8 +4,9 @@ the hot path on hand-written sm_100a CUDA (libfx_b200.so) instead of stock PyTor
 Same CLI (``--data-dir --device --batch-size --verbose``, src/feature_extraction.py:510-535), same
 importable names and the same five artifacts under ``outputs/``:
 
-    python -m ssip_b200.feature_extraction --data-dir mri_dataset_brain_cancer_oc --device cuda
-    torchrun --nproc-per-node 8 -m ssip_b200.feature_extraction --device cuda      # image-sharded
+    python -m ssip_b200.feature_extraction --data-dir mri_dataset_brain_cancer_oc --device cuda    # every visible GPU
+    python -m ssip_b200.feature_extraction --device cuda:3                                         # that GPU only
+    torchrun --nproc-per-node 8 -m ssip_b200.feature_extraction --device cuda      # the same sharding under torchrun
 
 What changes underneath: files are still decoded by Pillow on the host (a thread pool instead of
 a serial loop), but Resize(256)/CenterCrop(224)/ToTensor/Normalize is one fused CUDA kernel that
@@ -39,7 +40,7 @@ from PIL import Image, UnidentifiedImageError
 
 from . import _artifacts
 from . import _native as N
-from ._decode_pool import DecodePool
+from ._decode_pool import DecodePool, host_resize_if_oversized, rebuild_exception
 from . import dist as fxdist
 from .engine import Engine, pack_images
 
@@ -74,6 +75,8 @@ WEIGHTS_ENV = "SSIP_B200_WEIGHTS"
 PRECISION_ENV = "SSIP_B200_PRECISION"
 GRAY_CARRIAGE_ENV = "SSIP_B200_GRAY_CARRIAGE"  # "1": ship R==G==B files as one plane
 DECODE_THREADS_ENV = "SSIP_B200_DECODE_THREADS"
+SINGLE_GPU_ENV = "SSIP_B200_SINGLE_GPU"  # "1": `--device cuda` stays on the current GPU even if several are visible
+ALL_RANKS_HOST_ENV = "SSIP_B200_ALL_RANKS_HOST"  # "1": under torchrun every rank (not only rank 0) gets the host matrix
 DECODE_MODE_ENV = "SSIP_B200_DECODE"  # "process" | "thread" | "auto" (default: worker processes from 512 files up)
 
 
@@ -91,7 +94,7 @@ class ImageRecord:
 class ExtractionResults:
     """What extract_embeddings returns (fields as src/feature_extraction.py:95-102)."""
 
-    embeddings: np.ndarray
+    embeddings: np.ndarray  # host fp32 [N_ok,512]; under torchrun on rank 0 only (None elsewhere, see ALL_RANKS_HOST_ENV)
     records: List[ImageRecord]
     failures: List[Path]
     per_file_times: List[float]
@@ -261,7 +264,7 @@ class _CudaTransform:
             return eng.preprocess_nchw(dev, descs, len(arrays))
 
     def __call__(self, img: Image.Image) -> torch.Tensor:
-        return self.batch([_decoded_array(img)])[0].cpu()
+        return self.batch([_decoded_array(host_resize_if_oversized(img))])[0].cpu()
 
     def __repr__(self) -> str:
         return (f"FusedCudaTransform(Resize({TARGET_RESIZE}), CenterCrop({TARGET_CROP}), ToTensor(), "
@@ -316,7 +319,7 @@ def _load_file(path: Path):
     """Decode one file on a pool thread -> HWC uint8 array, or the exception to report."""
     try:
         with Image.open(path) as img:
-            arr = _decoded_array(img)
+            arr = _decoded_array(host_resize_if_oversized(img))
             if os.environ.get(GRAY_CARRIAGE_ENV) == "1" and (arr[..., 0] == arr[..., 1]).all() and (arr[..., 1] == arr[..., 2]).all():
                 arr = np.ascontiguousarray(arr[..., 0])
             return arr
@@ -353,8 +356,10 @@ def _unpin(t: Optional[torch.Tensor]) -> None:
         t._fx_pinned = False  # type: ignore[attr-defined]
 
 
-def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int):
-    """Single-GPU pass over `records`: embeddings + bookkeeping.
+def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int, sink: Optional[torch.Tensor] = None):
+    """Single-GPU pass over `records`: embeddings + bookkeeping.  With `sink` (a contiguous fp32 CUDA view with room for
+    [len(records), 512]: this rank's slot of the all-gather buffer) the rows stay on the device -- the trunk's last
+    kernel writes row i of the kept records at sink[i] -- and the returned matrix is None.
 
     Pipeline slots (fx_embed_host_async, N.HOST_SLOTS of them): while the GPU works on earlier batches (two at a
     time, one per engine lane), the host decodes the next one into a free pinned staging buffer and its H2D copy
@@ -367,7 +372,8 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
     threads = int(os.environ.get(DECODE_THREADS_ENV, "0")) or min(32, (os.cpu_count() or 8))
     nslots = N.HOST_SLOTS
     staging: List[Optional[torch.Tensor]] = [None] * nslots
-    outs = [torch.empty((batch_size, 512), dtype=torch.float32).pin_memory() for _ in range(nslots)]
+    outs = [torch.empty((batch_size, 512), dtype=torch.float32).pin_memory() for _ in range(nslots)] if sink is None else []
+    written = 0  # rows already placed in `sink`
     pending: List[Optional[Tuple[List[int], int]]] = [None] * nslots  # per slot: (record indices, n)
     t_last = time.perf_counter()
 
@@ -377,7 +383,8 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
             return
         ok, n = pending[slot]
         eng.embed_host_wait(slot)
-        blocks.append(outs[slot][:n].numpy().copy())
+        if sink is None:
+            blocks.append(outs[slot][:n].numpy().copy())
         kept.extend(ok)
         now = time.perf_counter()
         times.extend([(now - t_last) / n] * n)  # batch wall time / successes, as src/feature_extraction.py:297-300
@@ -417,8 +424,8 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
         jobs, ok, off = [], [], 0
         for k, (rec, m) in enumerate(zip(chunk, metas)):
             if isinstance(m[0], str):  # failure triple (kind, exception name, text)
-                if m[0] != "decode":
-                    raise RuntimeError(f"{m[1]} while opening {rec.absolute_path}: {m[2]}")
+                if m[0] != "decode":  # not one of the two the reference tolerates: same exception class as thread mode
+                    raise rebuild_exception(m[1], m[2])
                 fail(rec, m[2])
                 continue
             h, w, bands, pil_mode = m
@@ -440,7 +447,7 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
         for job, idx, res in zip(jobs, ok, done):
             if not isinstance(res, int):  # pixel data broken although the header parsed
                 if res[0] != "decode":
-                    raise RuntimeError(f"{res[1]} while decoding {job[0]}: {res[2]}")
+                    raise rebuild_exception(res[1], res[2])
                 fail(records[idx], res[2])
                 continue
             descs[n].offset, descs[n].height, descs[n].width, descs[n].channels = job[1], job[2], job[3], res
@@ -458,12 +465,23 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
                 if staged is None:
                     continue
                 descs, n_ok, total, ok = staged
-                eng.embed_host_async(slot, staging[slot], descs, n_ok, total, outs[slot])
+                if sink is None:
+                    eng.embed_host_async(slot, staging[slot], descs, n_ok, total, outs[slot])
+                else:
+                    eng.embed_host_async_dev(slot, staging[slot], descs, n_ok, total, sink[written : written + n_ok])
+                    written += n_ok
                 pending[slot] = (ok, n_ok)
                 slot = (slot + 1) % nslots
             for k in range(nslots):  # oldest first
                 finish((slot + k) % nslots)
     finally:
+        # an exception above (channel-policy error, worker error, unsupported geometry) can leave up to HOST_SLOTS
+        # batches in flight: their DMA reads staging[slot] and writes outs[slot], so drain before releasing either
+        for k in range(nslots):
+            try:
+                eng.embed_host_wait(k)
+            except Exception:  # noqa: BLE001 - the original exception is the one to report
+                pass
         if use_procs:
             for k in range(nslots):
                 _unpin(staging[k])
@@ -471,6 +489,9 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
                 pool_cm.release(k)
         else:
             pool_cm.shutdown(wait=True)
+    if sink is not None:  # batches were submitted, and their rows placed, in record order
+        assert kept == sorted(kept) and len(kept) == written
+        return None, kept, failures, times
     order = np.argsort(np.asarray(kept, dtype=np.int64), kind="stable") if kept else np.zeros(0, np.int64)
     local = np.concatenate(blocks, axis=0)[order] if blocks else np.empty((0, 512), np.float32)
     kept = [kept[i] for i in order]
@@ -481,9 +502,10 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int)
 def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_size: int = BATCH_SIZE) -> ExtractionResults:
     """Feature extraction over `records` (signature of src/feature_extraction.py:251-255).
 
-    Under torchrun (WORLD_SIZE > 1) the records are sharded contiguously over the ranks, each rank
-    runs its shard on its own GPU, and one NCCL all-gather assembles [N,512]; every rank returns
-    the full result.  Row i of `embeddings` belongs to `records[i]` of the returned (kept) list.
+    With WORLD_SIZE > 1 (the workers `main` starts for ``--device cuda`` on a multi-GPU box, or torchrun) the records
+    are sharded contiguously over the ranks, each rank runs its shard on its own GPU writing its rows straight into its
+    slot of the gather buffer, and ONE in-place NCCL all-gather assembles [N,512] on every GPU (`device_embeddings`);
+    the host matrix `embeddings` is materialised on rank 0.  Row i belongs to `records[i]` of the returned (kept) list.
     """
     eng = get_engine(device, min_batch=batch_size)
     logging.info("Beginning feature extraction over %d records", len(records))
@@ -492,10 +514,35 @@ def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_s
         fxdist.bind_to_gpu_numa_node(eng.device_index)  # one rank per GPU: stay on that GPU's socket
     rank, size = fxdist.world()
     lo, hi = fxdist.shard_bounds(len(records), rank, size) if distributed else (0, len(records))
-    local, kept, failures, times = _extract_local(records[lo:hi], eng, batch_size)
+    error: Optional[BaseException] = None
+    gather_buf = sink = None
+    cap = 0
+    if distributed:
+        # one [R * ceil(N/R), 512] buffer per GPU; this rank's rows are written into its slot by the trunk
+        # itself, one in-place NCCL all-gather assembles the matrix, and only rank 0 copies it to the host
+        cap = fxdist.shard_bounds(len(records), 0, size)[1]
+        with torch.cuda.device(eng.device):
+            gather_buf = torch.empty((size * cap, 512), dtype=torch.float32, device=eng.device)
+        sink = gather_buf[rank * cap : (rank + 1) * cap]
+    try:
+        local, kept, failures, times = _extract_local(records[lo:hi], eng, batch_size, sink=sink)
+    except Exception as exc:  # noqa: BLE001 - re-raised below, after the other ranks have been told
+        if not distributed:
+            raise
+        error = exc
+    if distributed:
+        # a rank that failed (e.g. a channel-policy error in its shard) must not leave its peers waiting in the
+        # all-gather: exchange the outcome first, then every rank raises
+        outcomes = fxdist.allgather_objects(None if error is None else f"{type(error).__name__}: {error}")
+        if error is not None:
+            raise error
+        bad = [(r, o) for r, o in enumerate(outcomes) if o is not None]
+        if bad:
+            raise RuntimeError(f"feature extraction failed on rank {bad[0][0]}: {bad[0][1]}")
     kept = [lo + k for k in kept]
     if distributed:
-        full = fxdist.allgather_rows(local.to(eng.device))
+        with torch.cuda.device(eng.device):
+            full, _ = fxdist.allgather_inplace(gather_buf, cap, len(kept))
         meta = fxdist.allgather_objects((kept, failures, times))
         kept = fxdist.concat_in_rank_order([m[0] for m in meta])
         failures = fxdist.concat_in_rank_order([m[1] for m in meta])
@@ -504,8 +551,11 @@ def extract_embeddings(records: List[ImageRecord], device: torch.device, batch_s
         full = local
     if full.shape[0] == 0:
         raise RuntimeError("No embeddings were generated; all images failed to decode?")
-    matrix = full.cpu().numpy()
-    logging.info("Computed embeddings with shape %s", matrix.shape)
+    # the host copy of the gathered matrix is rank 0's job (it writes the artifacts); the other ranks keep the device
+    # tensor only, unless SSIP_B200_ALL_RANKS_HOST=1 asks for the reference's "numpy on every caller" everywhere
+    want_host = not distributed or rank == 0 or os.environ.get(ALL_RANKS_HOST_ENV) == "1"
+    matrix = full.cpu().numpy() if want_host else None
+    logging.info("Computed embeddings with shape %s", tuple(full.shape))
     return ExtractionResults(embeddings=matrix, records=[records[i] for i in kept], failures=failures, per_file_times=times,
                              device_embeddings=full if full.is_cuda else None)
 
@@ -665,9 +715,39 @@ def parse_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
     return parser.parse_args(argv)
 
 
+def _fan_out(argv: Optional[Sequence[str]], n_gpus: int) -> int:
+    """``--device cuda`` on a box with several visible GPUs = all of them (the reference's flag set is
+    unchanged, CUDA_VISIBLE_DEVICES restricts the set): start one worker process per GPU with the torchrun environment
+    (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*), each running this module's CLI with the same arguments; rank 0 writes the
+    artifacts.  The parent never touches CUDA.  Returns the first non-zero worker exit code (0 if all succeeded)."""
+    import socket
+    import subprocess
+    import sys
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:  # a free rendezvous port
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    args = list(sys.argv[1:] if argv is None else argv)
+    root = str(Path(__file__).resolve().parent.parent)  # where the `ssip_b200` alias lives
+    pythonpath = os.pathsep.join(x for x in (root, os.environ.get("PYTHONPATH", "")) if x)
+    procs = []
+    for r in range(n_gpus):
+        env = dict(os.environ, PYTHONPATH=pythonpath, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(n_gpus), LOCAL_WORLD_SIZE=str(n_gpus),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-m", "ssip_b200.feature_extraction", *map(str, args)], env=env))
+    codes = [p.wait() for p in procs]
+    return next((c for c in codes if c), 0)
+
+
 def main(argv: Optional[Sequence[str]] = None) -> None:
     args = parse_args(argv)
     rank, size, _ = fxdist.env_world()
+    if (size == 1 and args.device == "cuda" and os.environ.get(SINGLE_GPU_ENV) != "1" and torch.cuda.is_available()
+            and torch.cuda.device_count() > 1):
+        rc = _fan_out(argv, torch.cuda.device_count())
+        if rc:
+            raise SystemExit(rc)
+        return
     if rank == 0:
         configure_logging(verbose=args.verbose)
     else:  # only rank 0 owns the log file and the artifacts

@@ -214,6 +214,13 @@ def test_process_decode_pool_gives_the_same_result_as_threads(dataset, tmp_path,
     b = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=6)
     assert np.array_equal(a.embeddings, b.embeddings)
     assert [r.relative_path for r in a.records] == [r.relative_path for r in b.records]
+    # ... and both are the reference's rows: the oracle port on the very same files (JPEG included)
+    ref = _oracle(records, 6)
+    assert [r.relative_path for r in b.records] == [r.relative_path for r in ref.records]
+    assert sorted(p.name for p in ref.failures) == ["b_truncated.jpg", "zz_broken.png"]
+    rel = np.linalg.norm(b.embeddings - ref.embeddings, axis=1) / np.linalg.norm(ref.embeddings, axis=1)
+    cos = (b.embeddings * ref.embeddings).sum(1) / (np.linalg.norm(b.embeddings, axis=1) * np.linalg.norm(ref.embeddings, axis=1))
+    assert rel.max() <= 1e-2 and cos.min() >= 0.999, (rel.max(), cos.min())
     assert sorted(p.name for p in a.failures) == sorted(p.name for p in b.failures) == ["b_truncated.jpg", "zz_broken.png"]
     monkeypatch.setenv(fx.GRAY_CARRIAGE_ENV, "1")  # R==G==B files travel as one plane: same embeddings
     c = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=6)
@@ -222,3 +229,35 @@ def test_process_decode_pool_gives_the_same_result_as_threads(dataset, tmp_path,
     Image.fromarray(imgs[1][..., 0]).save(full / "sans_label" / "c_gray.png")  # true mode "L": the reference raises
     with pytest.raises(RuntimeError, match="broadcast shape"):
         fx.extract_embeddings(fx.discover_image_records(full), torch.device("cuda:0"), batch_size=6)
+
+
+def test_real_mri_files_match_the_reference_goldens(golden_dir, monkeypatch):
+    """16 JPEGs of the reference's own dataset (tests/golden/mri_real, minted by make_golden_mri.py from
+    the unmodified src.feature_extraction): the fused transform is bit-exact on every file, the embeddings are within
+    BASELINE.json's tolerance of the reference's, in bf16 and in the tight mode, with thread and process decode."""
+    import hashlib
+
+    g = np.load(golden_dir / "mri_real_golden.npz")
+    records = fx.discover_image_records(golden_dir / "mri_real")
+    assert [str(r.relative_path) for r in records] == g["paths"].tolist()
+    transform = fx.build_transform()
+    for r, pre in zip(records, g["pre_sha256"]):
+        t = fx.preprocess_image(r.absolute_path, transform)
+        assert hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest() == str(pre)
+    want = g["emb_randbn"]  # weights_env: random-bn:1234
+
+    def check(res, tol, cos_tol):
+        assert not res.failures and [r.relative_path for r in res.records] == [r.relative_path for r in records]
+        rel = np.linalg.norm(res.embeddings - want, axis=1) / np.linalg.norm(want, axis=1)
+        cos = (res.embeddings * want).sum(1) / (np.linalg.norm(res.embeddings, axis=1) * np.linalg.norm(want, axis=1))
+        assert rel.max() <= tol and cos.min() >= cos_tol, (rel.max(), cos.min())
+
+    a = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=5)
+    check(a, 1e-2, 0.999)
+    monkeypatch.setenv(fx.DECODE_MODE_ENV, "process")
+    monkeypatch.setenv(fx.DECODE_THREADS_ENV, "4")
+    b = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=16)
+    assert np.array_equal(a.embeddings, b.embeddings)
+    monkeypatch.setenv(fx.DECODE_MODE_ENV, "thread")
+    monkeypatch.setenv(fx.PRECISION_ENV, "fp32")
+    check(fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=8), 1e-5, 0.999999)

@@ -250,6 +250,21 @@ assert kept == [0, 1, 2, 3, 4, 5, 6, 7, 8], kept
 assert torch.equal(full, rows[kept]), (full.shape,)
 empty = fxdist.allgather_rows(torch.zeros((0, 512)))
 assert empty.shape == (0, 512)
+# the in-place form the drop-in uses: every rank's rows already sit in its slot of one [size * cap, D] buffer
+cap = fxdist.shard_bounds(n, 0, size)[1]
+for drop in (0, 2):  # full shards (result is a view of the buffer), then two decode failures on rank 0 (compaction)
+    buf = torch.full((size * cap, 512), float("nan"))
+    mine = rows[lo:hi]
+    if rank == 0 and drop:
+        mine = mine[:-drop]
+    buf[rank * cap : rank * cap + mine.shape[0]] = mine
+    full, counts = fxdist.allgather_inplace(buf, cap, mine.shape[0])
+    want_counts = [cap - drop, n - cap]
+    assert counts == want_counts, counts
+    want_rows = list(range(0, cap - drop)) + list(range(cap, n))
+    assert torch.equal(full, rows[want_rows]), (drop, full.shape)
+    if not drop:
+        assert full.data_ptr() == buf.data_ptr()  # no copy when the shards are full
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()
 sys.stdout.write("rank %d ok\n" % rank); sys.stdout.flush()

@@ -183,3 +183,32 @@ def test_head_port_matches_reference_golden(golden_dir):
     got = rp.port_generate_pseudo_labels(model, [(a, p) for a, _, p in loader], torch.device("cpu"), float(g["pseudo_threshold"]))
     assert [p for p, _, _ in got] == g["pseudo_paths"].tolist()
     assert [l for _, l, _ in got] == g["pseudo_labels"].tolist()
+
+
+# ---- real MRI files: fixture minted by tests/golden/make_golden_mri.py from the real reference ----
+
+
+def mri_real_records(golden_dir):
+    """The 16 committed JPEGs of the reference's own dataset in discover_image_records order (= the fixture's row order)."""
+    from ssip_b200.feature_extraction import discover_image_records
+
+    g = np.load(golden_dir / "mri_real_golden.npz")
+    records = discover_image_records(golden_dir / "mri_real")
+    assert [str(r.relative_path) for r in records] == g["paths"].tolist()
+    return g, records
+
+
+def test_real_mri_fixture_pins_decode_transform_and_port(golden_dir):
+    g, records = mri_real_records(golden_dir)
+    assert len(records) == 16 and {r.label for r in records} == {"cancer", "normal", None}
+    for r, pix, pre in zip(records, g["pixels_sha256"], g["pre_sha256"]):
+        with Image.open(r.absolute_path) as img:
+            arr = np.ascontiguousarray(np.asarray(img))
+        assert arr.shape == (512, 512, 3)
+        assert hashlib.sha256(arr.tobytes()).hexdigest() == str(pix)  # same libjpeg decode as in the build container
+        assert hashlib.sha256(rp.c_preprocess_rgb(arr).tobytes()).hexdigest() == str(pre)  # C restatement == reference transform
+    port = [rp.PortRecord(r.absolute_path, r.relative_path, r.bucket, r.label) for r in records]
+    for key, randbn in (("emb_default", False), ("emb_randbn", True)):
+        got = rp.port_extract_embeddings(port, torch.device("cpu"), batch_size=5, randomize_bn=randbn).embeddings
+        rel = np.linalg.norm(got - g[key], axis=1) / np.linalg.norm(g[key], axis=1)
+        assert rel.max() <= 1e-6, (key, rel.max())  # same torch build; oneDNN may pick another kernel on another CPU
