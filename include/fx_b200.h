@@ -214,6 +214,58 @@ int fx_embed_host_async_dev(fx_handle h, int slot, const uint8_t *src_host, size
                             const fx_image_desc *descs_host, int n, float *emb_dev);
 
 /*
+ * ---- GPU JPEG decode feeding the preprocess kernel ----
+ * Replaces `Image.open(path)` + Pillow's libjpeg decode inside the reference's serial loop
+ * (src/feature_extraction.py:238, 276-284) for baseline 8-bit three-component JPEGs with a complete bitstream: nvJPEG
+ * (hardware JPEG engines when available, else its CUDA decoder; loaded with dlopen at fx_jpeg_init) decodes a whole batch
+ * straight into the device image buffer the preprocess kernel reads.  Every other file is reported as FX_FILE_HOST_DECODE
+ * and must be decoded by the caller with the reference's own Pillow call, which keeps the per-file
+ * (UnidentifiedImageError, OSError) semantics of :281-284.  NOT bit-exact against libjpeg-turbo (IDCT / chroma
+ * up-sampling differ; measured in profiles/r02_nvjpeg_tolerance.md): opt-in, the host decode pool is the default.
+ */
+#define FX_JPEG_BACKEND_AUTO 0     /* hardware engines if the handle can be created for them, else the CUDA decoder */
+#define FX_JPEG_BACKEND_HARDWARE 1 /* NVJPEG_BACKEND_HARDWARE */
+#define FX_JPEG_BACKEND_GPU 2      /* NVJPEG_BACKEND_GPU_HYBRID */
+
+#define FX_FILE_GPU_JPEG 0    /* read into the slot's bitstream buffer, will be decoded on the GPU */
+#define FX_FILE_HOST_DECODE 1 /* readable, but not a JPEG this path takes: the caller decodes it (or reports its failure) */
+#define FX_FILE_UNREADABLE 2  /* stat/open/read failed: the caller's own open() reports the reference's error */
+
+typedef struct fx_file_info {
+    int32_t status; /* FX_FILE_* */
+    int32_t height, width, components;
+    int32_t subsampling; /* nvjpegChromaSubsampling_t value, -1 unknown */
+    int32_t encoding;    /* SOF marker: 0xC0 baseline, 0xC2 progressive, ... */
+    int32_t precision;   /* bits per sample */
+    int32_t reserved;
+    uint64_t offset, length; /* position / size of the bitstream in the slot's page-locked buffer */
+} fx_file_info;
+
+/* Load nvJPEG and create the decoder for `backend` (idempotent; FX_ERR_UNSUPPORTED when nvJPEG cannot be had). */
+int fx_jpeg_init(fx_handle h, int backend);
+/* FX_JPEG_BACKEND_HARDWARE / _GPU the decoder runs on, FX_JPEG_BACKEND_AUTO (0) before fx_jpeg_init. */
+int fx_jpeg_backend(fx_handle h);
+/* Frame header + eligibility of one bitstream in host memory (no decode). */
+int fx_jpeg_probe(fx_handle h, const uint8_t *data, size_t length, fx_file_info *info);
+/* Read the n files of one batch into slot `slot`'s page-locked bitstream buffer with a native thread pool
+ * (FX_IO_THREADS, default 8) and fill info[i].  Waits for the slot's previous batch first. */
+int fx_jpeg_read_files(fx_handle h, int slot, const char *const *paths, int n, fx_file_info *info);
+/* Decode n bitstreams (host memory) to interleaved RGB at dst_dev + descs[i].offset (pitch = width * 3) on `stream`;
+ * synchronises the stream before returning.  Test / study entry point. */
+int fx_jpeg_decode(fx_handle h, const uint8_t *const *data, const size_t *lengths, int n, uint8_t *dst_dev,
+                   const fx_image_desc *descs, void *stream);
+/*
+ * One pipelined step (as fx_embed_host_async / _dev) over the files last read into `slot` by fx_jpeg_read_files:
+ * entries with info[i].status == FX_FILE_GPU_JPEG are decoded by nvJPEG, for the others host_pixels[i] holds the
+ * caller-decoded HWC uint8 pixels; descs lays the decoded images out in the slot's device buffer (total_bytes).
+ * `info` / `descs` list only the files that take part (failures already dropped), in row order.  Exactly one of
+ * emb_host (rows copied back) / emb_dev (rows left on the device) is non-NULL.  FX_ERR_UNSUPPORTED when nvJPEG rejects
+ * the batch: nothing was queued, re-submit the batch host-decoded.  Pair with fx_embed_host_wait(slot).
+ */
+int fx_embed_files_async(fx_handle h, int slot, const fx_file_info *info, const uint8_t *const *host_pixels,
+                         const fx_image_desc *descs, int n, size_t total_bytes, float *emb_host, float *emb_dev);
+
+/*
  * ---- on-device post-processing of an [n][d] fp32 embedding matrix ----
  * At N = 1M the reference's numpy / scikit-learn post-processing scans 2 GB on the host several times; these are the
  * same reductions as single HBM-bound passes over the (gathered) device buffer.  d <= 4096.  Column statistics

@@ -23,11 +23,14 @@ MAX_LANES = 2
 MAX_CLASSES = 32
 TRANSFORM_EXTRACT, TRANSFORM_SQUARE224 = 0, 1
 HOST_SLOTS = 4
+JPEG_BACKEND_AUTO, JPEG_BACKEND_HARDWARE, JPEG_BACKEND_GPU = 0, 1, 2
+FILE_GPU_JPEG, FILE_HOST_DECODE, FILE_UNREADABLE = 0, 1, 2
 
 # every symbol include/fx_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "fx_version", "fx_abi_version", "fx_last_error", "fx_create", "fx_destroy", "fx_load_weights",
     "fx_preprocess_nchw_f32", "fx_preprocess", "fx_forward", "fx_stage_nchw_f32", "fx_select_lane", "fx_set_transform", "fx_load_head", "fx_classify", "fx_embed", "fx_embed_host", "fx_embed_host_async", "fx_embed_host_async_dev", "fx_embed_host_wait",
+    "fx_jpeg_init", "fx_jpeg_backend", "fx_jpeg_probe", "fx_jpeg_read_files", "fx_jpeg_decode", "fx_embed_files_async",
     "fx_column_stats", "fx_standardize", "fx_neighbor_probe", "fx_launch_count", "fx_profile_enable", "fx_profile_read", "fx_debug_conv", "fx_debug_folded", "fx_debug_tma_probe", "fx_debug_umma_shift", "fx_debug_stem_pool", "fx_debug_mma_rate", "fx_debug_staging",
     "fx_host_resized_size", "fx_host_crop_offset", "fx_host_coeffs",
 )
@@ -44,6 +47,11 @@ class FxError(RuntimeError):
 
 class ImageDesc(ctypes.Structure):
     _fields_ = [("offset", c_uint64), ("height", c_int32), ("width", c_int32), ("channels", c_int32), ("reserved", c_int32)]
+
+
+class FileInfo(ctypes.Structure):
+    _fields_ = [("status", c_int32), ("height", c_int32), ("width", c_int32), ("components", c_int32), ("subsampling", c_int32),
+                ("encoding", c_int32), ("precision", c_int32), ("reserved", c_int32), ("offset", c_uint64), ("length", c_uint64)]
 
 
 class MatrixStats(ctypes.Structure):
@@ -93,6 +101,12 @@ def lib() -> ctypes.CDLL:
     L.fx_embed_host_async.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(ImageDesc), c_int, c_void_p]
     L.fx_embed_host_async_dev.argtypes = [c_void_p, c_int, c_void_p, c_size_t, POINTER(ImageDesc), c_int, c_void_p]
     L.fx_embed_host_wait.argtypes = [c_void_p, c_int]
+    L.fx_jpeg_init.argtypes = [c_void_p, c_int]
+    L.fx_jpeg_backend.argtypes = [c_void_p]
+    L.fx_jpeg_probe.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(FileInfo)]
+    L.fx_jpeg_read_files.argtypes = [c_void_p, c_int, POINTER(c_char_p), c_int, POINTER(FileInfo)]
+    L.fx_jpeg_decode.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_int, c_void_p, POINTER(ImageDesc), c_void_p]
+    L.fx_embed_files_async.argtypes = [c_void_p, c_int, POINTER(FileInfo), POINTER(c_void_p), POINTER(ImageDesc), c_int, c_size_t, c_void_p, c_void_p]
     L.fx_column_stats.argtypes = [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p, c_void_p, POINTER(MatrixStats), c_void_p]
     L.fx_standardize.argtypes = [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.fx_neighbor_probe.argtypes = [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]

@@ -696,226 +696,6 @@ int tc_encode_map(fx_engine* e, CUtensorMap* m, const void* base, int rank, cons
     return FX_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// EXPERIMENTAL, OFF BY DEFAULT (FX_TC4=1): the CTA-pair kernel on clusters of FOUR for the L2 -> SM bound 3x3 / stride-1
-// layers with Cout >= 256.  Pairs (0,1) and (2,3) of a cluster work on the same N tile and on adjacent M
-// pair tiles; every CTA fetches only a QUARTER of the weight K-block and multicasts it to the CTA of the same rank in both
-// pairs, so a CTA receives 16 KB (A) + 16 KB (B) per K-block but the cluster reads B from L2 once instead of twice.
-// A producer writes into the other pair's stage, hence `empty` = both pairs are done with it (two multicast commits).
-// Written without access to a GPU: compiled (the PTX forms assemble), not yet run -- enable and test before trusting it.
-// ------------------------------------------------------------------------------------------
-template <int BN, int BK, int STAGES>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kTcThreads, 1)
-tc4_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bq, const TcConvParams p) {
-    constexpr int kA = 128 * BK * 2, kB = (BN / 2) * BK * 2;
-    extern __shared__ uint8_t smem_raw[];
-    pdl_launch_dependents();
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sA = sbase, sB = sbase + STAGES * kA;
-    const uint32_t bars = sB + STAGES * kB;
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
-    const uint32_t tslot = tempty0 + 16;
-    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
-    float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) bias_s[i] = __ldg(p.bias + i);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank4 = cluster_ctarank();
-    const uint32_t rank = rank4 & 1, pr = rank4 >> 1;  // CTA within its pair, pair within the cluster
-    const bool leader = rank == 0;
-    const int quad = blockIdx.x >> 2, n_quads = gridDim.x >> 2;
-    constexpr uint32_t kTmemCols = 2 * BN;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a);
-        tma_prefetch_desc(&map_bq);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(full0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
-            mbar_init(empty0 + 8 * i, 2);  // one multicast commit from EACH pair's leader
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(tfull0 + 8 * i, 1);                        // multicast commit of this pair's leader
-            mbar_init(tempty0 + 8 * i, 2 * (kTcThreads - 128));  // every epilogue thread of both CTAs of the pair
-        }
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc_2cta(tslot, kTmemCols);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tslot_ptr;
-    pdl_wait();
-
-    const int num_kb = p.kh * p.kw * p.cchunks;
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
-    const int m_quads = (((m_tiles + 1) >> 1) + 1) >> 1;
-    const int n_units = m_quads * p.n_tiles_n;  // unit u: N tile u % n_tiles_n, M pair tiles 2 * (u / n_tiles_n) + {0, 1}
-
-    if (warp == 0) {
-        // ===== TMA producer (all four CTAs): own 128 A rows + a quarter of the weight K-block, multicast to both pairs =====
-        if (elect_one_sync()) {
-            const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));
-            uint32_t stage = 0, phase = 0;
-            for (int u = quad; u < n_units; u += n_quads) {
-                const int n_tile = u % p.n_tiles_n;
-                int m_tile = (2 * (u / p.n_tiles_n) + (int)pr) * 2 + (int)rank;
-                const int tw = m_tile % p.tiles_w;
-                m_tile /= p.tiles_w;
-                const int th = m_tile % p.tiles_h;
-                const int tg = m_tile / p.tiles_h;  // >= tiles_g for the leftovers: every load is out of bounds -> zeros
-                const int w0 = (tw << p.wt_log2) * p.cw_mul - p.pad_w;
-                const int h0 = (th << p.ht_log2) * p.ch_mul - p.pad_h;
-                const int n0 = tg << p.nt_log2;
-                int kb = 0;
-                for (int r = 0; r < p.kh; ++r)
-                    for (int s = 0; s < p.kw; ++s)
-                        for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
-                            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                            if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * (kA + kB));
-                            tma_load_4d_2cta(sA + stage * kA, &map_a, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            tma_load_2d_2cta_multicast(sB + stage * kB + pr * (kB / 2), &map_bq, full0 + 8 * stage, kb * BK,
-                                                       n_tile * BN + (int)rank * (BN / 2) + (int)pr * (BN / 4), mc_mask);
-                            if (!leader) mbar_arrive_leader(full0 + 8 * stage);
-                            if (++stage == STAGES) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
-                        }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (the leader of each pair) =====
-        if (leader) {
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-            constexpr uint64_t desc_hi = make_smem_desc<BK>(0) & 0xFFFFFFFF00000000ull;
-            const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));
-            uint32_t stage = 0, phase = 0;
-            int it = 0;
-            for (int u = quad; u < n_units; u += n_quads, ++it) {
-                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-                mbar_wait(tempty0 + 8 * as, aphase ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);
-                    tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint32_t a_lo = (sA + stage * kA) >> 4, b_lo = (sB + stage * kB) >> 4;
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, (kb | k) != 0);
-                        umma_commit_2cta_mask(empty0 + 8 * stage, 0xF);  // the stage is free once BOTH pairs have read it
-                        if (kb == num_kb - 1) umma_commit_2cta_mask(tfull0 + 8 * as, pair_mask);
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue (all four CTAs): own 128 accumulator rows -> (+bias, +residual, ReLU) -> global =====
-        const int q = warp & 3;
-        const int cg = (warp - 4) >> 2;
-        const int row = q * 32 + lane;
-        const int wl = row & ((1 << p.wt_log2) - 1);
-        const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
-        const int nl = row >> (p.wt_log2 + p.ht_log2);
-        constexpr int cpg = BN / 4, nci = cpg / 16;
-        const int ch0 = cg * cpg;
-        int it = 0;
-        for (int u = quad; u < n_units; u += n_quads, ++it) {
-            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int n_tile = u % p.n_tiles_n;
-            int m_tile = (2 * (u / p.n_tiles_n) + (int)pr) * 2 + (int)rank;
-            const int tw = m_tile % p.tiles_w;
-            m_tile /= p.tiles_w;
-            const int th = m_tile % p.tiles_h;
-            const int tg = m_tile / p.tiles_h;
-            const int ow = (tw << p.wt_log2) + wl, oh = (th << p.ht_log2) + hl, img = (tg << p.nt_log2) + nl;
-            const bool valid = ow < p.wo && oh < p.ho && img < p.batch;
-            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
-            const size_t obase = pix * p.cout + (size_t)n_tile * BN;
-            uint4 res[BN / 32];
-            const bool has_res = valid && p.residual != nullptr;
-            if (has_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + ch0);
-#pragma unroll
-                for (int j = 0; j < BN / 32; ++j) res[j] = __ldg(rp + j);
-            }
-            mbar_wait(tfull0 + 8 * as, aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-            for (int ci = 0; ci < nci; ++ci) {
-                const int c0 = ch0 + ci * 16;
-                uint32_t v[16];
-                tmem_ld16(taddr + ch0 + ci * 16, v);
-                tmem_ld_wait();
-                if (valid) {
-                    float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(bias_s + n_tile * BN + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b = bp[j];
-                        f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-                    }
-                    if (has_res) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint4 rv = res[ci * 2 + j];
-                            const unsigned uu[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                f[8 * j + 2 * k] += __uint_as_float(uu[k] << 16);
-                                f[8 * j + 2 * k + 1] += __uint_as_float(uu[k] & 0xffff0000u);
-                            }
-                        }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (p.out_f32) {
-                        float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint4 o;
-                            unsigned* ou = &o.x;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
-                                ou[k] = *reinterpret_cast<const unsigned*>(&h2);
-                            }
-                            op[j] = o;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive_leader(tempty0 + 8 * as);
-        }
-    }
-
-    tc_fence_before();
-    cluster_sync_all();  // peers' shared memory / barriers stay alive until all four CTAs are done
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc_2cta(tmem_base, kTmemCols);
-    }
-}
-
 template <int BN, int BK, int STAGES>
 static int launch_tc(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const TcConvParams& p,
                      cudaStream_t stream) {
@@ -956,23 +736,6 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma
     if (const char* dbg = getenv("FX_DEBUG_TC_PAIRS")) pairs = std::max(1, std::min(pairs, atoi(dbg)));  // fabric experiments only
     FX_CUDA(e, launch_pdl(tc2_conv_kernel<BN, BK, STAGES, RESB>, dim3(2 * pairs), dim3(kTcThreads), kSmem, stream, ma, ma1, mb, mb2, mbh, p));  // cluster dims are a kernel attribute
     FX_LAUNCH_CHECK(e, "tc2_conv_kernel");
-    return FX_OK;
-}
-
-// FX_TC4=1: the experimental 4-CTA-cluster kernel (weight K-blocks multicast to two pairs) for plain Cout % 256 == 0 launches.
-template <int BN, int BK, int STAGES>
-static int launch_tc4(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& mbq, const TcConvParams& p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (128 * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4;
-    static bool attr_done[256] = {};  // per device ordinal
-    if (!attr_done[e->device & 255]) {
-        FX_CUDA(e, cudaFuncSetAttribute(tc4_conv_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        attr_done[e->device & 255] = true;
-    }
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
-    const int n_units = ((((m_tiles + 1) / 2) + 1) / 2) * p.n_tiles_n;
-    const int quads = std::max(1, std::min(n_units, e->sm_count / 4));
-    FX_CUDA(e, launch_pdl(tc4_conv_kernel<BN, BK, STAGES>, dim3(4 * quads), dim3(kTcThreads), kSmem, stream, ma, mbq, p));  // cluster dims are a kernel attribute
-    FX_LAUNCH_CHECK(e, "tc4_conv_kernel");
     return FX_OK;
 }
 
@@ -1118,14 +881,10 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
             if (resb_on && p.n_tiles_n == 1 && n_res <= kResKb) return launch_tc2<128, 64, 6, true>(e, ma, ma1, mb, mb2, mbh, p, stream);
             return launch_tc2<128, 64, 8>(e, ma, ma1, mb, mb2, mbh, p, stream);
         }
-        default: {
-            static const bool tc4_on = [] {
-                const char* v = getenv("FX_TC4");
-                return v && v[0] == '1';
-            }();
-            if (tc4_on && !ds && !p.s2planes && g.stride == 1) return launch_tc4<256, 64, 6>(e, ma, mbh, p, stream);  // mbh: {64, BN/4} boxes
+        default:
+            // (a 4-CTA-cluster variant with the weight K-blocks multicast to two pairs was measured on B200 in round 2:
+            // byte-identical rows, 64 us instead of 47.5 us per layer3 / layer4 launch -- removed)
             return launch_tc2<256, 64, 6>(e, ma, ma1, mb, mb2, mbh, p, stream);
-        }
     }
 }
 

@@ -306,6 +306,7 @@ void fx_destroy(fx_handle e) {
     for (auto& L : e->layers) free_layer(L);
     preprocess_free(e);
     tc_free(e);
+    jpeg_free(e);
     lane_store(e);
     for (auto& ln : e->lanes) {
         cudaFree(ln.in0);
@@ -601,19 +602,15 @@ int fx_embed(fx_handle e, const uint8_t* src_dev, const fx_image_desc* descs, in
 
 // Host-buffer path, pipelined over FX_HOST_SLOTS slots: the H2D copy of a batch (copy stream) overlaps the kernels
 // of the earlier ones (two lane streams); the D2H of the embeddings follows the kernels on the lane's stream.
-// emb_host: rows are copied back to the host (fx_embed_host_async); emb_dev_out: rows are written straight to that device
-// address, e.g. the rank's slot of an all-gather buffer (fx_embed_host_async_dev).  Exactly one of them is given.
-static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
-                             float* emb_host, float* emb_dev_out) {
-    if (!e) return FX_ERR_INVALID;
-    if (slot < 0 || slot >= FX_HOST_SLOTS || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || (!emb_host && !emb_dev_out))))
-        return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: bad arguments");
-    for (int i = 0; i < n; ++i) {
-        const size_t need = descs[i].offset + (size_t)descs[i].height * descs[i].width * descs[i].channels;
-        if (descs[i].height < 1 || descs[i].width < 1 || need > total_bytes)
-            return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: image " + std::to_string(i) + " lies outside the buffer");
-    }
-    FX_CUDA(e, cudaSetDevice(e->device));
+}  // extern "C"
+
+namespace fx {
+
+// The two halves of a pipelined host-buffer step, shared by fx_embed_host_async* (engine.cu) and fx_embed_files_async
+// (decode.cu).  prepare: the slot's events / device buffers exist, its previous batch is finished, src_dev holds
+// `total_bytes`.  The caller then fills hs.src_dev on e->copy_stream and records hs.copied.  compute: the lane's stream
+// waits for hs.copied, runs preprocess + trunk, and either copies the rows to emb_host or leaves them at emb_dev_out.
+int embed_slot_prepare(fx_engine* e, int slot, size_t total_bytes) {
     fx_engine::HostSlot& hs = e->slots[slot];
     if (!hs.copied) {
         FX_CUDA(e, cudaEventCreateWithFlags(&hs.copied, cudaEventDisableTiming));
@@ -624,7 +621,6 @@ static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, siz
         FX_CUDA(e, cudaEventSynchronize(hs.done));
         hs.busy = false;
     }
-    if (n == 0) return FX_OK;
     if (total_bytes > hs.cap) {
         cudaFree(hs.src_dev);
         hs.src_dev = nullptr;
@@ -634,8 +630,11 @@ static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, siz
         if (a != cudaSuccess) return set_error(e, FX_ERR_NOMEM, std::string("cudaMalloc(h2d staging): ") + cudaGetErrorString(a));
         hs.cap = cap;
     }
-    FX_CUDA(e, cudaMemcpyAsync(hs.src_dev, src_host, total_bytes, cudaMemcpyHostToDevice, e->copy_stream));
-    FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
+    return FX_OK;
+}
+
+int embed_slot_compute(fx_engine* e, int slot, const fx_image_desc* descs, int n, float* emb_host, float* emb_dev_out) {
+    fx_engine::HostSlot& hs = e->slots[slot];
     const int lane = slot % FX_MAX_LANES;
     if (!e->lane_stream[lane]) FX_CUDA(e, cudaStreamCreateWithFlags(&e->lane_stream[lane], cudaStreamNonBlocking));
     cudaStream_t s = e->lane_stream[lane];
@@ -650,6 +649,31 @@ static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, siz
     FX_CUDA(e, cudaEventRecord(hs.done, s));
     hs.busy = true;
     return FX_OK;
+}
+
+}  // namespace fx
+
+extern "C" {
+
+// emb_host: rows are copied back to the host (fx_embed_host_async); emb_dev_out: rows are written straight to that device
+// address, e.g. the rank's slot of an all-gather buffer (fx_embed_host_async_dev).  Exactly one of them is given.
+static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,
+                             float* emb_host, float* emb_dev_out) {
+    if (!e) return FX_ERR_INVALID;
+    if (slot < 0 || slot >= FX_HOST_SLOTS || n < 0 || n > e->max_batch || (n > 0 && (!src_host || !descs || (!emb_host && !emb_dev_out))))
+        return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: bad arguments");
+    for (int i = 0; i < n; ++i) {
+        const size_t need = descs[i].offset + (size_t)descs[i].height * descs[i].width * descs[i].channels;
+        if (descs[i].height < 1 || descs[i].width < 1 || need > total_bytes)
+            return set_error(e, FX_ERR_INVALID, "fx_embed_host_async: image " + std::to_string(i) + " lies outside the buffer");
+    }
+    FX_CUDA(e, cudaSetDevice(e->device));
+    int rc = embed_slot_prepare(e, slot, total_bytes);
+    if (rc != FX_OK || n == 0) return rc;
+    fx_engine::HostSlot& hs = e->slots[slot];
+    FX_CUDA(e, cudaMemcpyAsync(hs.src_dev, src_host, total_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
+    return embed_slot_compute(e, slot, descs, n, emb_host, emb_dev_out);
 }
 
 int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,

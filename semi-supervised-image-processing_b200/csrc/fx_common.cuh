@@ -183,6 +183,7 @@ struct fx_engine {
     float* head_w = nullptr;  // [head_classes][512]
     float* head_b = nullptr;
     int head_classes = 0;
+    void* jpeg_state = nullptr;  // nvJPEG decode context (decode.cu), created by fx_jpeg_init
     cudaStream_t lane_stream[FX_MAX_LANES] = {};  // kernels + D2H of the host-buffer path, one per lane
     cudaStream_t copy_stream = nullptr;           // H2D of the host-buffer path
 };
@@ -268,6 +269,9 @@ int post_standardize(fx_engine* e, const float* x, long long n, int d, const dou
                      cudaStream_t stream);
 int post_neighbor_probe(fx_engine* e, const float* x, long long n, int d, const int64_t* qidx_host, int q, int64_t* nbr_host,
                         float* sim_host, cudaStream_t stream);
+
+// decode.cu (GPU JPEG decode feeding the preprocess kernel)
+void jpeg_free(fx_engine* e);
 
 // conv_tc.cu (bf16 tcgen05 implicit-GEMM path)
 int tc_init(fx_engine* e);

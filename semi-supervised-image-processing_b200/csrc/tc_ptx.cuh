@@ -210,19 +210,6 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// the same load, delivered to this offset in every CTA of `cta_mask` (bytes counted on each destination pair's leader)
-__device__ __forceinline__ void tma_load_2d_2cta_multicast(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
-        :
-        : "r"(dst), "l"(desc), "r"(bar & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1)
-        : "memory");
-}
-// arrive (once the issued MMAs retire) on the barrier at this offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_2cta_mask(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
-                 : "memory");
-}
 // arrive (once the issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

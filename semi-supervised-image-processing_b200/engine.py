@@ -294,6 +294,55 @@ class Engine:
         self._check(self._lib.fx_embed_host_wait(self._h, slot))
         self._slot_keep.pop(slot, None)
 
+    # -- GPU JPEG decode ---------------------------------------------------
+    _JPEG_BACKENDS = {"auto": N.JPEG_BACKEND_AUTO, "hardware": N.JPEG_BACKEND_HARDWARE, "gpu": N.JPEG_BACKEND_GPU}
+
+    def jpeg_init(self, backend: str = "auto") -> str:
+        """Load nvJPEG and create the batched decoder (fx_jpeg_init); returns the backend it runs on ("hardware" | "gpu").
+        Raises FxError (FX_ERR_UNSUPPORTED) when nvJPEG cannot be had."""
+        self._check(self._lib.fx_jpeg_init(self._h, self._JPEG_BACKENDS[backend]))
+        return {N.JPEG_BACKEND_HARDWARE: "hardware", N.JPEG_BACKEND_GPU: "gpu"}[int(self._lib.fx_jpeg_backend(self._h))]
+
+    def jpeg_probe(self, data: bytes) -> "N.FileInfo":
+        info = N.FileInfo()
+        buf = (ctypes.c_char * len(data)).from_buffer_copy(data)
+        self._check(self._lib.fx_jpeg_probe(self._h, ctypes.addressof(buf), len(data), ctypes.byref(info)))
+        return info
+
+    def jpeg_read_files(self, slot: int, paths: Sequence[str]):
+        """Read one batch of files into the slot's page-locked bitstream buffer with the library's thread pool; returns
+        the fx_file_info array (status: N.FILE_GPU_JPEG | N.FILE_HOST_DECODE | N.FILE_UNREADABLE, geometry)."""
+        n = len(paths)
+        arr = (ctypes.c_char_p * max(n, 1))(*[p.encode() if isinstance(p, str) else bytes(p) for p in paths])
+        info = (N.FileInfo * max(n, 1))()
+        self._check(self._lib.fx_jpeg_read_files(self._h, slot, arr, n, info))
+        return info
+
+    def jpeg_decode(self, blobs: Sequence[bytes], sizes: Sequence[Tuple[int, int]]) -> List[torch.Tensor]:
+        """Decode JPEG bitstreams on the GPU (nvJPEG) -> list of uint8 CUDA tensors [h,w,3].  Test / study entry point."""
+        n = len(blobs)
+        descs = (N.ImageDesc * max(n, 1))()
+        off = 0
+        for i, (h, w) in enumerate(sizes):
+            descs[i].offset, descs[i].height, descs[i].width, descs[i].channels = off, h, w, 3
+            off += (h * w * 3 + 255) // 256 * 256
+        out = torch.empty(max(off, 1), dtype=torch.uint8, device=self.device)
+        keep = [(ctypes.c_char * len(b)).from_buffer_copy(b) for b in blobs]
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[ctypes.addressof(k) for k in keep])
+        lens = (ctypes.c_size_t * max(n, 1))(*[len(b) for b in blobs])
+        self._check(self._lib.fx_jpeg_decode(self._h, ptrs, lens, n, out.data_ptr(), descs, self._stream()))
+        return [out[descs[i].offset : descs[i].offset + h * w * 3].view(h, w, 3) for i, (h, w) in enumerate(sizes)]
+
+    def embed_files_async(self, slot: int, info, host_pixels: Sequence[Optional[np.ndarray]], descs, n: int, total_bytes: int, out) -> None:
+        """One pipelined step over the files last read into `slot` (jpeg_read_files): info / descs list the n files that
+        take part, host_pixels[i] is the caller-decoded array of an entry that is not N.FILE_GPU_JPEG (else None).
+        `out`: pinned host tensor / array for the rows, or a CUDA tensor to leave them on the device."""
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[(a.ctypes.data if a is not None else None) for a in host_pixels])
+        on_dev = isinstance(out, torch.Tensor) and out.is_cuda
+        dst = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        self._slot_keep[slot] = (info, host_pixels, descs, out, ptrs)
+        self._check(self._lib.fx_embed_files_async(self._h, slot, info, ptrs, descs, n, total_bytes, None if on_dev else dst, dst if on_dev else None))
+
     def embed_images(self, images: Sequence[np.ndarray]) -> np.ndarray:
         """Convenience: list of decoded HWC uint8 arrays -> [n,512] (chunks of max_batch)."""
         chunks = []

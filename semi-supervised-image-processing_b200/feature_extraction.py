@@ -40,7 +40,7 @@ from PIL import Image, UnidentifiedImageError
 
 from . import _artifacts
 from . import _native as N
-from ._decode_pool import DecodePool, host_resize_if_oversized, rebuild_exception
+from ._decode_pool import HOST_RESIZE_SHORT_SIDE, DecodePool, host_resize_if_oversized, rebuild_exception
 from . import dist as fxdist
 from .engine import Engine, pack_images
 
@@ -77,7 +77,8 @@ GRAY_CARRIAGE_ENV = "SSIP_B200_GRAY_CARRIAGE"  # "1": ship R==G==B files as one 
 DECODE_THREADS_ENV = "SSIP_B200_DECODE_THREADS"
 SINGLE_GPU_ENV = "SSIP_B200_SINGLE_GPU"  # "1": `--device cuda` stays on the current GPU even if several are visible
 ALL_RANKS_HOST_ENV = "SSIP_B200_ALL_RANKS_HOST"  # "1": under torchrun every rank (not only rank 0) gets the host matrix
-DECODE_MODE_ENV = "SSIP_B200_DECODE"  # "process" | "thread" | "auto" (default: worker processes from 512 files up)
+DECODE_MODE_ENV = "SSIP_B200_DECODE"  # "process" | "thread" | "nvjpeg" | "auto" (default: worker processes from 512 files up)
+JPEG_BACKEND_ENV = "SSIP_B200_NVJPEG_BACKEND"  # "auto" | "hardware" | "gpu": which nvJPEG decoder SSIP_B200_DECODE=nvjpeg uses
 
 
 @dataclass(frozen=True)
@@ -392,6 +393,10 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int,
         pending[slot] = None
 
     mode = os.environ.get(DECODE_MODE_ENV, "auto")
+    use_nvjpeg = mode == "nvjpeg"
+    if use_nvjpeg:
+        backend = eng.jpeg_init(os.environ.get(JPEG_BACKEND_ENV, "auto"))  # FxError if nvJPEG cannot be had: no silent fallback
+        logging.info("JPEG files are decoded on the GPU (nvJPEG, %s backend); everything else by Pillow on the host", backend)
     use_procs = mode == "process" or (mode == "auto" and len(records) >= 512)
     gray = os.environ.get(GRAY_CARRIAGE_ENV) == "1"
 
@@ -417,6 +422,45 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int,
             staging[slot] = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8).pin_memory()
         _, descs, total = pack_images(arrays, out=staging[slot].numpy())
         return descs, len(arrays), total, ok
+
+    def stage_with_nvjpeg(pool, chunk, lo, slot):
+        """SURVEY.md 8f rank 1, GPU option: the library reads the batch's files into the slot's page-locked bitstream
+        buffer (native threads) and nvJPEG decodes the baseline RGB JPEGs among them straight into the device image buffer;
+        every other file (and every JPEG the frame header or the missing end-of-image marker makes doubtful) takes the
+        reference's own Pillow call on a pool thread, with the reference's failure handling."""
+        finish(slot)  # the slot's bitstream buffer and decoder state are free once its previous batch is out
+        info = eng.jpeg_read_files(slot, [str(r.absolute_path) for r in chunk])
+        on_gpu = [info[k].status == N.FILE_GPU_JPEG and min(info[k].height, info[k].width) <= HOST_RESIZE_SHORT_SIDE for k in range(len(chunk))]
+        host_idx = [k for k, g in enumerate(on_gpu) if not g]
+        host = dict(zip(host_idx, pool.map(_load_file, [chunk[k].absolute_path for k in host_idx]))) if host_idx else {}
+        take, pixels, ok, shapes = [], [], [], []
+        for k, rec in enumerate(chunk):
+            if on_gpu[k]:
+                take.append(k)
+                pixels.append(None)
+                shapes.append((info[k].height, info[k].width, 3))
+            else:
+                item = host[k]
+                if isinstance(item, BaseException):
+                    fail(rec, str(item))
+                    continue
+                take.append(k)
+                pixels.append(np.ascontiguousarray(item))
+                shapes.append((item.shape[0], item.shape[1], 1 if item.ndim == 2 else item.shape[2]))
+            ok.append(lo + k)
+        if not take:
+            return None
+        n = len(take)
+        sel = (N.FileInfo * n)()
+        descs = (N.ImageDesc * n)()
+        off = 0
+        for j, (k, (h, w, c)) in enumerate(zip(take, shapes)):
+            sel[j] = info[k]
+            if pixels[j] is not None:
+                sel[j].status = N.FILE_HOST_DECODE
+            descs[j].offset, descs[j].height, descs[j].width, descs[j].channels = off, h, w, c
+            off += (h * w * c + 255) // 256 * 256
+        return (sel, pixels), descs, n, off, ok
 
     def stage_with_processes(pool: DecodePool, chunk, lo, slot):
         """Header pass -> layout -> worker processes decode straight into the slot's shared, page-locked buffer."""
@@ -455,21 +499,49 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int,
             n += 1
         return (descs, n, off, kept_idx) if n else None
 
+    use_procs = use_procs and not use_nvjpeg
     pool_cm = _process_pool(threads, nslots) if use_procs else ThreadPoolExecutor(max_workers=threads)
-    stage = stage_with_processes if use_procs else stage_with_threads
+    stage = stage_with_nvjpeg if use_nvjpeg else (stage_with_processes if use_procs else stage_with_threads)
+
+    def submit(slot, descs, n_ok, total, files=None):
+        nonlocal written
+        out = outs[slot] if sink is None else sink[written : written + n_ok]
+        if files is not None:
+            eng.embed_files_async(slot, files[0], files[1], descs, n_ok, total, out)
+        elif sink is None:
+            eng.embed_host_async(slot, staging[slot], descs, n_ok, total, out)
+        else:
+            eng.embed_host_async_dev(slot, staging[slot], descs, n_ok, total, out)
+        written += n_ok
+
     try:
         with torch.cuda.device(eng.device):
             slot = 0
             for lo in range(0, len(records), batch_size):
-                staged = stage(pool_cm, records[lo : lo + batch_size], lo, slot)
+                chunk = records[lo : lo + batch_size]
+                mark = len(failures)
+                staged = stage(pool_cm, chunk, lo, slot)
                 if staged is None:
                     continue
-                descs, n_ok, total, ok = staged
-                if sink is None:
-                    eng.embed_host_async(slot, staging[slot], descs, n_ok, total, outs[slot])
+                if use_nvjpeg:
+                    files, descs, n_ok, total, ok = staged
+                    try:
+                        submit(slot, descs, n_ok, total, files)
+                    except N.FxError as exc:
+                        if exc.status != N.FX_ERR_UNSUPPORTED:
+                            raise
+                        # nvJPEG turned the batch down (a bitstream the header walk could not fault; nothing was queued):
+                        # redo the whole batch with Pillow on the host, bookkeeping included
+                        logging.warning("nvJPEG rejected a batch (%s): decoding it on the host", exc.text)
+                        del failures[mark:]
+                        staged = stage_with_threads(pool_cm, chunk, lo, slot)
+                        if staged is None:
+                            continue
+                        descs, n_ok, total, ok = staged
+                        submit(slot, descs, n_ok, total)
                 else:
-                    eng.embed_host_async_dev(slot, staging[slot], descs, n_ok, total, sink[written : written + n_ok])
-                    written += n_ok
+                    descs, n_ok, total, ok = staged
+                    submit(slot, descs, n_ok, total)
                 pending[slot] = (ok, n_ok)
                 slot = (slot + 1) % nslots
             for k in range(nslots):  # oldest first
