@@ -317,7 +317,9 @@ int fx_profile_read(fx_handle h, float *ms, int capacity);
  * to fp32.  Synchronises `stream` before returning.
  */
 int fx_debug_conv(fx_handle h, const fx_conv_bn *layer, int hin, int win, const float *in_dev,
-                  const float *residual_dev, int n, int relu, float *out_dev, void *stream);
+                  const float *residual_dev, int n, int relu /* bit 0: ReLU; bit 1 (BF16 engines, cin % 64 == 0): write the
+                  fp32 accumulator itself instead of its bf16 rounding, through the per-tap kernel */,
+                  float *out_dev, void *stream);
 
 /* The fused stem: conv1 7x7/s2 + folded bn1 + ReLU + 3x3/s2/p1 max-pool in ONE tcgen05 kernel
  * (torchvision/models/resnet.py:197-200,268-271).  in_dev fp32 NHWC [n][224][224][3] (normalised),

@@ -758,8 +758,10 @@ int fx_profile_read(fx_handle e, float* ms, int capacity) {
 // ---- test / inspection entry points -------------------------------------------------------
 
 int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const float* in_dev, const float* residual_dev, int n,
-                  int relu, float* out_dev, void* stream_) {
+                  int relu_flags, float* out_dev, void* stream_) {
     if (!e) return FX_ERR_INVALID;
+    const int relu = relu_flags & 1;
+    const bool f32_out = (relu_flags & 2) != 0 && e->precision == FX_PRECISION_BF16 && layer && layer->cin != 3;
     if (!layer || !in_dev || !out_dev || n < 1 || n > e->max_batch) return set_error(e, FX_ERR_INVALID, "fx_debug_conv: bad arguments");
     FX_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -803,6 +805,11 @@ int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const 
             in_act = bin;
         }
         if (residual_dev && (rc = f32_to_bf16(e, residual_dev, bres, out_count, stream)) != FX_OK) break;
+        if (f32_out) {  // the accumulator itself (+bias, +residual, ReLU), not rounded to bf16: tensor-core accumulation probe
+            rc = tc_conv_packed(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, nullptr, out_dev, n, relu,
+                                stream);
+            break;
+        }
         if (flat_supported(L.g))
             rc = flat_conv(e, L, static_cast<const __nv_bfloat16*>(in_act), residual_dev ? bres : nullptr, bout, n, relu, false, stream);
         else

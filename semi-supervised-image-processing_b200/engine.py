@@ -365,8 +365,9 @@ class Engine:
         return raw, v
 
     def debug_conv(self, weight: torch.Tensor, bn: Optional[Dict[str, torch.Tensor]], stride: int, pad: int,
-                   x_nhwc: torch.Tensor, residual_nhwc: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
-        """Run one conv+bn group through the library: x fp32 NHWC CUDA -> fp32 NHWC CUDA."""
+                   x_nhwc: torch.Tensor, residual_nhwc: Optional[torch.Tensor] = None, relu: bool = False, f32_out: bool = False) -> torch.Tensor:
+        """Run one conv+bn group through the library: x fp32 NHWC CUDA -> fp32 NHWC CUDA.  f32_out (bf16 engines): the
+        fp32 accumulator (+bias, +residual, ReLU) itself instead of its bf16 rounding."""
         cout, cin, kh, kw = (int(v) for v in weight.shape)
         n, hin, win, _ = (int(v) for v in x_nhwc.shape)
         keep = []
@@ -389,7 +390,7 @@ class Engine:
         x = x_nhwc.contiguous()
         r = residual_nhwc.contiguous() if residual_nhwc is not None else None
         self._check(self._lib.fx_debug_conv(self._h, ctypes.byref(e), hin, win, x.data_ptr(), r.data_ptr() if r is not None else None,
-                                            n, int(relu), out.data_ptr(), self._stream()))
+                                            n, int(relu) | (2 if f32_out else 0), out.data_ptr(), self._stream()))
         return out
 
     def debug_stem_pool(self, weight: torch.Tensor, bn: Dict[str, torch.Tensor], x_nhwc: torch.Tensor) -> torch.Tensor:
