@@ -757,7 +757,7 @@ void tc_free(fx_engine* e) {
 }
 
 // Pick the power-of-two output box (Wt, Ht, Nt), Wt*Ht*Nt = 128, that wastes the fewest rows.
-static void choose_tile(int n, int ho, int wo, int& wt, int& ht, int& nt) {
+void choose_tile(int n, int ho, int wo, int& wt, int& ht, int& nt) {
     long long best = -1;
     for (int a = 0; a <= 7; ++a)
         for (int b = 0; a + b <= 7; ++b) {

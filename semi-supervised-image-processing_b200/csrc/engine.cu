@@ -49,9 +49,12 @@ static void free_layer(PackedLayer& L) {
     cudaFree(L.w_f32);
     cudaFree(L.w_bf16);
     cudaFree(L.bias);
+    cudaFree(L.w_h16);
+    cudaFree(L.w_l16);
     L.w_f32 = nullptr;
     L.w_bf16 = nullptr;
     L.bias = nullptr;
+    L.w_h16 = L.w_l16 = nullptr;
 }
 
 // Fold BN into the conv (fp64), reorder OIHW -> O,KH,KW,I, upload in the engine's precision.
@@ -99,6 +102,14 @@ static int pack_layer(fx_engine* e, const fx_conv_bn& src, int hin, int win, Pac
                 for (int i = 0; i < g.cin; ++i) w[((size_t)o * taps + t) * cp + i] = L.host_w[((size_t)o * taps + t) * g.cin + i];
         FX_CUDA(e, cudaMalloc(&L.w_f32, sizeof(float) * w.size()));
         FX_CUDA(e, cudaMemcpy(L.w_f32, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+        if (e->tight_tc && !stem && g.cin % 64 == 0 && g.cout % 64 == 0) {  // split fp16 pack for the tensor-core tight mode
+            std::vector<uint16_t> hi, lo;
+            L.w_scale_log2 = split_pack_weights(L.host_w, hi, lo);
+            FX_CUDA(e, cudaMalloc(&L.w_h16, 2 * hi.size()));
+            FX_CUDA(e, cudaMalloc(&L.w_l16, 2 * lo.size()));
+            FX_CUDA(e, cudaMemcpy(L.w_h16, hi.data(), 2 * hi.size(), cudaMemcpyHostToDevice));
+            FX_CUDA(e, cudaMemcpy(L.w_l16, lo.data(), 2 * lo.size(), cudaMemcpyHostToDevice));
+        }
         return FX_OK;
     }
     // bf16 GEMM-B pack [cout][K]
@@ -187,6 +198,36 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
         ProfScope ps(e, 0, stream);
         if ((rc = run_conv(e, 0, e->in0, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
         if ((rc = maxpool_3x3s2(e, B, A, n, 112, 112, 64, bf16, stream)) != FX_OK) return rc;
+    }
+    if (!bf16 && e->tight_tc) {
+        // Tight mode on the tensor cores (conv_split.cu): from here on activations are split fp16 (hi plane, lo plane:
+        // the bytes of the fp32 tensor).  X = block input, T = conv1 output, Y = block output / downsample branch.
+        const size_t pooled = (size_t)n * 56 * 56 * 64;
+        if ((rc = f32_to_split(e, static_cast<const float*>(A), C, pooled, stream)) != FX_OK) return rc;
+        void *X = C, *T = B, *Y = A;
+        int l = 1;
+        for (int stage = 0; stage < 4; ++stage)
+            for (int blk = 0; blk < 2; ++blk) {
+                const bool down = stage > 0 && blk == 0;
+                const bool last = stage == 3 && blk == 1;
+                auto conv = [&](int idx, const void* in, const void* res, void* out, float* out_f32, int relu) {
+                    ProfScope ps(e, idx, stream);
+                    return split_conv(e, e->layers[idx], in, res, out_f32 ? nullptr : out, out_f32, n, relu, stream);
+                };
+                if (!down) {
+                    if ((rc = conv(l, X, nullptr, T, nullptr, 1)) != FX_OK) return rc;
+                    if ((rc = conv(l + 1, T, X, Y, last ? e->final_f32 : nullptr, 1)) != FX_OK) return rc;
+                    std::swap(X, Y);
+                    l += 2;
+                } else {
+                    if ((rc = conv(l, X, nullptr, T, nullptr, 1)) != FX_OK) return rc;
+                    if ((rc = conv(l + 2, X, nullptr, Y, nullptr, 0)) != FX_OK) return rc;
+                    if ((rc = conv(l + 1, T, Y, X, nullptr, 1)) != FX_OK) return rc;  // X's old contents are dead once both readers ran
+                    l += 3;
+                }
+            }
+        ProfScope ps(e, kNumLayers, stream);
+        return avgpool_7x7(e, e->final_f32, false, emb, n, 49, kEmbed, stream);
     }
     // four stages of two BasicBlocks            (resnet.py:89-105, 273-276)
     int li = 1;
@@ -374,6 +415,7 @@ int fx_create(fx_handle* out, int device, int max_batch, int precision) {
     if ((err = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return fail(set_error(e, FX_ERR_CUDA, cudaGetErrorString(err)));
     if (const char* g = getenv("FX_GRAPHS")) e->graphs_on = g[0] != '0';
+    if (const char* g = getenv("FX_TIGHT_SIMT")) e->tight_tc = g[0] != '1';
     if (const char* g = getenv("FX_GRAPH_MAX_BATCH")) e->graph_max_batch = atoi(g);
     if ((rc = preprocess_init(e)) != FX_OK) return fail(rc);
     if ((rc = tc_init(e)) != FX_OK) return fail(rc);
@@ -793,7 +835,12 @@ int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const 
         if (!bf16) {
             if (stem)
                 rc = simt_conv(e, L, static_cast<const float*>(in_act), kIn0H, kIn0W, kIn0C, 0, residual_dev, out_dev, n, relu, stream);
-            else
+            else if (L.w_h16) {  // tight mode on the tensor cores: split the operands, run, join
+                if ((rc = f32_to_split(e, in_dev, e->act[0], in_count, stream)) != FX_OK) break;
+                if (residual_dev && (rc = f32_to_split(e, residual_dev, e->act[2], out_count, stream)) != FX_OK) break;
+                if ((rc = split_conv(e, L, e->act[0], residual_dev ? e->act[2] : nullptr, e->act[1], nullptr, n, relu, stream)) != FX_OK) break;
+                rc = split_to_f32(e, e->act[1], out_dev, out_count, stream);
+            } else
                 rc = simt_conv(e, L, in_dev, hin, win, g.cin, g.pad, residual_dev, out_dev, n, relu, stream);
             break;
         }

@@ -85,6 +85,10 @@ struct PackedLayer {
     __nv_bfloat16* w_bf16 = nullptr;
     float* bias = nullptr;
     int k_bf16 = 0;
+    // tight mode on the tensor cores (conv_split.cu): folded weights * 2^w_scale_log2 as fp16 hi / lo planes, [cout][K]
+    void* w_h16 = nullptr;
+    void* w_l16 = nullptr;
+    int w_scale_log2 = 0;
     std::vector<float> host_w;  // folded, [cout][kh][kw][cin] (bf16-rounded in BF16 precision)
     std::vector<float> host_b;
 };
@@ -121,6 +125,7 @@ struct fx_engine {
     float* final_f32 = nullptr;  // [max_batch][49][512]
     size_t act_bytes = 0;
     void* tc_state = nullptr;  // tcgen05 path: tensor maps etc. (conv_tc.cu)
+    bool tight_tc = true;      // FP32 precision: split-fp16 tensor-core convs (conv_split.cu); FX_TIGHT_SIMT=1 keeps the CUDA-core kernel
 
     // per-launch timing of fx_forward (fx_profile_*): event pairs for the 20 convs + avgpool
     bool prof_on = false;
@@ -279,6 +284,13 @@ void tc_free(fx_engine* e);
 // Runs layer `li` on NHWC bf16 activations.  out_f32 != nullptr: write fp32 instead of bf16.
 int tc_conv(fx_engine* e, int li, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
             float* out_f32, int n, int relu, cudaStream_t stream);
+
+// conv_split.cu (tight-tolerance mode on the tensor cores: split fp16 operands, register accumulation)
+int split_conv(fx_engine* e, const PackedLayer& L, const void* in, const void* residual, void* out, float* out_f32, int n, int relu,
+               cudaStream_t stream);
+int f32_to_split(fx_engine* e, const float* in, void* out_split, size_t count, cudaStream_t stream);
+int split_to_f32(fx_engine* e, const void* in_split, float* out, size_t count, cudaStream_t stream);
+int split_pack_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
 
 // conv_flat.cu (bf16 tcgen05 weight-stationary halo-tile path: stem, layer1, layer2 3x3/s1)
 bool flat_supported(const LayerGeom& g);

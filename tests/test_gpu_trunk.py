@@ -196,6 +196,35 @@ def test_conv_layer_fp32(eng_fp32, case):
     assert _rel(got, want) < 2e-6
 
 
+def test_tight_mode_cuda_core_kernel_stays_available_and_agrees(eng_fp32):
+    """FX_TIGHT_SIMT=1 (read at fx_create) keeps the fp32 CUDA-core convolution of round 1; the default tight mode runs the
+    split-fp16 tensor-core kernel (conv_split.cu).  Both are fp32-accurate: per layer within 2e-6 of the fp64 reference
+    and within 3e-6 of each other, at K = 576 and at K = 4608 (where a plain tensor-core accumulation is 4e-6 off)."""
+    os.environ["FX_TIGHT_SIMT"] = "1"
+    try:
+        simt = Engine(0, max_batch=64, precision="fp32")
+    finally:
+        os.environ.pop("FX_TIGHT_SIMT")
+    for case in (LAYER_CASES[1], LAYER_CASES[5], LAYER_CASES[10]):
+        cin, cout, k, stride, hin, n, residual, relu = case
+        n = min(n, 8)
+        w, bn, x = _case_tensors(cin, cout, k, hin, n, residual, seed=cin + cout + k + hin)
+        pad = k // 2
+        ho = (hin + 2 * pad - k) // stride + 1
+        res = torch.randn(n, ho, ho, cout, generator=torch.Generator().manual_seed(7)) if residual else None
+        a = simt.debug_conv(w, bn, stride, pad, x.cuda(), res.cuda() if res is not None else None, relu).cpu()
+        b = eng_fp32.debug_conv(w, bn, stride, pad, x.cuda(), res.cuda() if res is not None else None, relu).cpu()
+        want = _torch_conv(w, bn, x, stride, pad, res, relu, round_bf16=False)
+        assert _rel(a, want) < 2e-6 and _rel(b, want) < 2e-6 and _rel(a, b) < 3e-6, (case, _rel(a, want), _rel(b, want))
+    simt.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+    eng_fp32.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+    imgs = list(synthetic.noise_images(12, 224, 224, seed=5))
+    a, b = _embed(simt, imgs), _embed(eng_fp32, imgs)
+    rel = np.linalg.norm(a - b, axis=1) / np.linalg.norm(a, axis=1)
+    assert rel.max() < 5e-6, rel.max()
+    simt.close()
+
+
 # ---- whole path -----------------------------------------------------------------------------------
 
 

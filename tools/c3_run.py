@@ -7,7 +7,8 @@ on the gathered device matrix, artifacts written at scale.
 The plumbing is that of ssip_b200.feature_extraction.extract_embeddings under torchrun (same Engine calls, same
 dist.allgather_inplace, same post-processing and writers); only the per-file decode is replaced by a resident pool of
 decoded synthetic images, because 1 M PNG files (150 GB decoded) are not something the box can be handed:
-record i of the run is pool image (i * 7919) % POOL, copied host -> device for every batch like any decoded image.
+record i of the run is pool image i % POOL, copied host -> device for every batch like any decoded image (the pool is
+page-locked and carries its first batch again at the end, so every batch is one contiguous slice: no host-side packing).
 Checks: (a) a seeded sample of rows against the CPU port of the reference on the same images, (b) rows of records that
 map to the same pool image are bit-identical wherever (rank, batch, position) they were computed -- the size-independent
 determinism property of SURVEY.md 8e, (c) the device statistics against numpy on the host copy."""
@@ -29,7 +30,7 @@ from ssip_b200 import dist as fxdist  # noqa: E402
 from ssip_b200 import feature_extraction as fx  # noqa: E402
 from ssip_b200.engine import Engine, uniform_descs  # noqa: E402
 
-POOL, STRIDE, B, IMG = 4096, 7919, 512, 224 * 224 * 3
+POOL, B, IMG = 4096, 512, 224 * 224 * 3
 
 
 def main():
@@ -52,11 +53,11 @@ def main():
     eng = Engine(local, max_batch=B, precision="bf16")
     eng.load_state_dict(fx._seeded_backbone(1234, True).state_dict())
     rng = np.random.default_rng(99)  # the same pool on every rank
-    pool = torch.from_numpy(rng.integers(0, 256, (POOL, IMG), dtype=np.uint8)).pin_memory()
+    pool_np = rng.integers(0, 256, (POOL, IMG), dtype=np.uint8)
+    pool = torch.from_numpy(np.concatenate([pool_np, pool_np[:B]], axis=0)).pin_memory()  # + one batch of wrap-around
     gather_buf = torch.empty((size * cap, 512), dtype=torch.float32, device=dev)
     sink = gather_buf[rank * cap : (rank + 1) * cap]
     nslots = N.HOST_SLOTS
-    staging = [torch.empty(B * IMG, dtype=torch.uint8).pin_memory() for _ in range(nslots)]
     descs = {}
 
     def barrier():
@@ -65,19 +66,18 @@ def main():
         torch.cuda.synchronize()
 
     stages = {}
-    # ---- stage 1: the extraction loop (host gather of the batch -> H2D -> preprocess -> trunk -> rows in the gather slot) ----
+    # ---- stage 1: the extraction loop (H2D of the batch -> preprocess -> trunk -> rows in the rank's gather slot) ----
     barrier()
     t0 = time.perf_counter()
     written, slot = 0, 0
     for s in range(lo, hi, B):
         e = min(hi, s + B)
         k = e - s
-        idx = torch.from_numpy((np.arange(s, e, dtype=np.int64) * STRIDE) % POOL)
+        o = s % POOL
         eng.embed_host_wait(slot)
-        torch.index_select(pool, 0, idx, out=staging[slot][: k * IMG].view(k, IMG))  # the "decode": pack the batch's images
         if k not in descs:
             descs[k] = uniform_descs(k, 224, 224)
-        eng.embed_host_async_dev(slot, staging[slot], descs[k], k, k * IMG, sink[written : written + k])
+        eng.embed_host_async_dev(slot, pool[o : o + k].view(-1), descs[k], k, k * IMG, sink[written : written + k])
         written += k
         slot = (slot + 1) % nslots
     for k in range(nslots):
@@ -123,10 +123,10 @@ def main():
         work.mkdir(parents=True, exist_ok=True)
         t0 = time.perf_counter()
         _artifacts.write_npy(work / "embeddings.npy", full)
-        stages["embeddings.npy (2 GB) streamed device -> pinned -> file"] = time.perf_counter() - t0
+        stages[f"embeddings.npy ({n * 2048 / 1e9:.2f} GB) streamed device -> pinned -> file"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         _artifacts.write_embeddings_csv(work / "embeddings.csv", records)
-        stages["embeddings.csv (1 M rows)"] = time.perf_counter() - t0
+        stages[f"embeddings.csv ({n:,} rows)"] = time.perf_counter() - t0
         # ---- stage 5: the host copy the drop-in returns on rank 0 ----
         t0 = time.perf_counter()
         host = full.cpu().numpy()
@@ -136,13 +136,13 @@ def main():
 
         prng = np.random.default_rng(5)
         rows = np.sort(prng.choice(n, size=48, replace=False))
-        imgs = [pool[(int(i) * STRIDE) % POOL].numpy().reshape(224, 224, 3) for i in rows]
+        imgs = [pool[int(i) % POOL].numpy().reshape(224, 224, 3) for i in rows]
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // 2))
         want = rp.port_embed_arrays(imgs, seed=1234, randomize_bn=True)
         got = host[rows]
         rel = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
         cos = (got * want).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(want, axis=1))
-        # records i and i + POOL map to the same pool image (STRIDE is invertible mod POOL): rows must be bit-identical
+        # records i and i + POOL are the same pool image: their rows must be bit-identical
         reps = n // POOL
         dup_ok = all(bool(torch.equal(full[j * POOL : (j + 1) * POOL], full[:POOL])) for j in range(1, reps))
         tail_ok = bool(torch.equal(full[reps * POOL :], full[: n - reps * POOL]))
@@ -160,7 +160,7 @@ def main():
     if rank == 0:
         lines = [f"# C3: {n:,} synthetic 224x224 images on {size} x B200, batch {B}/GPU, in-place all-gather of [N,512]", "",
                  f"`torchrun --nproc-per-node {size} tools/c3_run.py --images {n}`; host cores {len(os.sched_getaffinity(0))} per rank after NUMA binding; "
-                 f"every record is a host -> device copy of 150,528 B (pool of {POOL} decoded images, record i = pool image (i * {STRIDE}) % {POOL}).", "",
+                 f"every record is a host -> device copy of 150,528 B (page-locked pool of {POOL} decoded images, record i = pool image i % {POOL}).", "",
                  "| stage | seconds |", "|---|---|"]
         for k, v in stages.items():
             lines.append(f"| {k} | {v:.3f} |")

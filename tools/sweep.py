@@ -1,5 +1,6 @@
 """BASELINE.json configs 4 and 5 as measurements (one GPU):
-  * C5: batch-size sweep 1..1024, bf16 (tcgen05) vs fp32 tight-tolerance mode: latency per batch and images/s,
+  * C5: batch-size sweep 1..1024, bf16 (tcgen05) vs fp32 tight-tolerance mode (split-fp16 tcgen05 convs with
+    register accumulation; FX_TIGHT_SIMT=1 for the CUDA-core kernel): latency per batch and images/s,
     device-resident inputs, CUDA events, 3 warm-ups, median of 10.
   * C4: 512x512 MRI-like gray sources (3 identical channels, and 1-channel gray carriage) -> 224: preprocess
     kernel GB/s (algorithmic bytes: source once + bf16 staging once) and end-to-end images/s.
@@ -43,7 +44,7 @@ print("| batch | bf16 ms | bf16 img/s | fp32 ms | fp32 img/s |")
 print("|---|---|---|---|---|")
 pool = torch.randint(0, 256, (1024 * 150528,), dtype=torch.uint8, device=dev)
 engines = {}
-for prec, maxb in (("bf16", 1024), ("fp32", 256)):
+for prec, maxb in (("bf16", 1024), ("fp32", 1024)):
     e = Engine(0, maxb, prec)
     e.load_state_dict(state)
     engines[prec] = e
