@@ -61,11 +61,14 @@ __device__ __forceinline__ void tmem_ld32s(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
-template <int BN, int STAGES>
+// BK: channels per K-block (64: SWIZZLE_128B rows; 16: the stem's space-to-depth pixels, SWIZZLE_32B rows).
+// GROUP: K-blocks accumulated in TMEM before the hand-over (1 for BK = 64: a chain of 4 k-steps; 4 for BK = 16: the same).
+template <int BN, int BK, int STAGES, int GROUP>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, const SplitParams p) {
-    constexpr int kA = 128 * 64 * 2, kB = BN * 64 * 2, kStage = 2 * kA + 2 * kB;
+    constexpr int kA = 128 * BK * 2, kB = BN * BK * 2, kStage = 2 * kA + 2 * kB;
+    constexpr int KSTEPS = BK / 16;
     constexpr int HC = BN / 2;  // accumulator columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
@@ -125,10 +128,10 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
                             mbar_expect_tx(full0 + 8 * stage, kStage);
                             const uint32_t st = sbase + stage * kStage;
-                            tma_load_4d(st, &map_ah, full0 + 8 * stage, cc * 64, w0 + s, h0 + r, n0);
-                            tma_load_4d(st + kA, &map_al, full0 + 8 * stage, cc * 64, w0 + s, h0 + r, n0);
-                            tma_load_2d(st + 2 * kA, &map_bh, full0 + 8 * stage, kb * 64, n_tile * BN);
-                            tma_load_2d(st + 2 * kA + kB, &map_bl, full0 + 8 * stage, kb * 64, n_tile * BN);
+                            tma_load_4d(st, &map_ah, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                            tma_load_4d(st + kA, &map_al, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                            tma_load_2d(st + 2 * kA, &map_bh, full0 + 8 * stage, kb * BK, n_tile * BN);
+                            tma_load_2d(st + 2 * kA + kB, &map_bl, full0 + 8 * stage, kb * BK, n_tile * BN);
                             if (++stage == STAGES) {
                                 stage = 0;
                                 phase ^= 1;
@@ -137,30 +140,33 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one K-block (4 k-steps x 3 split terms) per TMEM buffer, then hand it over =====
+        // ===== MMA issuer: GROUP K-blocks (KSTEPS k-steps x 3 split terms each) per TMEM buffer, then hand it over =====
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f32 accumulate, fp16 x fp16, M 128
-        constexpr uint64_t desc_hi = make_smem_desc<64>(0) & 0xFFFFFFFF00000000ull;
+        constexpr uint64_t desc_hi = make_smem_desc_rowb<BK * 2>(0) & 0xFFFFFFFF00000000ull;
         uint32_t stage = 0, phase = 0, g = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const uint32_t buf = g & 1, bphase = (g >> 1) & 1;
-                mbar_wait(tempty0 + 8 * buf, bphase ^ 1);
+                const int in_group = kb % GROUP;
+                if (in_group == 0) mbar_wait(tempty0 + 8 * buf, bphase ^ 1);
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
+                const bool hand_over = in_group == GROUP - 1 || kb == num_kb - 1;
                 if (elect_one_sync()) {
                     const uint32_t st = sbase + stage * kStage;
                     const uint32_t ah = st >> 4, al = (st + kA) >> 4, bh = (st + 2 * kA) >> 4, bl = (st + 2 * kA + kB) >> 4;
                     const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, k != 0);
+                    for (int k = 0; k < KSTEPS; ++k) {
+                        umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, (in_group | k) != 0);
                         umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bl + 2 * k), idesc, 1);
                         umma_bf16(d, desc_hi | (uint64_t)(al + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, 1);
                     }
                     umma_commit(empty0 + 8 * stage);
-                    umma_commit(tfull0 + 8 * buf);
+                    if (hand_over) umma_commit(tfull0 + 8 * buf);
                 }
                 __syncwarp();
+                if (hand_over) ++g;
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -180,7 +186,7 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
             float acc[HC];
 #pragma unroll
             for (int j = 0; j < HC; ++j) acc[j] = 0.f;
-            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+            for (int ho = 0; ho < (num_kb + GROUP - 1) / GROUP; ++ho, ++g) {
                 const uint32_t buf = g & 1, bphase = (g >> 1) & 1;
                 mbar_wait(tfull0 + 8 * buf, bphase);
                 tc_fence_after();
@@ -318,18 +324,18 @@ int split_pack_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, s
     return s;
 }
 
-template <int BN, int STAGES>
+template <int BN, int BK, int STAGES, int GROUP>
 static int launch_split(fx_engine* e, const CUtensorMap& mah, const CUtensorMap& mal, const CUtensorMap& mbh, const CUtensorMap& mbl,
                         const SplitParams& p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (2 * 128 * 64 * 2 + 2 * BN * 64 * 2) + (2 * STAGES + 4) * 8 + 32 + 512 * 4;
+    constexpr int kSmem = 1024 + STAGES * (2 * 128 * BK * 2 + 2 * BN * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 512 * 4;
     static_assert(kSmem <= 232448, "split_conv_kernel: shared memory");
     static bool attr_done[256] = {};
     if (!attr_done[e->device & 255]) {
-        FX_CUDA(e, cudaFuncSetAttribute(split_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        FX_CUDA(e, cudaFuncSetAttribute(split_conv_kernel<BN, BK, STAGES, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_done[e->device & 255] = true;
     }
     const int grid = std::min(p.total_tiles, e->sm_count);
-    FX_CUDA(e, launch_pdl(split_conv_kernel<BN, STAGES>, dim3(grid), dim3(kSplitThreads), kSmem, stream, mah, mal, mbh, mbl, p));
+    FX_CUDA(e, launch_pdl(split_conv_kernel<BN, BK, STAGES, GROUP>, dim3(grid), dim3(kSplitThreads), kSmem, stream, mah, mal, mbh, mbl, p));
     FX_LAUNCH_CHECK(e, "split_conv_kernel");
     return FX_OK;
 }
@@ -385,8 +391,165 @@ int split_conv(fx_engine* e, const PackedLayer& L, const void* in, const void* r
     if (rc == FX_OK) rc = tc_encode_map(e, &mbh, L.w_h16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "split conv W hi");
     if (rc == FX_OK) rc = tc_encode_map(e, &mbl, L.w_l16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "split conv W lo");
     if (rc != FX_OK) return rc;
-    if (bn == 128) return launch_split<128, 3>(e, mah, mal, mbh, mbl, p, stream);
-    return launch_split<64, 4>(e, mah, mal, mbh, mbl, p, stream);
+    if (bn == 128) return launch_split<128, 64, 3, 1>(e, mah, mal, mbh, mbl, p, stream);
+    return launch_split<64, 64, 4, 1>(e, mah, mal, mbh, mbl, p, stream);
+}
+
+// ---- the stem in the tight mode ------------------------------------------------------------------
+// conv1 7x7 / stride 2 / pad 3 + bn1 + ReLU (torchvision/models/resnet.py:197-199, 268-270) as a 4x4 / stride-1 conv over the
+// SPACE-TO-DEPTH form of the normalised crop (fx_common.cuh: [n][115][116][16], channel (dy*2+dx)*3+c), split fp16:
+// 16 K-blocks of one 16-channel pixel each, handed over every four.  Output: split [n][112][112][64].
+
+// fp32 staging tensor [n][230][232][4] (what fx_preprocess writes for FX_PRECISION_FP32) -> split s2d planes
+__global__ void in0_to_split_s2d_kernel(const float* __restrict__ in0, __half* __restrict__ hi, __half* __restrict__ lo, int n) {
+    const size_t total = (size_t)n * kS2dH * kS2dW;  // one thread per s2d pixel: 16 channels = 32 B per plane
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t img = i / (kS2dH * kS2dW);
+        const int rem = (int)(i - img * kS2dH * kS2dW);
+        const int Y = rem / kS2dW, X = rem - Y * kS2dW;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        if (X < kS2dW - 1) {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const float4 px = *reinterpret_cast<const float4*>(in0 + ((img * kIn0H + (2 * Y + dy)) * kIn0W + (2 * X + dx)) * kIn0C);
+                    v[(dy * 2 + dx) * 3 + 0] = px.x;
+                    v[(dy * 2 + dx) * 3 + 1] = px.y;
+                    v[(dy * 2 + dx) * 3 + 2] = px.z;
+                }
+        }
+        uint4 oh[2], ol[2];
+        __half2* ph = reinterpret_cast<__half2*>(oh);
+        __half2* pl = reinterpret_cast<__half2*>(ol);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            const float2 hf = __half22float2(h);
+            ph[j] = h;
+            pl[j] = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        }
+        reinterpret_cast<uint4*>(hi)[2 * i] = oh[0];
+        reinterpret_cast<uint4*>(hi)[2 * i + 1] = oh[1];
+        reinterpret_cast<uint4*>(lo)[2 * i] = ol[0];
+        reinterpret_cast<uint4*>(lo)[2 * i + 1] = ol[1];
+    }
+}
+
+// 3x3 / stride-2 / pad-1 max-pool (resnet.py:200) on a split tensor: max over hi + lo, re-split.  8 channels per thread.
+__global__ void maxpool_split_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, __half* __restrict__ out_hi,
+                                     __half* __restrict__ out_lo, int n, int h, int w, int c) {
+    const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1, cv = c / 8;
+    const size_t total = (size_t)n * ho * wo * cv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % cv);
+        size_t q = i / cv;
+        const int x = (int)(q % wo);
+        q /= wo;
+        const int y = (int)(q % ho);
+        const int img = (int)(q / ho);
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = 2 * y - 1 + dy;
+            if (iy < 0 || iy >= h) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = 2 * x - 1 + dx;
+                if (ix < 0 || ix >= w) continue;
+                const size_t off = (((size_t)img * h + iy) * w + ix) * c + (size_t)cc * 8;
+                const uint4 a = *reinterpret_cast<const uint4*>(in_hi + off), b = *reinterpret_cast<const uint4*>(in_lo + off);
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
+                    m[2 * k] = fmaxf(m[2 * k], fa.x + fb.x);
+                    m[2 * k + 1] = fmaxf(m[2 * k + 1], fa.y + fb.y);
+                }
+            }
+        }
+        uint4 oh, ol;
+        __half2* ph = reinterpret_cast<__half2*>(&oh);
+        __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 hh = __floats2half2_rn(m[2 * k], m[2 * k + 1]);
+            const float2 hf = __half22float2(hh);
+            ph[k] = hh;
+            pl[k] = __floats2half2_rn(m[2 * k] - hf.x, m[2 * k + 1] - hf.y);
+        }
+        const size_t oo = (((size_t)img * ho + y) * wo + x) * c + (size_t)cc * 8;
+        *reinterpret_cast<uint4*>(out_hi + oo) = oh;
+        *reinterpret_cast<uint4*>(out_lo + oo) = ol;
+    }
+}
+
+// Space-to-depth pack of the folded stem weights [64][7][7][3] -> [64][4*4*16] (as engine.cu's bf16 stem pack), fp32.
+void split_stem_s2d_weights(const std::vector<float>& host_w, int cout, std::vector<float>& out) {
+    out.assign((size_t)cout * 16 * kS2dC, 0.f);
+    for (int o = 0; o < cout; ++o)
+        for (int r = 0; r < 7; ++r)
+            for (int s = 0; s < 7; ++s)
+                for (int i = 0; i < 3; ++i)
+                    out[(size_t)o * 16 * kS2dC + ((r >> 1) * 4 + (s >> 1)) * kS2dC + ((r & 1) * 2 + (s & 1)) * 3 + i] =
+                        host_w[((size_t)o * 49 + r * 7 + s) * 3 + i];
+}
+
+// in0_f32: the fp32 staging tensor of the n staged images; s2d_split: scratch for its split s2d form (2 planes of
+// n*115*116*16 fp16); conv_split: [n][112][112][64] split; pooled_split: [n][56][56][64] split.
+int split_stem(fx_engine* e, const PackedLayer& L, const float* in0_f32, void* s2d_split, void* conv_out_split, void* pooled_split, int n,
+               cudaStream_t stream) {
+    if (!L.w_h16 || !L.w_l16 || L.g.cout != 64) return set_error(e, FX_ERR_STATE, "split_stem: the stem has no split weight pack");
+    const size_t s2d_count = (size_t)n * kS2dH * kS2dW * kS2dC, conv_count = (size_t)n * 112 * 112 * 64, pool_count = (size_t)n * 56 * 56 * 64;
+    __half* s_hi = static_cast<__half*>(s2d_split);
+    {
+        const size_t px = (size_t)n * kS2dH * kS2dW;
+        in0_to_split_s2d_kernel<<<(int)std::min<size_t>((px + 255) / 256, (size_t)e->sm_count * 16), 256, 0, stream>>>(in0_f32, s_hi, s_hi + s2d_count, n);
+        FX_LAUNCH_CHECK(e, "in0_to_split_s2d_kernel");
+    }
+    SplitParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.batch = n;
+    p.ho = p.wo = 112;
+    p.cout = 64;
+    p.bias = L.bias;
+    p.unscale = std::ldexp(1.0f, -L.w_scale_log2);
+    p.out_hi = static_cast<__half*>(conv_out_split);
+    p.out_lo = p.out_hi + conv_count;
+    p.relu = 1;
+    p.n_tiles_n = 1;
+    choose_tile(n, 112, 112, p.wt_log2, p.ht_log2, p.nt_log2);
+    p.tiles_w = (112 + (1 << p.wt_log2) - 1) >> p.wt_log2;
+    p.tiles_h = (112 + (1 << p.ht_log2) - 1) >> p.ht_log2;
+    p.tiles_g = (n + (1 << p.nt_log2) - 1) >> p.nt_log2;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
+    p.kh = p.kw = 4;
+    p.cchunks = 1;
+    p.cw_mul = p.ch_mul = 1;
+    CUtensorMap mah, mal, mbh, mbl;
+    const uint64_t dims[4] = {(uint64_t)kS2dC, (uint64_t)kS2dW, (uint64_t)kS2dH, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)kS2dC * 2, (uint64_t)kS2dW * kS2dC * 2, (uint64_t)kS2dH * kS2dW * kS2dC * 2};
+    const uint32_t box[4] = {16, 1u << p.wt_log2, 1u << p.ht_log2, 1u << p.nt_log2};
+    const uint32_t estr[4] = {1, 1, 1, 1};
+    int rc = tc_encode_map(e, &mah, s_hi, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_32B, "split stem A hi");
+    if (rc == FX_OK) rc = tc_encode_map(e, &mal, s_hi + s2d_count, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_32B, "split stem A lo");
+    const uint64_t bd[2] = {256, 64};
+    const uint64_t bs[1] = {512};
+    const uint32_t bbox[2] = {16, 64};
+    const uint32_t be[2] = {1, 1};
+    if (rc == FX_OK) rc = tc_encode_map(e, &mbh, L.w_h16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_32B, "split stem W hi");
+    if (rc == FX_OK) rc = tc_encode_map(e, &mbl, L.w_l16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_32B, "split stem W lo");
+    if (rc != FX_OK) return rc;
+    if ((rc = launch_split<64, 16, 8, 4>(e, mah, mal, mbh, mbl, p, stream)) != FX_OK) return rc;
+    __half* o_hi = static_cast<__half*>(pooled_split);
+    const size_t items = pool_count / 8;
+    maxpool_split_kernel<<<(int)std::min<size_t>((items + 255) / 256, (size_t)e->sm_count * 32), 256, 0, stream>>>(p.out_hi, p.out_lo, o_hi,
+                                                                                                                    o_hi + pool_count, n, 112, 112, 64);
+    FX_LAUNCH_CHECK(e, "maxpool_split_kernel");
+    return FX_OK;
 }
 
 }  // namespace fx

@@ -102,9 +102,12 @@ static int pack_layer(fx_engine* e, const fx_conv_bn& src, int hin, int win, Pac
                 for (int i = 0; i < g.cin; ++i) w[((size_t)o * taps + t) * cp + i] = L.host_w[((size_t)o * taps + t) * g.cin + i];
         FX_CUDA(e, cudaMalloc(&L.w_f32, sizeof(float) * w.size()));
         FX_CUDA(e, cudaMemcpy(L.w_f32, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
-        if (e->tight_tc && !stem && g.cin % 64 == 0 && g.cout % 64 == 0) {  // split fp16 pack for the tensor-core tight mode
+        const bool stem7 = stem && g.kh == 7 && g.kw == 7 && g.cout == 64;
+        if (e->tight_tc && (stem7 || (!stem && g.cin % 64 == 0 && g.cout % 64 == 0))) {  // split fp16 pack for the tensor-core tight mode
             std::vector<uint16_t> hi, lo;
-            L.w_scale_log2 = split_pack_weights(L.host_w, hi, lo);
+            std::vector<float> s2d;
+            if (stem7) split_stem_s2d_weights(L.host_w, g.cout, s2d);  // the stem runs as a 4x4 conv over the space-to-depth crop
+            L.w_scale_log2 = split_pack_weights(stem7 ? s2d : L.host_w, hi, lo);
             FX_CUDA(e, cudaMalloc(&L.w_h16, 2 * hi.size()));
             FX_CUDA(e, cudaMalloc(&L.w_l16, 2 * lo.size()));
             FX_CUDA(e, cudaMemcpy(L.w_h16, hi.data(), 2 * hi.size(), cudaMemcpyHostToDevice));
@@ -194,16 +197,19 @@ static int forward(fx_engine* e, int n, float* emb, cudaStream_t stream) {
         if ((rc = flat_conv(e, e->layers[0], static_cast<const __nv_bfloat16*>(e->in0), nullptr, static_cast<__nv_bfloat16*>(A), n, 1,
                             true, stream, tile_sched(0))) != FX_OK)
             return rc;
+    } else if (e->tight_tc) {
+        // tight mode on the tensor cores: fp32 staging -> split space-to-depth (second half of in0) -> conv1 -> max-pool -> C
+        ProfScope ps(e, 0, stream);
+        char* s2d = static_cast<char*>(e->in0) + (size_t)e->max_batch * kIn0H * kIn0W * kIn0C * 4;
+        if ((rc = split_stem(e, e->layers[0], static_cast<const float*>(e->in0), s2d, B, C, n, stream)) != FX_OK) return rc;
     } else {
         ProfScope ps(e, 0, stream);
         if ((rc = run_conv(e, 0, e->in0, nullptr, B, nullptr, n, 1, stream)) != FX_OK) return rc;
         if ((rc = maxpool_3x3s2(e, B, A, n, 112, 112, 64, bf16, stream)) != FX_OK) return rc;
     }
     if (!bf16 && e->tight_tc) {
-        // Tight mode on the tensor cores (conv_split.cu): from here on activations are split fp16 (hi plane, lo plane:
-        // the bytes of the fp32 tensor).  X = block input, T = conv1 output, Y = block output / downsample branch.
-        const size_t pooled = (size_t)n * 56 * 56 * 64;
-        if ((rc = f32_to_split(e, static_cast<const float*>(A), C, pooled, stream)) != FX_OK) return rc;
+        // Tight mode on the tensor cores (conv_split.cu): activations are split fp16 (hi plane, lo plane: the bytes of the
+        // fp32 tensor).  X = block input, T = conv1 output, Y = block output / downsample branch.
         void *X = C, *T = B, *Y = A;
         int l = 1;
         for (int stage = 0; stage < 4; ++stage)
@@ -289,7 +295,8 @@ static void lane_load(fx_engine* e, int lane) {
 static int lane_alloc(fx_engine* e) {
     const bool bf16 = e->precision == FX_PRECISION_BF16;
     const size_t esz = bf16 ? 2 : 4, mb = (size_t)e->max_batch;
-    const size_t in0_bytes = bf16 ? mb * kS2dH * kS2dW * kS2dC * 2 : mb * kIn0H * kIn0W * kIn0C * 4;
+    // FP32: the fp32 staging tensor, followed by as many bytes again for its split space-to-depth form (conv_split.cu)
+    const size_t in0_bytes = bf16 ? mb * kS2dH * kS2dW * kS2dC * 2 : 2 * mb * kIn0H * kIn0W * kIn0C * 4;
     e->act_bytes = mb * 112 * 112 * 64 * esz;  // largest activation: the conv1 output of the unfused (fp32) stem
     int rc = FX_OK;
     auto alloc = [&](void** p, size_t bytes) {
@@ -874,11 +881,22 @@ int fx_debug_conv(fx_handle e, const fx_conv_bn* layer, int hin, int win, const 
 int fx_debug_stem_pool(fx_handle e, const fx_conv_bn* layer, const float* in_dev, int n, float* out_dev, void* stream_) {
     if (!e) return FX_ERR_INVALID;
     if (!layer || !in_dev || !out_dev || n < 1 || n > e->max_batch) return set_error(e, FX_ERR_INVALID, "fx_debug_stem_pool: bad arguments");
-    if (e->precision != FX_PRECISION_BF16) return set_error(e, FX_ERR_UNSUPPORTED, "fx_debug_stem_pool: bf16 engines only");
+    if (e->precision != FX_PRECISION_BF16 && !e->tight_tc)
+        return set_error(e, FX_ERR_UNSUPPORTED, "fx_debug_stem_pool: bf16 engines and the tensor-core tight mode only");
     FX_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PackedLayer L;
     int rc = pack_layer(e, *layer, kCrop, kCrop, L);
+    if (e->precision != FX_PRECISION_BF16) {  // tight mode: fp32 staging -> split space-to-depth -> conv1 -> max-pool -> fp32
+        if (rc == FX_OK) rc = pad_nhwc3_to_in0(e, in_dev, e->in0, false, n, stream);
+        char* s2d = static_cast<char*>(e->in0) + (size_t)e->max_batch * kIn0H * kIn0W * kIn0C * 4;
+        if (rc == FX_OK) rc = split_stem(e, L, static_cast<const float*>(e->in0), s2d, e->act[1], e->act[2], n, stream);
+        if (rc == FX_OK) rc = split_to_f32(e, e->act[2], out_dev, (size_t)n * 56 * 56 * 64, stream);
+        cudaError_t serr = cudaStreamSynchronize(stream);
+        free_layer(L);
+        if (rc == FX_OK && serr != cudaSuccess) rc = set_error(e, FX_ERR_CUDA, std::string("fx_debug_stem_pool: ") + cudaGetErrorString(serr));
+        return rc;
+    }
     if (rc == FX_OK && !flat_supported(L.g)) rc = set_error(e, FX_ERR_UNSUPPORTED, "fx_debug_stem_pool: not the 7x7/s2 stem");
     if (rc == FX_OK) rc = pad_nhwc3_to_in0(e, in_dev, e->in0, true, n, stream);
     __nv_bfloat16* bout = static_cast<__nv_bfloat16*>(e->act[0]);

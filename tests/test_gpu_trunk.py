@@ -196,6 +196,16 @@ def test_conv_layer_fp32(eng_fp32, case):
     assert _rel(got, want) < 2e-6
 
 
+@pytest.mark.parametrize("n", [1, 9])
+def test_stem_tight_mode_on_tensor_cores(eng_fp32, n):
+    # conv1 + bn1 + ReLU + max-pool through the split-fp16 kernel (4x4 conv over the space-to-depth crop): fp32-accurate
+    w, bn, x = _case_tensors(3, 64, 7, 224, n, False, seed=199 + n)
+    got = eng_fp32.debug_stem_pool(w, bn, x.cuda()).cpu()
+    conv = _torch_conv(w, bn, x, 2, 3, None, True, round_bf16=False)
+    want = F.max_pool2d(conv.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert _rel(got, want) < 2e-6, _rel(got, want)
+
+
 def test_tight_mode_cuda_core_kernel_stays_available_and_agrees(eng_fp32):
     """FX_TIGHT_SIMT=1 (read at fx_create) keeps the fp32 CUDA-core convolution of round 1; the default tight mode runs the
     split-fp16 tensor-core kernel (conv_split.cu).  Both are fp32-accurate: per layer within 2e-6 of the fp64 reference
