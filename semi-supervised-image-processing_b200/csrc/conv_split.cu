@@ -61,8 +61,8 @@ __device__ __forceinline__ void tmem_ld32s(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
-// BK: channels per K-block (64: SWIZZLE_128B rows; 16: the stem's space-to-depth pixels, SWIZZLE_32B rows).
-// GROUP: K-blocks accumulated in TMEM before the hand-over (1 for BK = 64: a chain of 4 k-steps; 4 for BK = 16: the same).
+// BK: channels per K-block (64: SWIZZLE_128B rows; 16 / 32 narrower rows are possible but starve on TMA box issue).
+// GROUP: K-blocks accumulated in TMEM before the hand-over (1: a chain of BK / 16 k-steps).
 template <int BN, int BK, int STAGES, int GROUP>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -182,7 +182,29 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         const int hl = (row >> p.wt_log2) & ((1 << p.ht_log2) - 1);
         const int nl = row >> (p.wt_log2 + p.ht_log2);
         uint32_t g = 0;
+        // BN = 64 (layer 1, the stem): the residual of the tile is fetched into registers BEFORE the K loop, so its latency
+        // hides behind the tile's MMAs; with 64 columns per warp (BN = 128) the registers are not there and it is read at the end.
+        constexpr bool kPrefetchRes = HC == 32;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int n_tile = t % p.n_tiles_n;
+            int m_tile = t / p.n_tiles_n;
+            const int tw = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int th = m_tile % p.tiles_h;
+            const int tg = m_tile / p.tiles_h;
+            const int ow = (tw << p.wt_log2) + wl, oh = (th << p.ht_log2) + hl, img = (tg << p.nt_log2) + nl;
+            const bool valid = ow < p.wo && oh < p.ho && img < p.batch;
+            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
+            const int c0 = n_tile * BN + half * HC;
+            const size_t obase = pix * p.cout + c0;
+            uint4 pre_h[kPrefetchRes ? HC / 8 : 1], pre_l[kPrefetchRes ? HC / 8 : 1];
+            if (kPrefetchRes && p.res_hi && valid) {
+#pragma unroll
+                for (int j = 0; j < HC / 8; ++j) {
+                    pre_h[j] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase) + j);
+                    pre_l[j] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + obase) + j);
+                }
+            }
             float acc[HC];
 #pragma unroll
             for (int j = 0; j < HC; ++j) acc[j] = 0.f;
@@ -202,25 +224,21 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
                 tc_fence_before();
                 mbar_arrive(tempty0 + 8 * buf);
             }
-            const int n_tile = t % p.n_tiles_n;
-            int m_tile = t / p.n_tiles_n;
-            const int tw = m_tile % p.tiles_w;
-            m_tile /= p.tiles_w;
-            const int th = m_tile % p.tiles_h;
-            const int tg = m_tile / p.tiles_h;
-            const int ow = (tw << p.wt_log2) + wl, oh = (th << p.ht_log2) + hl, img = (tg << p.nt_log2) + nl;
-            if (!(ow < p.wo && oh < p.ho && img < p.batch)) continue;
-            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
-            const int c0 = n_tile * BN + half * HC;
-            const size_t obase = pix * p.cout + c0;
+            if (!valid) continue;
 #pragma unroll
             for (int c = 0; c < HC; c += 8) {
                 float f[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = fmaf(acc[c + j], p.unscale, bias_s[c0 + c + j]);
                 if (p.res_hi) {
-                    const uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase + c));
-                    const uint4 rl = __ldg(reinterpret_cast<const uint4*>(p.res_lo + obase + c));
+                    uint4 rh, rl;
+                    if (kPrefetchRes) {
+                        rh = pre_h[kPrefetchRes ? c / 8 : 0];
+                        rl = pre_l[kPrefetchRes ? c / 8 : 0];
+                    } else {
+                        rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + obase + c));
+                        rl = __ldg(reinterpret_cast<const uint4*>(p.res_lo + obase + c));
+                    }
                     const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
                     const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
@@ -397,30 +415,37 @@ int split_conv(fx_engine* e, const PackedLayer& L, const void* in, const void* r
 
 // ---- the stem in the tight mode ------------------------------------------------------------------
 // conv1 7x7 / stride 2 / pad 3 + bn1 + ReLU (torchvision/models/resnet.py:197-199, 268-270) as a 4x4 / stride-1 conv over the
-// SPACE-TO-DEPTH form of the normalised crop (fx_common.cuh: [n][115][116][16], channel (dy*2+dx)*3+c), split fp16:
-// 16 K-blocks of one 16-channel pixel each, handed over every four.  Output: split [n][112][112][64].
+// SPACE-TO-DEPTH form of the normalised crop (fx_common.cuh: [n][115][116][16], channel (dy*2+dx)*3+c), split fp16, with the
+// four horizontal taps gathered into the channel dimension: four 64-wide K-blocks.  Output: split [n][112][112][64].
 
-// fp32 staging tensor [n][230][232][4] (what fx_preprocess writes for FX_PRECISION_FP32) -> split s2d planes
-__global__ void in0_to_split_s2d_kernel(const float* __restrict__ in0, __half* __restrict__ hi, __half* __restrict__ lo, int n) {
-    const size_t total = (size_t)n * kS2dH * kS2dW;  // one thread per s2d pixel: 16 channels = 32 B per plane
+// fp32 staging tensor [n][230][232][4] (what fx_preprocess writes for FX_PRECISION_FP32) -> split planes of the
+// X-GATHERED space-to-depth crop [n][115][112][64]: position (Y, X) holds the four s2d pixels (Y, X .. X+3), i.e. channel
+// s*16 + (dy*2+dx)*3 + c = padded pixel (2Y+dy, 2(X+s)+dx), channel c.  With the four horizontal taps in the channel
+// dimension a K-block is one 128-byte row per pixel (SWIZZLE_128B, the box shape every other layer uses) and the stem is
+// a 4x1 conv: 4 TMA boxes per operand and tile instead of 16 boxes of 32-byte rows, which the TMA unit could not feed
+// fast enough (measured: 1.08 ms per launch at batch 256 with per-tap 16-channel boxes).
+constexpr int kXsW = 112, kXsC = 64;
+__global__ void in0_to_split_xs2d_kernel(const float* __restrict__ in0, __half* __restrict__ hi, __half* __restrict__ lo, int n) {
+    // one thread per (position, s): 16 channels = one 32-byte piece of each plane
+    const size_t total = (size_t)n * kS2dH * kXsW * 4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t img = i / (kS2dH * kS2dW);
-        const int rem = (int)(i - img * kS2dH * kS2dW);
-        const int Y = rem / kS2dW, X = rem - Y * kS2dW;
+        const int s = (int)(i & 3);
+        const size_t pos = i >> 2;
+        const size_t img = pos / (kS2dH * kXsW);
+        const int rem = (int)(pos - img * kS2dH * kXsW);
+        const int Y = rem / kXsW, X = rem - Y * kXsW + s;  // s2d pixel (Y, X), X <= 114
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        if (X < kS2dW - 1) {
+        for (int j = 12; j < 16; ++j) v[j] = 0.f;
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
+        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const float4 px = *reinterpret_cast<const float4*>(in0 + ((img * kIn0H + (2 * Y + dy)) * kIn0W + (2 * X + dx)) * kIn0C);
-                    v[(dy * 2 + dx) * 3 + 0] = px.x;
-                    v[(dy * 2 + dx) * 3 + 1] = px.y;
-                    v[(dy * 2 + dx) * 3 + 2] = px.z;
-                }
-        }
+            for (int dx = 0; dx < 2; ++dx) {
+                const float4 px = *reinterpret_cast<const float4*>(in0 + ((img * kIn0H + (2 * Y + dy)) * kIn0W + (2 * X + dx)) * kIn0C);
+                v[(dy * 2 + dx) * 3 + 0] = px.x;
+                v[(dy * 2 + dx) * 3 + 1] = px.y;
+                v[(dy * 2 + dx) * 3 + 2] = px.z;
+            }
         uint4 oh[2], ol[2];
         __half2* ph = reinterpret_cast<__half2*>(oh);
         __half2* pl = reinterpret_cast<__half2*>(ol);
@@ -498,17 +523,19 @@ void split_stem_s2d_weights(const std::vector<float>& host_w, int cout, std::vec
                         host_w[((size_t)o * 49 + r * 7 + s) * 3 + i];
 }
 
-// in0_f32: the fp32 staging tensor of the n staged images; s2d_split: scratch for its split s2d form (2 planes of
-// n*115*116*16 fp16); conv_split: [n][112][112][64] split; pooled_split: [n][56][56][64] split.
-int split_stem(fx_engine* e, const PackedLayer& L, const float* in0_f32, void* s2d_split, void* conv_out_split, void* pooled_split, int n,
+size_t split_stem_scratch_bytes(int n) { return (size_t)n * kS2dH * kXsW * kXsC * 2 * 2; }
+
+// in0_f32: the fp32 staging tensor of the n staged images; xs2d_split: scratch for its x-gathered split form
+// (split_stem_scratch_bytes); conv_out_split: [n][112][112][64] split; pooled_split: [n][56][56][64] split.
+int split_stem(fx_engine* e, const PackedLayer& L, const float* in0_f32, void* xs2d_split, void* conv_out_split, void* pooled_split, int n,
                cudaStream_t stream) {
     if (!L.w_h16 || !L.w_l16 || L.g.cout != 64) return set_error(e, FX_ERR_STATE, "split_stem: the stem has no split weight pack");
-    const size_t s2d_count = (size_t)n * kS2dH * kS2dW * kS2dC, conv_count = (size_t)n * 112 * 112 * 64, pool_count = (size_t)n * 56 * 56 * 64;
-    __half* s_hi = static_cast<__half*>(s2d_split);
+    const size_t xs_count = (size_t)n * kS2dH * kXsW * kXsC, conv_count = (size_t)n * 112 * 112 * 64, pool_count = (size_t)n * 56 * 56 * 64;
+    __half* s_hi = static_cast<__half*>(xs2d_split);
     {
-        const size_t px = (size_t)n * kS2dH * kS2dW;
-        in0_to_split_s2d_kernel<<<(int)std::min<size_t>((px + 255) / 256, (size_t)e->sm_count * 16), 256, 0, stream>>>(in0_f32, s_hi, s_hi + s2d_count, n);
-        FX_LAUNCH_CHECK(e, "in0_to_split_s2d_kernel");
+        const size_t items = (size_t)n * kS2dH * kXsW * 4;
+        in0_to_split_xs2d_kernel<<<(int)std::min<size_t>((items + 255) / 256, (size_t)e->sm_count * 32), 256, 0, stream>>>(in0_f32, s_hi, s_hi + xs_count, n);
+        FX_LAUNCH_CHECK(e, "in0_to_split_xs2d_kernel");
     }
     SplitParams p;
     std::memset(&p, 0, sizeof(p));
@@ -526,24 +553,25 @@ int split_stem(fx_engine* e, const PackedLayer& L, const float* in0_f32, void* s
     p.tiles_h = (112 + (1 << p.ht_log2) - 1) >> p.ht_log2;
     p.tiles_g = (n + (1 << p.nt_log2) - 1) >> p.nt_log2;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
-    p.kh = p.kw = 4;
+    p.kh = 4;  // filter-row pairs; the four horizontal taps live in the 64 channels
+    p.kw = 1;
     p.cchunks = 1;
     p.cw_mul = p.ch_mul = 1;
     CUtensorMap mah, mal, mbh, mbl;
-    const uint64_t dims[4] = {(uint64_t)kS2dC, (uint64_t)kS2dW, (uint64_t)kS2dH, (uint64_t)n};
-    const uint64_t strides[3] = {(uint64_t)kS2dC * 2, (uint64_t)kS2dW * kS2dC * 2, (uint64_t)kS2dH * kS2dW * kS2dC * 2};
-    const uint32_t box[4] = {16, 1u << p.wt_log2, 1u << p.ht_log2, 1u << p.nt_log2};
+    const uint64_t dims[4] = {(uint64_t)kXsC, (uint64_t)kXsW, (uint64_t)kS2dH, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)kXsC * 2, (uint64_t)kXsW * kXsC * 2, (uint64_t)kS2dH * kXsW * kXsC * 2};
+    const uint32_t box[4] = {64, 1u << p.wt_log2, 1u << p.ht_log2, 1u << p.nt_log2};
     const uint32_t estr[4] = {1, 1, 1, 1};
-    int rc = tc_encode_map(e, &mah, s_hi, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_32B, "split stem A hi");
-    if (rc == FX_OK) rc = tc_encode_map(e, &mal, s_hi + s2d_count, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_32B, "split stem A lo");
-    const uint64_t bd[2] = {256, 64};
+    int rc = tc_encode_map(e, &mah, s_hi, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "split stem A hi");
+    if (rc == FX_OK) rc = tc_encode_map(e, &mal, s_hi + xs_count, 4, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "split stem A lo");
+    const uint64_t bd[2] = {256, 64};  // [cout][(r, s, 16 channels)]: K-block r = the 64 weights of filter-row pair r
     const uint64_t bs[1] = {512};
-    const uint32_t bbox[2] = {16, 64};
+    const uint32_t bbox[2] = {64, 64};
     const uint32_t be[2] = {1, 1};
-    if (rc == FX_OK) rc = tc_encode_map(e, &mbh, L.w_h16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_32B, "split stem W hi");
-    if (rc == FX_OK) rc = tc_encode_map(e, &mbl, L.w_l16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_32B, "split stem W lo");
+    if (rc == FX_OK) rc = tc_encode_map(e, &mbh, L.w_h16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "split stem W hi");
+    if (rc == FX_OK) rc = tc_encode_map(e, &mbl, L.w_l16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "split stem W lo");
     if (rc != FX_OK) return rc;
-    if ((rc = launch_split<64, 16, 8, 4>(e, mah, mal, mbh, mbl, p, stream)) != FX_OK) return rc;
+    if ((rc = launch_split<64, 64, 4, 1>(e, mah, mal, mbh, mbl, p, stream)) != FX_OK) return rc;
     __half* o_hi = static_cast<__half*>(pooled_split);
     const size_t items = pool_count / 8;
     maxpool_split_kernel<<<(int)std::min<size_t>((items + 255) / 256, (size_t)e->sm_count * 32), 256, 0, stream>>>(p.out_hi, p.out_lo, o_hi,

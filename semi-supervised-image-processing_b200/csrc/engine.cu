@@ -295,8 +295,8 @@ static void lane_load(fx_engine* e, int lane) {
 static int lane_alloc(fx_engine* e) {
     const bool bf16 = e->precision == FX_PRECISION_BF16;
     const size_t esz = bf16 ? 2 : 4, mb = (size_t)e->max_batch;
-    // FP32: the fp32 staging tensor, followed by as many bytes again for its split space-to-depth form (conv_split.cu)
-    const size_t in0_bytes = bf16 ? mb * kS2dH * kS2dW * kS2dC * 2 : 2 * mb * kIn0H * kIn0W * kIn0C * 4;
+    // FP32: the fp32 staging tensor, followed by the scratch for its split space-to-depth form (conv_split.cu)
+    const size_t in0_bytes = bf16 ? mb * kS2dH * kS2dW * kS2dC * 2 : mb * kIn0H * kIn0W * kIn0C * 4 + split_stem_scratch_bytes(e->max_batch);
     e->act_bytes = mb * 112 * 112 * 64 * esz;  // largest activation: the conv1 output of the unfused (fp32) stem
     int rc = FX_OK;
     auto alloc = [&](void** p, size_t bytes) {

@@ -292,7 +292,8 @@ int f32_to_split(fx_engine* e, const float* in, void* out_split, size_t count, c
 int split_to_f32(fx_engine* e, const void* in_split, float* out, size_t count, cudaStream_t stream);
 int split_pack_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
 void split_stem_s2d_weights(const std::vector<float>& host_w, int cout, std::vector<float>& out);
-int split_stem(fx_engine* e, const PackedLayer& L, const float* in0_f32, void* s2d_split, void* conv_out_split, void* pooled_split, int n,
+size_t split_stem_scratch_bytes(int n);
+int split_stem(fx_engine* e, const PackedLayer& L, const float* in0_f32, void* xs2d_split, void* conv_out_split, void* pooled_split, int n,
                cudaStream_t stream);
 
 // conv_flat.cu (bf16 tcgen05 weight-stationary halo-tile path: stem, layer1, layer2 3x3/s1)

@@ -41,6 +41,10 @@ print("layer ms:", " ".join(f"{i}:{v / 5:.3f}" for i, v in enumerate(acc)))
 eng.close()
 """
 import tempfile
+if "--direct" in sys.argv:  # one interpreter, current FX_TIGHT_SIMT setting (what ncu is pointed at)
+    sys.argv = [sys.argv[0], str(ROOT)]
+    exec(compile(WORKER, "worker", "exec"))
+    sys.exit(0)
 tmp = Path(tempfile.mkdtemp()) / "w.py"
 tmp.write_text(WORKER)
 for knob in ("0", "1"):
