@@ -70,12 +70,15 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     constexpr int kA = 128 * BK * 2, kB = BN * BK * 2, kStage = 2 * kA + 2 * kB;
     constexpr int KSTEPS = BK / 16;
     constexpr int HC = BN / 2;  // accumulator columns per epilogue warp
+    // hand-over buffers: the whole TMEM (512 columns), so that the tensor core can run a short-K tile ahead while the
+    // accumulate warps are busy with the previous tile's epilogue (residual, split, stores)
+    constexpr int NBUF = 512 / BN;
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = sbase + STAGES * kStage;
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
-    const uint32_t tslot = tempty0 + 16;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 8 * NBUF;
+    const uint32_t tslot = tempty0 + 8 * NBUF;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,13 +95,13 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
             mbar_init(full0 + 8 * i, 1);
             mbar_init(empty0 + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NBUF; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, 256);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tslot, 2 * BN);
+    if (warp == 2) tmem_alloc(tslot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -146,7 +149,7 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         uint32_t stage = 0, phase = 0, g = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             for (int kb = 0; kb < num_kb; ++kb) {
-                const uint32_t buf = g & 1, bphase = (g >> 1) & 1;
+                const uint32_t buf = g % NBUF, bphase = (g / NBUF) & 1;
                 const int in_group = kb % GROUP;
                 if (in_group == 0) mbar_wait(tempty0 + 8 * buf, bphase ^ 1);
                 mbar_wait(full0 + 8 * stage, phase);
@@ -209,7 +212,7 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
 #pragma unroll
             for (int j = 0; j < HC; ++j) acc[j] = 0.f;
             for (int ho = 0; ho < (num_kb + GROUP - 1) / GROUP; ++ho, ++g) {
-                const uint32_t buf = g & 1, bphase = (g >> 1) & 1;
+                const uint32_t buf = g % NBUF, bphase = (g / NBUF) & 1;
                 mbar_wait(tfull0 + 8 * buf, bphase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * BN + half * HC + ((uint32_t)(q * 32) << 16);
@@ -278,7 +281,7 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -345,7 +348,7 @@ int split_pack_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, s
 template <int BN, int BK, int STAGES, int GROUP>
 static int launch_split(fx_engine* e, const CUtensorMap& mah, const CUtensorMap& mal, const CUtensorMap& mbh, const CUtensorMap& mbl,
                         const SplitParams& p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (2 * 128 * BK * 2 + 2 * BN * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 512 * 4;
+    constexpr int kSmem = 1024 + STAGES * (2 * 128 * BK * 2 + 2 * BN * BK * 2) + (2 * STAGES + 2 * (512 / BN)) * 8 + 32 + 512 * 4;
     static_assert(kSmem <= 232448, "split_conv_kernel: shared memory");
     static bool attr_done[256] = {};
     if (!attr_done[e->device & 255]) {
