@@ -720,9 +720,10 @@ static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, siz
     int rc = embed_slot_prepare(e, slot, total_bytes);
     if (rc != FX_OK || n == 0) return rc;
     fx_engine::HostSlot& hs = e->slots[slot];
-    FX_CUDA(e, cudaMemcpyAsync(hs.src_dev, src_host, total_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    static const int dbg = getenv("FX_DEBUG_E2E") ? atoi(getenv("FX_DEBUG_E2E")) : 0;  // measurement knob: 1 = skip the H2D copy, 2 = skip the D2H copy
+    if (!(dbg & 1)) FX_CUDA(e, cudaMemcpyAsync(hs.src_dev, src_host, total_bytes, cudaMemcpyHostToDevice, e->copy_stream));
     FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
-    return embed_slot_compute(e, slot, descs, n, emb_host, emb_dev_out);
+    return embed_slot_compute(e, slot, descs, n, (dbg & 2) ? nullptr : emb_host, (dbg & 2) && !emb_dev_out ? hs.emb_dev : emb_dev_out);
 }
 
 int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,

@@ -600,7 +600,9 @@ struct NormFma {
     float a[3], b[3];  // bf16_rn(fmaf(v, a[c], b[c])) == bf16_rn(((v / 255) - mean[c]) / std[c]) for v = 0..255
 };
 
-template <int NTH, int NTV>
+// CH = 3: RGB source.  CH = 1: gray carriage of an R==G==B file (fx_image_desc): ONE plane is resampled -- a third of the
+// loads and of the integer work -- and each of the three output channels normalises that byte with its own mean / std.
+template <int NTH, int NTV, int CH>
 __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8_t* __restrict__ src, const ImgDev* __restrict__ imgs,
                                                                      __nv_bfloat16* __restrict__ out, const NormFma nf, const int ppb) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -625,9 +627,9 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
 
     const int rlo = __ldg(vy_min + ya);
     const int nrows = __ldg(vy_min + yb - 1) + __ldg(vy_cnt + yb - 1) - rlo;
-    const int span_bytes = (img.col_hi - img.col_lo) * 3;
+    const int span_bytes = (img.col_hi - img.col_lo) * CH;
     const int src_pitch = (span_bytes + 15 + 16 + 3 * kFastTaps) & ~15;  // + alignment shift + zero-weight tap overreach
-    const size_t pitch = (size_t)img.w * 3;
+    const size_t pitch = (size_t)img.w * CH;
     const uint8_t* base = src + img.src_off;
 
     // stage the source rows (only the byte range the crop touches) with cp.async: the copies are in flight while the
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
     const uint32_t s_src_addr = (uint32_t)__cvta_generic_to_shared(s_src);
     for (int idx = tid; idx < nrows * nvec_max; idx += kS2dThreads) {
         const int r = (int)(((unsigned)idx * div_magic) >> 24), j = idx - r * nvec_max;
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(base + (size_t)(rlo + r) * pitch + (size_t)img.col_lo * 3);
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(base + (size_t)(rlo + r) * pitch + (size_t)img.col_lo * CH);
         const uintptr_t a0 = ga & ~(uintptr_t)15;
         const int shift = (int)(ga - a0);
         if (j == 0) s_rowoff[r] = r * src_pitch + shift;
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
     const bool active = X <= kCrop / 2 + 1;
     const int x0 = 2 * X - 3, x1 = 2 * X - 2;
     const int x0c = min(max(x0, 0), kCrop - 1), x1c = min(max(x1, 0), kCrop - 1);
-    const int off0 = (__ldg(hx_min + x0c) - img.col_lo) * 3, off1 = (__ldg(hx_min + x1c) - img.col_lo) * 3;
+    const int off0 = (__ldg(hx_min + x0c) - img.col_lo) * CH, off1 = (__ldg(hx_min + x1c) - img.col_lo) * CH;
     unsigned kx0[NTH], kx1[NTH];
 #pragma unroll
     for (int i = 0; i < NTH; ++i) {
@@ -694,11 +696,11 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
     pdl_wait();  // the staging tensor may still be read by the previous batch's stem kernel
     if (!active) return;
 
-    unsigned h0[NTV][3], h1[NTV][3];
+    unsigned h0[NTV][CH], h1[NTV][CH];
 #pragma unroll
     for (int i = 0; i < NTV; ++i)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) h0[i][c] = h1[i][c] = 0;
+        for (int c = 0; c < CH; ++c) h0[i][c] = h1[i][c] = 0;
     const int32_t* rowoff = s_rowoff;  // next staged row to enter the ring
     uint4* optr = reinterpret_cast<uint4*>(out + (((size_t)blockIdx.y * kS2dH + (ppb * b + 1)) * kS2dW + X) * kS2dC);
     for (int pj = 0; pj < npair; ++pj) {
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
 #pragma unroll
                 for (int i = 0; i + 1 < NTV; ++i)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
+                    for (int c = 0; c < CH; ++c) {
                         h0[i][c] = h0[i + 1][c];
                         h1[i][c] = h1[i + 1][c];
                     }
@@ -721,29 +723,35 @@ __global__ void __launch_bounds__(kS2dThreads) preprocess_s2d_kernel(const uint8
                 const uint8_t* p0 = rp + off0;
                 const uint8_t* p1 = rp + off1;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
+                for (int c = 0; c < CH; ++c) {
                     unsigned a0 = 1u << 23, a1 = 1u << 23;
 #pragma unroll
                     for (int i = 0; i < NTH; ++i) {
-                        a0 += kx0[i] * (unsigned)p0[c + 3 * i];
-                        a1 += kx1[i] * (unsigned)p1[c + 3 * i];
+                        a0 += kx0[i] * (unsigned)p0[c + CH * i];
+                        a1 += kx1[i] * (unsigned)p1[c + CH * i];
                     }
                     h0[NTV - 1][c] = a0 >> 24;
                     h1[NTV - 1][c] = a1 >> 24;
                 }
             }
             float z[6];
+            float f0[CH], f1[CH];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < CH; ++c) {
                 unsigned a0 = 1u << 23, a1 = 1u << 23;
 #pragma unroll
                 for (int i = 0; i < NTV; ++i) {
                     a0 += kv[i] * h0[i][c];
                     a1 += kv[i] * h1[i][c];
                 }
-                // top byte -> float 2^23 + v (one PRMT), then the normalisation as an FMA
-                z[c] = fmaf(__uint_as_float(__byte_perm(a0, 0x4B000000u, 0x7543)) - 8388608.f, na0[c], nb0[c]);
-                z[3 + c] = fmaf(__uint_as_float(__byte_perm(a1, 0x4B000000u, 0x7543)) - 8388608.f, na1[c], nb1[c]);
+                // top byte -> float 2^23 + v (one PRMT)
+                f0[c] = __uint_as_float(__byte_perm(a0, 0x4B000000u, 0x7543)) - 8388608.f;
+                f1[c] = __uint_as_float(__byte_perm(a1, 0x4B000000u, 0x7543)) - 8388608.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {  // the normalisation as an FMA; a gray plane feeds all three channels
+                z[c] = fmaf(f0[CH == 1 ? 0 : c], na0[c], nb0[c]);
+                z[3 + c] = fmaf(f1[CH == 1 ? 0 : c], na1[c], nb1[c]);
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -806,11 +814,14 @@ static PreKernel* pre_kernels() {
 
 using S2dKernel = void (*)(const uint8_t*, const ImgDev*, __nv_bfloat16*, NormFma, int);
 
-// [NTH class 2/4/5][NTV class 2/4/5]
+// [channels 3 / 1][NTH class 2/4/5][NTV class 2/4/5]
 static S2dKernel* s2d_kernels() {
-    static S2dKernel table[9] = {preprocess_s2d_kernel<2, 2>, preprocess_s2d_kernel<2, 4>, preprocess_s2d_kernel<2, 5>,
-                                 preprocess_s2d_kernel<4, 2>, preprocess_s2d_kernel<4, 4>, preprocess_s2d_kernel<4, 5>,
-                                 preprocess_s2d_kernel<5, 2>, preprocess_s2d_kernel<5, 4>, preprocess_s2d_kernel<5, 5>};
+#define FX_S2D_ROW(C) \
+    preprocess_s2d_kernel<2, 2, C>, preprocess_s2d_kernel<2, 4, C>, preprocess_s2d_kernel<2, 5, C>, preprocess_s2d_kernel<4, 2, C>, \
+        preprocess_s2d_kernel<4, 4, C>, preprocess_s2d_kernel<4, 5, C>, preprocess_s2d_kernel<5, 2, C>, preprocess_s2d_kernel<5, 4, C>, \
+        preprocess_s2d_kernel<5, 5, C>
+    static S2dKernel table[18] = {FX_S2D_ROW(3), FX_S2D_ROW(1)};
+#undef FX_S2D_ROW
     return table;
 }
 
@@ -848,7 +859,7 @@ int preprocess_init(fx_engine* e) {
     const int max_smem = 3072 + std::max(kMaxTmpRows * kCrop * 3 + kPreWarps * kRowBufCap, 97 * 1024);
     for (int i = 0; i < 27; ++i)
         FX_CUDA(e, cudaFuncSetAttribute(pre_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 18; ++i)
         FX_CUDA(e, cudaFuncSetAttribute(s2d_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     const char* old = getenv("FX_DEBUG_PRE_BANDED");  // measurement knob: force the banded kernel for the bf16 staging output
     e->pre_force_banded = old && old[0] == '1';
@@ -959,7 +970,7 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
     int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
     bool all_s2d = mode == PreOut::IN0_BF16 && !e->pre_force_banded && e->norm_fma_ok;  // every image can take the column-walk kernel
-    int s2d_smem = 0, s2d_smem16 = 0, s2d_nth = 2, s2d_ntv = 2;
+    int s2d_smem = 0, s2d_smem16 = 0, s2d_nth = 2, s2d_ntv = 2, s2d_channels = 3;
     bool s2d_ppb16 = e->s2d_ppb16;
     for (int i = 0; i < n; ++i) {
         const fx_image_desc& d = descs[i];
@@ -984,6 +995,8 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
         min_band = std::min(min_band, ge->band);
         // fast path: RGB, few taps, and the band's source rows + uint8 band fit in 96 KB (2 blocks / SM)
         const int src_pitch = ((ge->col_hi - ge->col_lo) * 3 + 15 + 16 + 3 * kFastTaps) & ~15;
+        const int s2d_pitch = ((ge->col_hi - ge->col_lo) * d.channels + 15 + 16 + 3 * kFastTaps) & ~15;  // as the s2d kernel computes it
+        if (i == 0) s2d_channels = d.channels;
         const int need = 16 * 8 * 4 + (kMaxTmpRows + 8) * 4 + ge->max_rows * src_pitch + (ge->max_rows + kFastTaps) * kRowBytes + 16;
         im.fast = d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->band == 16 && ge->max_rows <= kMaxTmpRows &&
                   need <= 96 * 1024;
@@ -991,12 +1004,13 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
             nth = std::max(nth, ge->cnt_h);
             ntv = std::max(ntv, ge->cnt_v);
         }
-        if (d.channels == 3 && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->noclip && ge->s2d_rows[0] <= kMaxTmpRows &&
-            s2d_smem_bytes(ge->s2d_rows[0], src_pitch) <= 100 * 1024) {
-            s2d_smem = std::max(s2d_smem, s2d_smem_bytes(ge->s2d_rows[0], src_pitch));
+        // column-walk kernel: every image of the batch has the same channel count (3, or 1 = gray carriage), few taps
+        if (d.channels == s2d_channels && ge->cnt_h <= kFastTaps && ge->cnt_v <= kFastTaps && ge->noclip && ge->s2d_rows[0] <= kMaxTmpRows &&
+            s2d_smem_bytes(ge->s2d_rows[0], s2d_pitch) <= 100 * 1024) {
+            s2d_smem = std::max(s2d_smem, s2d_smem_bytes(ge->s2d_rows[0], s2d_pitch));
             // (optional) bands of 16 row pairs: only while the staged rows stay small (up-scales)
-            if (ge->s2d_rows[1] <= kMaxTmpRows && s2d_smem_bytes(ge->s2d_rows[1], src_pitch) <= 32 * 1024)
-                s2d_smem16 = std::max(s2d_smem16, s2d_smem_bytes(ge->s2d_rows[1], src_pitch));
+            if (ge->s2d_rows[1] <= kMaxTmpRows && s2d_smem_bytes(ge->s2d_rows[1], s2d_pitch) <= 32 * 1024)
+                s2d_smem16 = std::max(s2d_smem16, s2d_smem_bytes(ge->s2d_rows[1], s2d_pitch));
             else
                 s2d_ppb16 = false;
             s2d_nth = std::max(s2d_nth, ge->cnt_h);
@@ -1016,7 +1030,7 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     plan.s2d = all_s2d;
     if (all_s2d) {
         const int ih = s2d_nth <= 2 ? 0 : (s2d_nth <= 4 ? 1 : 2), iv = s2d_ntv <= 2 ? 0 : (s2d_ntv <= 4 ? 1 : 2);
-        plan.kernel = ih * 3 + iv;
+        plan.kernel = (s2d_channels == 1 ? 9 : 0) + ih * 3 + iv;
         plan.ppb = s2d_ppb16 ? 16 : 8;
         plan.smem = s2d_ppb16 ? s2d_smem16 : s2d_smem;
         plan.bands = kS2dPairs / plan.ppb;

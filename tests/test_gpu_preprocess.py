@@ -130,6 +130,17 @@ def test_bf16_staging_column_walk_kernel_bit_exact(eng_b, shape):
     _check_staging(eng_b, synthetic.ragged_images([shape] * 3, seed=shape[0] + shape[1]))
 
 
+@pytest.mark.parametrize("shape", [(512, 512), (224, 224), (300, 500), (448, 333), (256, 256), (640, 480)])
+def test_bf16_staging_gray_carriage_column_walk_kernel_bit_exact(eng_b, shape):
+    """All-gray-carriage, few-tap batches take the one-plane variant of preprocess_s2d_kernel (the C4 workload as one
+    plane): the single resampled byte feeds the three channels, each with its own mean / std -- bit-exact against the
+    reference transform of the R==G==B image (src/feature_extraction.py:200-207 on a 3-channel file with equal planes)."""
+    h, w = shape
+    imgs = [np.ascontiguousarray(synthetic.mri_like_images(1, max(h, w), seed=h + w + k)[0][:h, :w, 0]) for k in range(2)]
+    imgs.append(np.random.default_rng(h * w).integers(0, 256, (h, w), dtype=np.uint8))  # noise: every tap matters
+    _check_staging(eng_b, imgs)
+
+
 def test_bf16_staging_mixed_batch_and_gray(eng_b):
     """Mixed geometry classes (incl. >5 taps and gray carriage) fall back to the banded kernel; same contract."""
     imgs = synthetic.ragged_images([(224, 224), (1000, 700), (512, 512), (2048, 1536), (61, 67)], seed=3)
