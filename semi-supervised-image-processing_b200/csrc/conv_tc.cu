@@ -50,6 +50,10 @@ struct TcConvParams {
     // (torchvision/models/resnet.py:239-243) on the SAME input and output tiling: one tap, no padding, no ReLU,
     // weights from map_b2.  It shares the launch (and fills the tail wave) of the block's 3x3 / stride-2 conv1.
     int ds_tiles;
+    // CTA-pair kernel with resident weights (layer2.0): the downsample conv is FUSED into its conv1 unit instead -- its
+    // input pixel (2 oh, 2 ow) is exactly the centre tap's A tile, so at that K-block a second MMA with the downsample
+    // weights accumulates into a second TMEM accumulator; no extra units, no second pass over the input
+    int ds_fused;
     const float* ds_bias;
     __nv_bfloat16* ds_out;
     int split_full, split_tail;  // CTA-pair kernel only: see the work-unit comment in tc2_conv_kernel
@@ -314,16 +318,19 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // RESB: 2 KB per epilogue warp (32 rows x 64 B) to turn the accumulator layout (one pixel per lane) into whole
     // 64-byte pieces of pixel rows before they go to global memory
     const uint32_t stage_out0 = (tslot + 16 + 2 * 512 * 4 + 127u) & ~127u;
+    const bool fused = RESB && p.ds_fused;
     for (int i = threadIdx.x; i < p.cout; i += kTcThreads) {
         bias_s[i] = __ldg(p.bias + i);
-        if (p.ds_tiles) bias_s[512 + i] = __ldg(p.ds_bias + i);
+        if (p.ds_tiles || fused) bias_s[512 + i] = __ldg(p.ds_bias + i);
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    constexpr uint32_t kTmemCols = 2 * BN;
+    // RESB (BN = 128): room for the fused downsample accumulator beside each of the two main ones
+    constexpr uint32_t kAccStride = RESB ? 2 * BN : BN;
+    constexpr uint32_t kTmemCols = 2 * kAccStride;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -349,10 +356,10 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t tmem_base = *tslot_ptr;
     const int num_kb = p.kh * p.kw * p.cchunks;
     if (RESB && warp == 0 && elect_one_sync()) {  // constant data: fetched before waiting for the previous kernel
-        const int n_res = num_kb + (p.ds_tiles ? p.cchunks : 0);
+        const int n_res = num_kb + ((p.ds_tiles || fused) ? p.cchunks : 0);
         if (leader) mbar_expect_tx(wbar, 2 * n_res * kB);
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d_2cta(sB + kb * kB, &map_b, wbar, kb * BK, (int)rank * (BN / 2));
-        if (p.ds_tiles)
+        if (p.ds_tiles || fused)
             for (int cc = 0; cc < p.cchunks; ++cc) tma_load_2d_2cta(sB + (num_kb + cc) * kB, &map_b2, wbar, cc * BK, (int)rank * (BN / 2));
         if (!leader) mbar_arrive_leader(wbar);
     }
@@ -365,7 +372,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // (p.split_tail > 0; layer4 at batch 256 has 98 tiles for 74 pairs) the tiles of the last, mostly empty wave are
     // cut into two 256 x BN/2 halves so that the tail wave costs half a tile time: unit u < split_full is full tile
     // u, the others are (tile split_full + (u - split_full) / 2, half (u - split_full) & 1), N = BN/2 MMAs.
-    const int n_units = p.split_tail ? p.split_full + 2 * p.split_tail : pair_tiles + p.ds_tiles;
+    const int n_units = p.split_tail ? p.split_full + 2 * p.split_tail : pair_tiles + p.ds_tiles;  // fused downsample: ds_tiles == 0
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own 128 A rows + own half of the weight K-block =====
@@ -432,10 +439,11 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * as, aphase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint32_t tmem_d = tmem_base + as * kAccStride;
                 const bool ds_unit = !p.split_tail && t0 >= pair_tiles;
                 const int nkb = ds_unit ? p.cchunks : num_kb;
                 const uint32_t idesc_u = (p.split_tail && t0 >= p.split_full) ? idesc_half : idesc;
+                const int centre0 = ((p.kh >> 1) * p.kw + (p.kw >> 1)) * p.cchunks;  // first K-block of the centre tap
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
@@ -445,6 +453,14 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             umma_bf16_2cta(tmem_d, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc_u, (kb | k) != 0);
+                        if (RESB && fused && kb >= centre0 && kb < centre0 + p.cchunks) {
+                            // the 1x1 / stride-2 downsample reads input pixel (2 oh, 2 ow): this very A tile
+                            const int cc = kb - centre0;
+                            const uint32_t bd_lo = (sB + (num_kb + cc) * kB) >> 4;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_bf16_2cta(tmem_d + BN, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(bd_lo + 2 * k), idesc, (cc | k) != 0);
+                        }
                         umma_commit_2cta(empty0 + 8 * stage);
                         if (kb == nkb - 1) umma_commit_2cta(tfull0 + 8 * as);
                     }
@@ -466,9 +482,9 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int nl = row >> (p.wt_log2 + p.ht_log2);
         int it = 0;
         for (int t0 = pair; t0 < n_units; t0 += n_pairs, ++it) {
-            const bool ds = !p.split_tail && t0 >= pair_tiles;
+            const bool ds_unit = !p.split_tail && t0 >= pair_tiles;
             const int half = (p.split_tail && t0 >= p.split_full) ? ((t0 - p.split_full) & 1) : -1;
-            const int t = ds ? t0 - pair_tiles : (half >= 0 ? p.split_full + ((t0 - p.split_full) >> 1) : t0);
+            const int t = ds_unit ? t0 - pair_tiles : (half >= 0 ? p.split_full + ((t0 - p.split_full) >> 1) : t0);
             // output channels of this unit handled by this warp: BN/4 (full tile) or BN/8 (half tile) per column group
             const int cpg = half >= 0 ? BN / 8 : BN / 4;
             const int ch0 = (half >= 0 ? half * (BN / 2) : 0) + cg * cpg;  // first channel within the tile's BN
@@ -486,6 +502,10 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
             const size_t obase = pix * p.cout + (size_t)n_tile * BN;
 
+            // fused downsample: pass 0 drains the conv1 accumulator, pass 1 the downsample one beside it
+            const int n_pass = (RESB && fused) ? 2 : 1;
+            for (int pass = 0; pass < n_pass; ++pass) {
+            const bool ds = (RESB && fused) ? pass == 1 : ds_unit;
             // the residual does not depend on the accumulator: fetch this thread's BN/4 channels while the MMAs
             // of the tile are still running, so the load latency is off the epilogue's critical path
             constexpr int kResVec = BN / 32;  // uint4 (8 bf16) per thread
@@ -497,9 +517,11 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int j = 0; j < kResVec; ++j)
                     if (j < 2 * nci) res[j] = __ldg(rp + j);
             }
-            mbar_wait(tfull0 + 8 * as, aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+            if (pass == 0) {
+                mbar_wait(tfull0 + 8 * as, aphase);
+                tc_fence_after();
+            }
+            const uint32_t taddr = tmem_base + as * kAccStride + (pass ? BN : 0) + ((uint32_t)(q * 32) << 16);
             // Short-K units (nine K-blocks, or ONE for the grouped downsample) are paced by this epilogue, and a store in
             // which every lane writes 16 bytes of a different pixel row is 32 separate line requests.  RESB: stage the
             // warp's 32 rows x 64 B in shared memory (16-byte chunk c of row r at ((c ^ (r >> 1)) & 3), conflict-free
@@ -563,8 +585,10 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive_leader(tempty0 + 8 * as);
+            if (pass == n_pass - 1) {
+                tc_fence_before();
+                mbar_arrive_leader(tempty0 + 8 * as);
+            }
             if (staged) {
                 __syncwarp();
                 const int mypix = valid ? (int)pix : -1;
@@ -577,6 +601,7 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 __syncwarp();
             }
+            }  // pass
         }
     }
 
@@ -717,6 +742,7 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma
     constexpr int kBBytes = (BN / 2) * BK * 2;
     constexpr int kSmem = 1024 + STAGES * 128 * BK * 2 + (RESB ? kResKb : STAGES) * kBBytes + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4 +
                           (RESB ? 128 + 16 * 2048 : 0);
+    static_assert(!RESB || BN == 128, "the fused downsample accumulator needs 4 * BN <= 512 TMEM columns");
     static_assert(kSmem <= 232448, "tc2_conv_kernel: shared memory");
     static bool attr_done[256] = {};  // per device ordinal
     if (!attr_done[e->device & 255]) {
@@ -726,6 +752,14 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
     const int pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;
     if (p.ds_tiles) p.ds_tiles = pair_tiles;  // the downsample conv has the same tiling, counted in pair tiles here
+    static const bool fuse_on = [] {
+        const char* v = getenv("FX_TC_FUSEDS");
+        return !(v && v[0] == '0');
+    }();
+    if (RESB && p.ds_tiles && fuse_on && (p.kh & 1) && (p.kw & 1)) {  // downsample as a second accumulator of the conv1 unit
+        p.ds_fused = 1;
+        p.ds_tiles = 0;
+    }
     int pairs = std::max(1, std::min(pair_tiles + p.ds_tiles, e->sm_count / 2));
     // split the tail wave into half-N units when it would leave more than half of the pairs idle
     const int tail = pair_tiles % pairs;
