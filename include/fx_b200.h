@@ -41,7 +41,9 @@ typedef enum fx_status {
 } fx_status;
 
 /* Arithmetic of the trunk.  BF16 = tcgen05 tensor-core path (bf16 operands, fp32 accumulate);
- * FP32 = the tight-tolerance mode (fp32 operands and accumulate on the CUDA cores). */
+ * FP32 = the tight-tolerance mode: fp32-accurate results (relative L2 <= 1e-5 end to end against the reference's fp32
+ * path) from split fp16 operands on the tensor cores with round-to-nearest accumulation in registers (csrc/conv_split.cu);
+ * the environment variable FX_TIGHT_SIMT=1 at fx_create selects the plain fp32 CUDA-core kernel instead. */
 typedef enum fx_precision { FX_PRECISION_BF16 = 0, FX_PRECISION_FP32 = 1 } fx_precision;
 
 /* Geometry constants of the path: src/feature_extraction.py:64-67. */
