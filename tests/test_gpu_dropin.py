@@ -261,3 +261,20 @@ def test_real_mri_files_match_the_reference_goldens(golden_dir, monkeypatch):
     monkeypatch.setenv(fx.DECODE_MODE_ENV, "thread")
     monkeypatch.setenv(fx.PRECISION_ENV, "fp32")
     check(fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=8), 1e-5, 0.999999)
+
+
+def test_oversized_file_path_is_bit_identical_to_the_kernel_path(dataset, monkeypatch):
+    """Lowering the host-resize threshold sends the 300x500 / 512x512 / 640x480 files through Pillow's resize on the host
+    (the reference's own call) instead of the kernel's resampler: the embeddings must not change by a single bit -- which
+    also says the kernel's integer resampler IS Pillow's."""
+    from ssip_b200 import _decode_pool as dp
+
+    root, imgs = dataset
+    records = fx.discover_image_records(root)
+    monkeypatch.setenv(fx.DECODE_MODE_ENV, "thread")
+    a = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=8)
+    monkeypatch.setattr(dp, "HOST_RESIZE_SHORT_SIDE", 280)
+    monkeypatch.setattr(fx, "HOST_RESIZE_SHORT_SIDE", 280)
+    b = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=8)
+    assert np.array_equal(a.embeddings, b.embeddings)
+    assert [r.relative_path for r in a.records] == [r.relative_path for r in b.records]

@@ -421,3 +421,72 @@ def test_digest_equals_the_reference_loop(tmp_path):
     (tmp_path / "f0007.bin").unlink()
     with pytest.raises(FileNotFoundError):  # as the reference: a vanished file aborts the run
         A.dataset_digest(recs)
+
+
+def test_oversized_files_are_resized_on_the_host_exactly_as_the_reference_would(tmp_path, monkeypatch):
+    """Files whose short side exceeds what the preprocess kernel's band buffer takes are resized right after the decode with
+    the reference's own call (torchvision functional.resize -> PIL resize(BILINEAR), src/feature_extraction.py:200-203); the
+    kernel then sees a 256-short-side image, for which Resize(256) is the identity.  Threshold lowered here to keep it small."""
+    from PIL import Image
+    from torchvision.transforms import functional as TF
+
+    from ssip_b200 import _decode_pool as dp
+
+    monkeypatch.setattr(dp, "HOST_RESIZE_SHORT_SIDE", 300)
+    for h, w in [(640, 480), (333, 777), (301, 301)]:
+        arr = synthetic.ragged_images([(h, w)], seed=h)[0]
+        img = Image.fromarray(arr)
+        got = dp.host_resize_if_oversized(img)
+        want = TF.resize(img, 256)
+        assert got.size == want.size == dp.resized_size(h, w)[::-1]
+        assert np.array_equal(np.asarray(got), np.asarray(want))
+        # and the whole reference transform of the pre-resized image is the transform of the original
+        t = rp_transform()
+        assert torch.equal(t(got), t(img))
+    small = Image.fromarray(synthetic.ragged_images([(300, 500)], seed=1)[0])
+    assert dp.host_resize_if_oversized(small) is small
+    p = tmp_path / "big.png"
+    Image.fromarray(synthetic.ragged_images([(640, 480)], seed=2)[0]).save(p)
+    assert dp._probe_chunk([str(p)])[0][:2] == (341, 256)  # the header pass reports what the decode pass will deliver
+
+
+def rp_transform():
+    from oracle import reference_path as rp
+
+    return rp.port_transform()
+
+
+def test_worker_exceptions_come_back_as_their_own_class():
+    from PIL import Image, UnidentifiedImageError
+
+    from ssip_b200._decode_pool import rebuild_exception
+
+    assert type(rebuild_exception("ValueError", "x")) is ValueError
+    assert type(rebuild_exception("MemoryError", "x")) is MemoryError
+    assert type(rebuild_exception("DecompressionBombError", "x")) is Image.DecompressionBombError
+    assert type(rebuild_exception("UnidentifiedImageError", "x")) is UnidentifiedImageError
+    assert type(rebuild_exception("NoSuchThing", "x")) is RuntimeError and "NoSuchThing" in str(rebuild_exception("NoSuchThing", "x"))
+
+
+def test_cli_fan_out_starts_one_worker_per_visible_gpu(monkeypatch, tmp_path):
+    """`--device cuda` on a multi-GPU box = all of them: the parent starts WORLD_SIZE workers with the
+    torchrun environment and the same arguments, and reports the first failure.  (Workers replaced by a stub here.)"""
+    import subprocess as sp
+
+    calls = []
+
+    class FakeProc:
+        def __init__(self, cmd, env):
+            calls.append((cmd, {k: env[k] for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}, env["PYTHONPATH"]))
+            self.rank = int(env["RANK"])
+
+        def wait(self):
+            return 3 if self.rank == 2 else 0
+
+    monkeypatch.setattr(sp, "Popen", lambda cmd, env=None: FakeProc(cmd, env))
+    rc = fx._fan_out(["--data-dir", str(tmp_path), "--device", "cuda", "--batch-size", "64"], 4)
+    assert rc == 3 and len(calls) == 4
+    assert [c[1]["RANK"] for c in calls] == ["0", "1", "2", "3"] and {c[1]["WORLD_SIZE"] for c in calls} == {"4"}
+    assert len({c[1]["MASTER_PORT"] for c in calls}) == 1 and calls[0][1]["MASTER_ADDR"] == "127.0.0.1"
+    assert calls[0][0][1:3] == ["-m", "ssip_b200.feature_extraction"] and calls[0][0][-2:] == ["--batch-size", "64"]
+    assert str(ROOT) in calls[0][2].split(os.pathsep)
