@@ -34,8 +34,6 @@ int embed_slot_compute(fx_engine* e, int slot, const fx_image_desc* descs, int n
 
 namespace {
 
-constexpr int kJpegParts = 4;
-
 struct NvJpegApi {
     void* so = nullptr;
     decltype(&nvjpegCreateEx) CreateEx = nullptr;
@@ -55,22 +53,13 @@ struct JpegCtx {
     nvjpegHandle_t handle = nullptr;
     int backend = 0;  // FX_JPEG_BACKEND_HARDWARE or FX_JPEG_BACKEND_GPU, whichever the handle was created for
     nvjpegJpegStream_t probe_stream = nullptr;
-    // The host part of nvjpegDecodeBatched (bitstream parsing, Huffman set-up: 7.3 ms per 256 files, measured) is what paces
-    // the file path, and it is single-threaded per call.  A slot's JPEGs are therefore cut into kJpegParts sub-batches, each
-    // decoded by its own host thread with its own nvJPEG state on its own stream; the copy stream joins them by events.
-    struct Part {
+    struct Slot {
         nvjpegJpegState_t state = nullptr;
         int init_batch = 0;
-        cudaStream_t stream = nullptr;
-        cudaEvent_t done = nullptr;
-    };
-    struct Slot {
-        Part parts[kJpegParts];
         uint8_t* bits = nullptr;  // page-locked bitstream buffer of the slot (fx_jpeg_read_files)
         size_t bits_cap = 0;
     } slots[FX_HOST_SLOTS + 1];  // the extra one serves the synchronous fx_jpeg_decode
     int io_threads = 8;
-    int parts = kJpegParts;  // FX_JPEG_PARTS (1..kJpegParts)
 };
 
 template <typename T>
@@ -187,60 +176,27 @@ void parallel_for(int n, int threads, F&& body) {
     for (auto& th : pool) th.join();
 }
 
-// One sub-batch on one nvJPEG state / stream.  Returns an nvJPEG status; `what` names the failing call.
-nvjpegStatus_t decode_part(JpegCtx* jc, JpegCtx::Part& part, const unsigned char* const* ptrs, const size_t* lens, nvjpegImage_t* dests, int n,
-                           cudaStream_t stream, const char** what) {
-    if (part.init_batch != n) {
-        nvjpegStatus_t st = jc->api.DecodeBatchedInitialize(jc->handle, part.state, n, 1, NVJPEG_OUTPUT_RGBI);
-        if (st != NVJPEG_STATUS_SUCCESS) {
-            part.init_batch = 0;
-            *what = "nvjpegDecodeBatchedInitialize";
-            return st;
-        }
-        part.init_batch = n;
-    }
-    nvjpegStatus_t st = jc->api.DecodeBatched(jc->handle, part.state, ptrs, lens, dests, stream);
-    if (st != NVJPEG_STATUS_SUCCESS) {
-        part.init_batch = 0;  // nvjpegDecodeBatchedInitialize also resets a failed batch
-        *what = "nvjpegDecodeBatched";
-    }
-    return st;
-}
-
-// Decode n bitstreams; `join` (may be null) is made to wait for all of them.  With more than one part the sub-batches run on
-// their own host threads and streams.  FX_ERR_UNSUPPORTED when nvJPEG turns a bitstream down (nothing useful was decoded).
 int batched_decode(fx_engine* e, JpegCtx* jc, JpegCtx::Slot& s, const std::vector<const unsigned char*>& ptrs, const std::vector<size_t>& lens,
-                   std::vector<nvjpegImage_t>& dests, cudaStream_t join) {
+                   std::vector<nvjpegImage_t>& dests, cudaStream_t stream) {
     const int n = (int)ptrs.size();
     if (n == 0) return FX_OK;
-    const int parts = std::max(1, std::min(jc->parts, n / 16));  // small batches are not worth a thread
-    nvjpegStatus_t status[kJpegParts];
-    const char* what[kJpegParts] = {};
-    auto run = [&](int k) {
-        const int lo = (int)((long long)n * k / parts), hi = (int)((long long)n * (k + 1) / parts);
-        cudaSetDevice(e->device);
-        status[k] = decode_part(jc, s.parts[k], ptrs.data() + lo, lens.data() + lo, dests.data() + lo, hi - lo, s.parts[k].stream, &what[k]);
-        if (status[k] == NVJPEG_STATUS_SUCCESS) cudaEventRecord(s.parts[k].done, s.parts[k].stream);
-    };
-    if (parts == 1) {
-        run(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int k = 1; k < parts; ++k) pool.emplace_back(run, k);
-        run(0);
-        for (auto& th : pool) th.join();
-    }
-    for (int k = 0; k < parts; ++k) {
-        if (status[k] != NVJPEG_STATUS_SUCCESS) {
-            for (int j = 0; j < parts; ++j) cudaStreamSynchronize(s.parts[j].stream);  // the other parts' decodes must not outlive the call
-            return set_error(e, status[k] == NVJPEG_STATUS_ALLOCATOR_FAILURE ? FX_ERR_NOMEM : FX_ERR_UNSUPPORTED,
-                             std::string(what[k] ? what[k] : "nvjpeg") + ": " + nvjpeg_text(status[k]));
+    if (s.init_batch != n) {
+        // max_cpu_threads = 1: measured 4.9 ms of host time per 256 files against 7.3 ms with 8.  Cutting a batch into
+        // sub-batches on their own host threads / states / streams was measured too (round 2): 31.5 k -> 26 k (2 parts) -> 17 k
+        // images/s (4 parts) -- the library serialises them and re-initialises per size -- so one call per batch it stays;
+        // the GPU-side Huffman decode (~8 ms per 256 files of 512x512) is what paces the file path.
+        nvjpegStatus_t st = jc->api.DecodeBatchedInitialize(jc->handle, s.state, n, 1, NVJPEG_OUTPUT_RGBI);
+        if (st != NVJPEG_STATUS_SUCCESS) {
+            s.init_batch = 0;
+            return set_error(e, FX_ERR_CUDA, std::string("nvjpegDecodeBatchedInitialize: ") + nvjpeg_text(st));
         }
+        s.init_batch = n;
     }
-    if (join)
-        for (int k = 0; k < parts; ++k) FX_CUDA(e, cudaStreamWaitEvent(join, s.parts[k].done, 0));
-    else
-        for (int k = 0; k < parts; ++k) FX_CUDA(e, cudaEventSynchronize(s.parts[k].done));
+    nvjpegStatus_t st = jc->api.DecodeBatched(jc->handle, s.state, ptrs.data(), lens.data(), dests.data(), stream);
+    if (st != NVJPEG_STATUS_SUCCESS) {
+        s.init_batch = 0;  // nvjpegDecodeBatchedInitialize also resets a failed batch
+        return set_error(e, FX_ERR_UNSUPPORTED, std::string("nvjpegDecodeBatched: ") + nvjpeg_text(st));
+    }
     return FX_OK;
 }
 
@@ -250,11 +206,7 @@ void jpeg_free(fx_engine* e) {
     JpegCtx* jc = ctx_of(e);
     if (!jc) return;
     for (auto& s : jc->slots) {
-        for (auto& part : s.parts) {
-            if (part.state) jc->api.JpegStateDestroy(part.state);
-            if (part.stream) cudaStreamDestroy(part.stream);
-            if (part.done) cudaEventDestroy(part.done);
-        }
+        if (s.state) jc->api.JpegStateDestroy(s.state);
         if (s.bits) cudaFreeHost(s.bits);
     }
     if (jc->probe_stream) jc->api.JpegStreamDestroy(jc->probe_stream);
@@ -321,20 +273,14 @@ int fx_jpeg_init(fx_handle e, int backend) {
         return set_error(e, FX_ERR_UNSUPPORTED, std::string("fx_jpeg_init: nvjpegCreateEx: ") + nvjpeg_text(st));
     }
     e->jpeg_state = jc;
-    cudaError_t cerr = cudaSuccess;
     for (auto& s : jc->slots)
-        for (auto& part : s.parts) {
-            if (st == NVJPEG_STATUS_SUCCESS) st = a.JpegStateCreate(jc->handle, &part.state);
-            if (cerr == cudaSuccess) cerr = cudaStreamCreateWithFlags(&part.stream, cudaStreamNonBlocking);
-            if (cerr == cudaSuccess) cerr = cudaEventCreateWithFlags(&part.done, cudaEventDisableTiming);
-        }
+        if ((st = a.JpegStateCreate(jc->handle, &s.state)) != NVJPEG_STATUS_SUCCESS) break;
     if (st == NVJPEG_STATUS_SUCCESS) st = a.JpegStreamCreate(jc->handle, &jc->probe_stream);
-    if (st != NVJPEG_STATUS_SUCCESS || cerr != cudaSuccess) {
+    if (st != NVJPEG_STATUS_SUCCESS) {
         jpeg_free(e);
-        return set_error(e, FX_ERR_CUDA, std::string("fx_jpeg_init: nvjpeg state: ") + nvjpeg_text(st) + " / " + cudaGetErrorString(cerr));
+        return set_error(e, FX_ERR_CUDA, std::string("fx_jpeg_init: nvjpeg state: ") + nvjpeg_text(st));
     }
     if (const char* t = getenv("FX_IO_THREADS")) jc->io_threads = std::max(1, atoi(t));
-    if (const char* t = getenv("FX_JPEG_PARTS")) jc->parts = std::max(1, std::min(kJpegParts, atoi(t)));
     return FX_OK;
 }
 
@@ -447,10 +393,10 @@ int fx_jpeg_decode(fx_handle e, const uint8_t* const* data, const size_t* length
         dests[i].channel[0] = dst_dev + descs[i].offset;
         dests[i].pitch[0] = (size_t)descs[i].width * 3;
     }
-    FX_CUDA(e, cudaStreamSynchronize(stream));  // dst_dev may still be in use on the caller's stream
-    // the decoder's own streams do the work; the call returns when the pixels are there (the bitstreams are the
-    // caller's and may go away afterwards)
-    return batched_decode(e, jc, jc->slots[FX_HOST_SLOTS], ptrs, lens, dests, nullptr);
+    int rc = batched_decode(e, jc, jc->slots[FX_HOST_SLOTS], ptrs, lens, dests, stream);
+    if (rc != FX_OK) return rc;
+    FX_CUDA(e, cudaStreamSynchronize(stream));  // the bitstreams are the caller's and may go away once this returns
+    return FX_OK;
 }
 
 int fx_embed_files_async(fx_handle e, int slot, const fx_file_info* info, const uint8_t* const* host_pixels, const fx_image_desc* descs, int n,
@@ -494,11 +440,7 @@ int fx_embed_files_async(fx_handle e, int slot, const fx_file_info* info, const 
                                        cudaMemcpyHostToDevice, e->copy_stream));
         }
     }
-    if ((rc = batched_decode(e, jc, s, ptrs, lens, dests, e->copy_stream)) != FX_OK) {
-        cudaStreamSynchronize(e->copy_stream);  // host-decoded stragglers already queued: let them land before the caller re-stages
-        for (auto& part : s.parts) cudaStreamSynchronize(part.stream);
-        return rc;
-    }
+    if ((rc = batched_decode(e, jc, s, ptrs, lens, dests, e->copy_stream)) != FX_OK) return rc;
     FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
     return embed_slot_compute(e, slot, descs, n, emb_host, emb_dev);
 }
