@@ -477,6 +477,30 @@ def main():
     e2e_value = world * k_e2e * B / float(t.item())
     finite = bool(torch.isfinite(out_local).all().item()) and all(bool(np.isfinite(h.numpy()).all()) for h in host_out)
 
+    # ---- the same e2e pass for R==G==B data carried as ONE plane (fx_image_desc.channels = 1, the MRI case): a third of the
+    # H2D bytes, the one-plane preprocess kernel.  Extra line; the headline e2e above is the RGB workload. ----------------
+    gray_descs = uniform_descs(B, IMG_H, IMG_W, 1)
+    gray_in = [torch.from_numpy(np.random.default_rng(500 + rank * 10 + j).integers(0, 256, B * IMG_H * IMG_W, dtype=np.uint8)).pin_memory()
+               for j in range(n_host)]
+    for j in range(3):
+        eng.embed_host(gray_in[j % n_host], gray_descs, B, B * IMG_H * IMG_W, out=host_out[0])
+    gray_runs = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k_e2e):
+            slot = i % n_slots
+            eng.embed_host_wait(slot)
+            eng.embed_host_async(slot, gray_in[i % n_host], gray_descs, B, B * IMG_H * IMG_W, host_out[slot])
+        for slot in range(n_slots):
+            eng.embed_host_wait(slot)
+        torch.cuda.synchronize()
+        gray_runs.append(time.perf_counter() - t0)
+    t = torch.tensor([statistics.median(gray_runs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_gray_value = world * k_e2e * B / float(t.item())
+
     # ---- parity of the timed rows (outside the timed region): a seeded subsample of this rank's rows of the timed
     # steps against the CPU port of the reference path on the same pool images; max over ranks -----------------------
     from oracle import reference_path as rp  # the checker, never the thing measured
@@ -575,6 +599,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_BYTES, "d2h_bytes_per_step": B * 512 * 4,
                     "steps": k_e2e, "api": "fx_embed_host_async/wait, 4 slots over 2 lanes (pinned host uint8 in, host fp32 [B,512] out); median of 3 passes",
                     "pass_seconds": [round(x, 5) for x in e2e_runs]},
+            "e2e_gray_carriage": {"value": e2e_gray_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_H * IMG_W, "d2h_bytes_per_step": B * 512 * 4,
+                                  "note": "R==G==B sources carried as one plane (channels = 1): same path, a third of the host -> device bytes"},
             "gpu_launches": int(launches * world),
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "lanes": n_lanes,
