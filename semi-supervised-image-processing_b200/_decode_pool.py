@@ -124,54 +124,6 @@ def _decode_chunk(shm_name: str, jobs: Sequence[Tuple[str, int, int, int, int, b
     return out
 
 
-def _decode_region(shm_name: str, region_off: int, region_cap: int, paths: Sequence[str], gray: bool):
-    """Single pass (no header round trip first): decode `paths` one after the other, packing the pixels back to back
-    (256-byte aligned) into this worker's region [region_off, region_off + region_cap) of the shared staging buffer.
-    Per file: (byte offset, height, width, channels written, PIL mode, bands), a failure triple, or ("overflow",) from the
-    first file that no longer fits on (the parent then falls back to the two-pass protocol for the batch)."""
-    shm = _ATTACHED.get(shm_name)
-    if shm is None:
-        for old in list(_ATTACHED):
-            _ATTACHED.pop(old).close()
-        shm = _ATTACHED[shm_name] = shared_memory.SharedMemory(name=shm_name)
-        try:
-            from multiprocessing import resource_tracker
-
-            resource_tracker.unregister(shm._name, "shared_memory")
-        except Exception:  # noqa: BLE001
-            pass
-    buf = np.frombuffer(shm.buf, dtype=np.uint8)
-    out, off, end, full = [], region_off, region_off + region_cap, False
-    for path in paths:
-        if full:
-            out.append(("overflow",))
-            continue
-        try:
-            with Image.open(path) as img:
-                mode, bands = img.mode, len(img.getbands())
-                if bands not in (1, 3) or mode in ("I", "I;16", "I;16L", "I;16B", "F", "P"):
-                    # nothing the transform accepts: the parent raises what the reference's ToTensor / Normalize would
-                    out.append((-1, img.height, img.width, 0, mode, bands))
-                    continue
-                arr = np.asarray(host_resize_if_oversized(img))
-            if arr.dtype != np.uint8:
-                out.append((-1, arr.shape[0], arr.shape[1], 0, mode, bands))
-                continue
-            c = bands
-            if gray and bands == 3 and (arr[..., 0] == arr[..., 1]).all() and (arr[..., 1] == arr[..., 2]).all():
-                arr, c = arr[..., 0], 1
-            if off + arr.size > end:
-                full = True
-                out.append(("overflow",))
-                continue
-            buf[off : off + arr.size] = np.ascontiguousarray(arr).reshape(-1)
-            out.append((off, arr.shape[0], arr.shape[1], c, mode, bands))
-            off += (arr.size + 255) // 256 * 256
-        except BaseException as exc:  # noqa: BLE001
-            out.append(_failure(exc))
-    return out
-
-
 def _read_msg(stream):
     head = stream.read(8)
     if len(head) < 8:
@@ -195,8 +147,7 @@ def _worker_main() -> None:
         if msg is None:
             break
         op, args = msg
-        fn = {"probe": _probe_chunk, "decode": _decode_chunk, "region": _decode_region}[op]
-        _write_msg(out, fn(*args))
+        _write_msg(out, _probe_chunk(*args) if op == "probe" else _decode_chunk(*args))
     for shm in _ATTACHED.values():
         shm.close()
 
@@ -264,18 +215,6 @@ class DecodePool:
         name = self._shm[slot].name
         res: list = []
         for part in self._threads.map(lambda c: self._call("decode", (name, c)), self._chunks(list(jobs))):
-            res.extend(part)
-        return res
-
-    def decode_regions(self, slot: int, paths: Sequence[str], region_cap: int, gray: bool) -> list:
-        """Single-pass decode of one batch: the files are dealt to the workers in contiguous runs, worker k packs its run
-        into region k (region_cap bytes) of the slot's buffer.  One round trip per worker instead of two per 8 files."""
-        name = self._shm[slot].name
-        paths = list(paths)
-        per = (len(paths) + self.workers - 1) // self.workers
-        runs = [(k, paths[k * per : (k + 1) * per]) for k in range(self.workers) if paths[k * per : (k + 1) * per]]
-        res: list = []
-        for part in self._threads.map(lambda kr: self._call("region", (name, kr[0] * region_cap, region_cap, kr[1], gray)), runs):
             res.extend(part)
         return res
 

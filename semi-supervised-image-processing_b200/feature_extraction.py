@@ -462,50 +462,8 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int,
             off += (h * w * c + 255) // 256 * 256
         return (sel, pixels), descs, n, off, ok
 
-    # decoded sizes seen so far (256-byte aligned): the largest sizes the workers' regions, the mean says whether regions
-    # sized for the largest file would be mostly padding (ragged datasets keep the exact two-pass layout)
-    region = {"bytes_per_file": 0, "sum": 0, "count": 0}
-
-    def seen(nbytes: int) -> None:
-        region["bytes_per_file"] = max(region["bytes_per_file"], nbytes)
-        region["sum"] += nbytes
-        region["count"] += 1
-
     def stage_with_processes(pool: DecodePool, chunk, lo, slot):
-        """Worker processes decode straight into the slot's shared, page-locked buffer.  Once a batch has shown how large
-        the decoded files are, later batches take ONE pass: every worker packs its run of files into its own region of
-        the buffer (no header round trip, one request per worker); a batch that does not fit its regions (ragged sizes)
-        is redone with the two-pass protocol below."""
-        if region["bytes_per_file"] and region["bytes_per_file"] * region["count"] <= 1.5 * region["sum"]:
-            per = (len(chunk) + pool.workers - 1) // pool.workers
-            cap = (int(per * region["bytes_per_file"] * 1.125) + 4095) // 4096 * 4096
-            total = cap * pool.workers
-            finish(slot)
-            if staging[slot] is None or staging[slot].numel() < total:
-                _unpin(staging[slot])
-                staging[slot] = None
-                shm, _ = pool.buffer(slot, total)
-                staging[slot] = _pin(torch.frombuffer(shm.buf, dtype=torch.uint8))
-            done = pool.decode_regions(slot, [str(r.absolute_path) for r in chunk], cap, gray)
-            if not any(isinstance(r[0], str) and r[0] == "overflow" for r in done):
-                descs = (N.ImageDesc * len(chunk))()
-                n, kept_idx, mark = 0, [], len(failures)
-                for k, (rec, res) in enumerate(zip(chunk, done)):
-                    if isinstance(res[0], str):  # failure triple
-                        if res[0] != "decode":
-                            raise rebuild_exception(res[1], res[2])
-                        fail(rec, res[2])
-                        continue
-                    off, h, w, c, pil_mode, bands = res
-                    _check_mode(pil_mode, bands)  # raises like the reference's transform for anything but three 8-bit bands
-                    if off < 0:
-                        raise TypeError(f"unsupported pixel type for mode {pil_mode!r}")
-                    descs[n].offset, descs[n].height, descs[n].width, descs[n].channels = off, h, w, c
-                    seen((h * w * c + 255) // 256 * 256)
-                    kept_idx.append(lo + k)
-                    n += 1
-                return (descs, n, total, kept_idx) if n else None
-            region.update(bytes_per_file=0, sum=0, count=0)  # sizes changed under us: learn them again from the two-pass batch
+        """Header pass -> layout -> worker processes decode straight into the slot's shared, page-locked buffer."""
         metas = pool.probe([str(r.absolute_path) for r in chunk])
         jobs, ok, off = [], [], 0
         for k, (rec, m) in enumerate(zip(chunk, metas)):
@@ -537,7 +495,6 @@ def _extract_local(records: Sequence[ImageRecord], eng: Engine, batch_size: int,
                 fail(records[idx], res[2])
                 continue
             descs[n].offset, descs[n].height, descs[n].width, descs[n].channels = job[1], job[2], job[3], res
-            seen((job[2] * job[3] * res + 255) // 256 * 256)
             kept_idx.append(idx)
             n += 1
         return (descs, n, off, kept_idx) if n else None

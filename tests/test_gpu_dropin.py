@@ -256,7 +256,7 @@ def test_real_mri_files_match_the_reference_goldens(golden_dir, monkeypatch):
     check(a, 1e-2, 0.999)
     monkeypatch.setenv(fx.DECODE_MODE_ENV, "process")
     monkeypatch.setenv(fx.DECODE_THREADS_ENV, "4")
-    b = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=5)  # batch 1 two passes, batches 2..4 the single-pass regions
+    b = fx.extract_embeddings(records, torch.device("cuda:0"), batch_size=16)
     assert np.array_equal(a.embeddings, b.embeddings)
     monkeypatch.setenv(fx.DECODE_MODE_ENV, "thread")
     monkeypatch.setenv(fx.PRECISION_ENV, "fp32")

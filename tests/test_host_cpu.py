@@ -357,23 +357,6 @@ def test_decode_pool_processes_write_pillow_pixels_into_shared_memory(tmp_path):
             assert np.array_equal(buf[o : o + want.size].reshape(want.shape), want)
         del buf
         assert pool.buffer(1, off // 2)[1] is False  # reused, not re-created
-        # single pass: every worker packs its run of files into its own region of the buffer, no header round trip
-        cap = 256 * 1024
-        shm, _ = pool.buffer(0, cap * pool.workers)
-        res = pool.decode_regions(0, paths[:4] + [paths[5], paths[6]], cap, False)
-        buf = np.frombuffer(shm.buf, dtype=np.uint8)
-        for p, r in zip(paths[:4], res[:4]):
-            want = np.asarray(Image.open(p))
-            o, h, w, c, mode, bands = r
-            assert (h, w, c, mode, bands) == (want.shape[0], want.shape[1], 3, "RGB", 3) and o % 256 == 0
-            assert np.array_equal(buf[o : o + want.size].reshape(want.shape), want)
-        assert res[4][:2] == ("decode", "OSError")  # truncated JPEG
-        assert res[5][3:] == (1, "L", 1)  # decoded as one plane; the caller's _check_mode raises like the reference
-        offs = sorted(r[0] for r in res[:4])
-        assert offs[0] == 0 and offs[2] >= cap  # two files per worker: the second worker's run starts in region 1
-        del buf
-        tiny = pool.decode_regions(0, paths[:4], 16 * 1024, False)  # regions too small: first file that does not fit and all after it
-        assert ("overflow",) in tiny
     finally:
         pool.close()
 
