@@ -299,6 +299,10 @@ int fx_neighbor_probe(fx_handle h, const float *emb_dev, int64_t n, int d, const
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 uint64_t fx_launch_count(fx_handle h);
+/* Bytes the host-buffer entry points (fx_embed_host*) have copied host -> device since creation.  A uniform batch is
+ * copied as one 2-D copy of the source rows the crop can touch -- the transform never reads the rest (bench.py's
+ * e2e.h2d_bytes_per_step is counted here, not assumed). */
+uint64_t fx_h2d_bytes(fx_handle h);
 
 /*
  * Per-launch timing of fx_forward for roofline reporting: with profiling enabled every launch of the

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "fx_version", "fx_abi_version", "fx_last_error", "fx_create", "fx_destroy", "fx_load_weights",
     "fx_preprocess_nchw_f32", "fx_preprocess", "fx_forward", "fx_stage_nchw_f32", "fx_select_lane", "fx_set_transform", "fx_load_head", "fx_classify", "fx_embed", "fx_embed_host", "fx_embed_host_async", "fx_embed_host_async_dev", "fx_embed_host_wait",
     "fx_jpeg_init", "fx_jpeg_backend", "fx_jpeg_probe", "fx_jpeg_read_files", "fx_jpeg_decode", "fx_embed_files_async",
-    "fx_column_stats", "fx_standardize", "fx_neighbor_probe", "fx_launch_count", "fx_profile_enable", "fx_profile_read", "fx_debug_conv", "fx_debug_folded", "fx_debug_tma_probe", "fx_debug_umma_shift", "fx_debug_stem_pool", "fx_debug_mma_rate", "fx_debug_staging",
+    "fx_column_stats", "fx_standardize", "fx_neighbor_probe", "fx_launch_count", "fx_h2d_bytes", "fx_profile_enable", "fx_profile_read", "fx_debug_conv", "fx_debug_folded", "fx_debug_tma_probe", "fx_debug_umma_shift", "fx_debug_stem_pool", "fx_debug_mma_rate", "fx_debug_staging",
     "fx_host_resized_size", "fx_host_crop_offset", "fx_host_coeffs",
 )
 
@@ -112,6 +112,8 @@ def lib() -> ctypes.CDLL:
     L.fx_neighbor_probe.argtypes = [c_void_p, c_void_p, ctypes.c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.fx_launch_count.argtypes = [c_void_p]
     L.fx_launch_count.restype = c_uint64
+    L.fx_h2d_bytes.argtypes = [c_void_p]
+    L.fx_h2d_bytes.restype = c_uint64
     L.fx_profile_enable.argtypes = [c_void_p, c_int]
     L.fx_profile_read.argtypes = [c_void_p, c_void_p, c_int]
     L.fx_debug_conv.argtypes = [c_void_p, POINTER(ConvBn), c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]

@@ -55,6 +55,7 @@ struct GeomTableHost {
     int band;                // output rows per thread block
     int max_rows;            // source rows a band touches (upper bound)
     int col_lo, col_hi;      // source pixel columns touched by the crop [lo, hi)
+    int row_lo, row_hi;      // source rows touched by the crop [lo, hi)
     int cnt_h, cnt_v;        // largest tap count actually used inside the crop, per axis
     int s2d_rows[2];         // source rows a band of the s2d kernel touches (upper bound), bands of 8 / 16 row pairs
     bool noclip;             // all taps >= 0 and sums small enough that clip8 never clips
@@ -65,6 +66,7 @@ struct GeomEntry {
     int32_t* dev = nullptr;  // device copy of blob
     int ksh = 0, ksv = 0, band = 0, max_rows = 0, col_lo = 0, col_hi = 0, cnt_h = 0, cnt_v = 0;
     int s2d_rows[2] = {0, 0};
+    int row_lo = 0, row_hi = 0;  // source rows the crop touches: the only rows the kernels read (and the host path copies)
     bool noclip = false;
 };
 
@@ -103,6 +105,7 @@ struct fx_engine {
     bool weights_loaded = false;
     int staged = 0;  // images currently in the conv1 staging buffer
     uint64_t launches = 0;
+    uint64_t h2d_bytes = 0;  // bytes the host-buffer entry points have copied host -> device (fx_h2d_bytes)
     std::string err;
 
     // preprocess
@@ -245,6 +248,8 @@ void preprocess_free(fx_engine* e);
 int preprocess_lane_init(fx_engine* e);  // per-lane descriptor buffers -> the active lane's fields
 // true if `descs` repeats the active lane's previous batch (no upload needed); *kernel = the kernel that would launch
 bool preprocess_plan_hit(fx_engine* e, const fx_image_desc* descs, int n, PreOut mode, const void** kernel);
+// source rows [lo, hi) of an h x w image that the current transform's crop touches (geometry cache; FX_OK or an error)
+int preprocess_rows_needed(fx_engine* e, int h, int w, int* row_lo, int* row_hi);
 const void* avgpool_kernel_ptr(bool in_is_bf16);
 int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* descs, int n, PreOut mode,
                    void* out, cudaStream_t stream);

@@ -146,6 +146,8 @@ static bool build_geom(int h, int w, int transform, GeomTableHost& g) {
     g.w = w;
     g.col_lo = hmn[0];
     g.col_hi = hmn[kCrop - 1] + hct[kCrop - 1];
+    g.row_lo = vmn[0];
+    g.row_hi = vmn[kCrop - 1] + vct[kCrop - 1];
     g.cnt_h = *std::max_element(hct.begin(), hct.end());
     g.cnt_v = *std::max_element(vct.begin(), vct.end());
     g.band = 0;
@@ -905,11 +907,22 @@ static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
         ent.s2d_rows[0] = g.s2d_rows[0];
         ent.s2d_rows[1] = g.s2d_rows[1];
         ent.noclip = g.noclip;
+        ent.row_lo = g.row_lo;
+        ent.row_hi = g.row_hi;
         FX_CUDA(e, cudaMalloc(&ent.dev, sizeof(int32_t) * g.blob.size()));
         FX_CUDA(e, cudaMemcpy(ent.dev, g.blob.data(), sizeof(int32_t) * g.blob.size(), cudaMemcpyHostToDevice));
         it = e->geoms.emplace(key, ent).first;
     }
     *out = &it->second;
+    return FX_OK;
+}
+
+int preprocess_rows_needed(fx_engine* e, int h, int w, int* row_lo, int* row_hi) {
+    GeomEntry* ge = nullptr;
+    int rc = geom_lookup(e, h, w, &ge);
+    if (rc != FX_OK) return rc;
+    *row_lo = std::max(0, ge->row_lo);
+    *row_hi = std::min(h, ge->row_hi);
     return FX_OK;
 }
 

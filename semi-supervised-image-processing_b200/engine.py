@@ -105,6 +105,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.fx_launch_count(self._h))
 
+    @property
+    def h2d_bytes(self) -> int:
+        """Bytes the host-buffer calls have copied host -> device so far (fx_h2d_bytes)."""
+        return int(self._lib.fx_h2d_bytes(self._h))
+
     def profile(self, on: bool) -> None:
         """Bracket every trunk launch of forward() with CUDA events (fx_profile_enable)."""
         self._check(self._lib.fx_profile_enable(self._h, int(on)))
