@@ -135,6 +135,23 @@ def test_pipelined_slots_equal_the_synchronous_call():
             assert np.array_equal(outs[i].numpy(), sync[i])
     with pytest.raises(N.FxError):
         eng.embed_host_async(N.HOST_SLOTS, packed[0][0], packed[0][1], 16, packed[0][2], outs[0])
+    # uniform batches travel as one 2-D copy of the source rows the crop can touch (224 -> 256 -> centre 224: rows 14..211);
+    # ragged batches as the whole buffer.  Either way the rows equal the device-resident path's (inputs fully on the device).
+    from ssip_b200.engine import uniform_descs
+
+    x = synthetic.noise_images(16, 224, 224, seed=99)
+    pinned = torch.from_numpy(x.reshape(-1).copy()).pin_memory()
+    before = eng.h2d_bytes
+    got = eng.embed_host(pinned, uniform_descs(16, 224, 224), 16, x.size)
+    copied = eng.h2d_bytes - before
+    assert 0.85 * x.size < copied < 0.92 * x.size, (copied, x.size)
+    want = eng.embed_device(torch.from_numpy(x.reshape(-1)).cuda(), uniform_descs(16, 224, 224), 16).cpu().numpy()
+    assert np.array_equal(got, want)
+    ragged = synthetic.ragged_images([(224, 224), (300, 500)], seed=5)
+    buf, descs, total = pack_images(ragged)
+    before = eng.h2d_bytes
+    eng.embed_host(buf, descs, 2, total)
+    assert eng.h2d_bytes - before == total
 
 
 def test_config1_256_png_images_batch_32(tmp_path_factory):
