@@ -120,3 +120,20 @@ def test_extract_embeddings_with_gpu_decode(tmp_path, golden_dir, monkeypatch):
     Image.fromarray(synthetic.mri_like_images(1, 128, seed=2)[0][..., 0]).save(root / "sans_label" / "gray.jpg")
     with pytest.raises(RuntimeError, match="broadcast shape"):
         fx.extract_embeddings(fx.discover_image_records(root), torch.device("cuda:0"), batch_size=7)
+
+
+def test_gpu_decode_writes_rows_straight_into_a_device_sink(tmp_path, golden_dir, monkeypatch):
+    """The multi-GPU drop-in points the trunk's output at the rank's slot of the gather buffer (fx_embed_files_async with
+    emb_dev): same rows as through the host, for the nvJPEG and for the host-decode staging alike."""
+    monkeypatch.setenv(fx.WEIGHTS_ENV, "random-bn:1234")
+    root = _dataset(tmp_path, golden_dir)
+    records = fx.discover_image_records(root)
+    eng = fx.get_engine(torch.device("cuda:0"), min_batch=8)
+    for mode in ("nvjpeg", "thread"):
+        monkeypatch.setenv(fx.DECODE_MODE_ENV, mode)
+        host, kept_h, fail_h, _ = fx._extract_local(records, eng, 6)
+        sink = torch.full((len(records), 512), float("nan"), dtype=torch.float32, device="cuda")
+        none, kept_d, fail_d, _ = fx._extract_local(records, eng, 6, sink=sink)
+        assert none is None and kept_d == kept_h and [p.name for p in fail_d] == [p.name for p in fail_h]
+        assert torch.equal(sink[: len(kept_d)].cpu(), host), mode
+        assert bool(torch.isnan(sink[len(kept_d):]).all())  # nothing written past the kept rows
