@@ -112,6 +112,14 @@ struct fx_engine {
     float* lut_f32 = nullptr;            // [3][256]
     __nv_bfloat16* lut_bf16 = nullptr;   // [3][256]
     std::map<std::pair<int, int>, fx::GeomEntry> geoms;  // key: (height + (transform << 24), width)
+    // the coefficient tables live in ONE device arena (bump allocation): a new (height, width) costs a host-side table
+    // build and an asynchronous copy, not a cudaMalloc (a device-wide synchronisation) -- ragged datasets bring hundreds
+    // of new sizes per batch.  Dropped as a whole when full (preprocess.cu).
+    uint8_t* geom_arena = nullptr;
+    size_t geom_arena_cap = 0, geom_arena_used = 0;
+    std::vector<int32_t*> geom_spill;  // tables that did not fit in what was left of the arena (plain allocations)
+    cudaStream_t geom_stream = nullptr;  // every table upload goes through this stream ...
+    cudaEvent_t geom_ready = nullptr;    // ... and re-records this event: a consumer stream that waits for it sees every table so far
     int transform = FX_TRANSFORM_EXTRACT;
     fx::ImgDev* img_dev = nullptr;       // [max_batch]
     fx::ImgDev* img_host = nullptr;      // pinned, [max_batch]

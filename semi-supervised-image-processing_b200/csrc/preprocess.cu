@@ -100,7 +100,7 @@ int crop_offset(int size) {
 //   [.., +224*ksv)      vertical taps
 constexpr int kGeomHdr = 4 * kCrop;
 constexpr int kMaxTmpRows = 48;
-constexpr size_t kGeomCacheCap = 2048;  // distinct (height, width) coefficient tables kept on the device (about 10-60 KB each)
+constexpr size_t kGeomCacheCap = 8192;  // distinct (height, width) coefficient tables kept (the 64 MB arena usually fills first)
 constexpr int kS2dPairs = kCrop / 2 + 1;  // 113 s2d row pairs carry data; a band is 8 or 16 of them (the last one more)
 constexpr int kS2dVtRows = 34;           // output rows of the largest band (17 pairs)
 constexpr int kS2dThreads = 128;  // one thread per s2d column X = 1 .. 113
@@ -879,9 +879,27 @@ int preprocess_lane_init(fx_engine* e) {
     return FX_OK;
 }
 
-void preprocess_free(fx_engine* e) {
-    for (auto& kv : e->geoms) cudaFree(kv.second.dev);
+// Forget every cached geometry (callers make sure no kernel still reads the tables).
+static void geom_reset(fx_engine* e) {
+    for (int32_t* p : e->geom_spill) cudaFree(p);
+    e->geom_spill.clear();
     e->geoms.clear();
+    e->geom_arena_used = 0;
+    for (auto& p : e->pre_plan) {  // the plans' device records point at the tables
+        p.valid = false;
+        p.serial++;
+    }
+}
+
+void preprocess_free(fx_engine* e) {
+    geom_reset(e);
+    if (e->geom_stream) cudaStreamDestroy(e->geom_stream);
+    if (e->geom_ready) cudaEventDestroy(e->geom_ready);
+    e->geom_stream = nullptr;
+    e->geom_ready = nullptr;
+    cudaFree(e->geom_arena);
+    e->geom_arena = nullptr;
+    e->geom_arena_cap = 0;
     cudaFree(e->lut_f32);
     cudaFree(e->lut_bf16);
 }
@@ -909,8 +927,28 @@ static int geom_lookup(fx_engine* e, int h, int w, GeomEntry** out) {
         ent.noclip = g.noclip;
         ent.row_lo = g.row_lo;
         ent.row_hi = g.row_hi;
-        FX_CUDA(e, cudaMalloc(&ent.dev, sizeof(int32_t) * g.blob.size()));
-        FX_CUDA(e, cudaMemcpy(ent.dev, g.blob.data(), sizeof(int32_t) * g.blob.size(), cudaMemcpyHostToDevice));
+        const size_t bytes = (sizeof(int32_t) * g.blob.size() + 255) & ~(size_t)255;
+        if (!e->geom_arena) {
+            size_t mb = 64;
+            if (const char* v = getenv("FX_GEOM_ARENA_MB")) mb = (size_t)std::max(1, atoi(v));
+            FX_CUDA(e, cudaMalloc(&e->geom_arena, mb << 20));
+            e->geom_arena_cap = mb << 20;
+        }
+        if (e->geom_arena_used + bytes <= e->geom_arena_cap) {
+            ent.dev = reinterpret_cast<int32_t*>(e->geom_arena + e->geom_arena_used);
+            e->geom_arena_used += bytes;
+        } else {  // rare: one batch with more new sizes than the arena had room left (it is reset before the next batch)
+            FX_CUDA(e, cudaMalloc(&ent.dev, bytes));
+            e->geom_spill.push_back(ent.dev);
+        }
+        // asynchronous upload on the table stream (pageable source: staged by the runtime before the call returns); consumers
+        // wait for geom_ready, which being re-recorded behind every upload covers all tables uploaded so far
+        if (!e->geom_stream) {
+            FX_CUDA(e, cudaStreamCreateWithFlags(&e->geom_stream, cudaStreamNonBlocking));
+            FX_CUDA(e, cudaEventCreateWithFlags(&e->geom_ready, cudaEventDisableTiming));
+        }
+        FX_CUDA(e, cudaMemcpyAsync(ent.dev, g.blob.data(), sizeof(int32_t) * g.blob.size(), cudaMemcpyHostToDevice, e->geom_stream));
+        FX_CUDA(e, cudaEventRecord(e->geom_ready, e->geom_stream));
         it = e->geoms.emplace(key, ent).first;
     }
     *out = &it->second;
@@ -969,16 +1007,12 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
     plan.valid = false;
     plan.serial++;
     // The coefficient tables are cached per (height, width, transform) and a ragged dataset can hold any number of
-    // sizes: once the cache is full it is dropped as a whole (the tables of running kernels and of the other lane's
-    // plan go with it, hence the device-wide wait and the invalidated plans) and refills from this batch on.
-    if (e->geoms.size() > kGeomCacheCap) {
+    // sizes: the tables live in one device arena; once it (or the entry count) is nearly full everything is dropped (the
+    // tables of running kernels and of the other lane's plan go with it, hence the device-wide wait and the invalidated
+    // plans) and the cache refills from this batch on.
+    if (e->geoms.size() > kGeomCacheCap || !e->geom_spill.empty() || e->geom_arena_used > e->geom_arena_cap - e->geom_arena_cap / 4) {
         FX_CUDA(e, cudaDeviceSynchronize());
-        for (auto& kv : e->geoms) cudaFree(kv.second.dev);
-        e->geoms.clear();
-        for (auto& p : e->pre_plan) {
-            p.valid = false;
-            p.serial++;
-        }
+        geom_reset(e);
     }
     FX_CUDA(e, cudaEventSynchronize(e->img_host_free));
     int min_band = 16, max_tmp = 0, max_span = 0, fast_smem = 0, nth = 2, ntv = 2;
@@ -1038,6 +1072,7 @@ int preprocess_run(fx_engine* e, const uint8_t* src_dev, const fx_image_desc* de
             max_span = std::max(max_span, (ge->col_hi - ge->col_lo) * d.channels + 32);
         }
     }
+    if (e->geom_ready) FX_CUDA(e, cudaStreamWaitEvent(stream, e->geom_ready, 0));  // the tables this batch's records point at
     FX_CUDA(e, cudaMemcpyAsync(e->img_dev, e->img_host, sizeof(ImgDev) * n, cudaMemcpyHostToDevice, stream));
     FX_CUDA(e, cudaEventRecord(e->img_host_free, stream));
     plan.s2d = all_s2d;
