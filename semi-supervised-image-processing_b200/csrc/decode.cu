@@ -184,7 +184,9 @@ int batched_decode(fx_engine* e, JpegCtx* jc, JpegCtx::Slot& s, const std::vecto
         // max_cpu_threads = 1: measured 4.9 ms of host time per 256 files against 7.3 ms with 8.  Cutting a batch into
         // sub-batches on their own host threads / states / streams was measured too (round 2): 31.5 k -> 26 k (2 parts) -> 17 k
         // images/s (4 parts) -- the library serialises them and re-initialises per size -- so one call per batch it stays;
-        // the GPU-side Huffman decode (~8 ms per 256 files of 512x512) is what paces the file path.
+        // the GPU-side Huffman decode (~8 ms per 256 files of 512x512) is what paces the file path.  NVJPEG_BACKEND_HYBRID (Huffman
+        // on the host) was measured as well: its batched decode walks the files on ONE host thread whatever max_cpu_threads
+        // says -- 100 ms per 256 files, 2.6 k images/s.
         nvjpegStatus_t st = jc->api.DecodeBatchedInitialize(jc->handle, s.state, n, 1, NVJPEG_OUTPUT_RGBI);
         if (st != NVJPEG_STATUS_SUCCESS) {
             s.init_batch = 0;

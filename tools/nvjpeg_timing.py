@@ -23,7 +23,7 @@ os.environ[fx.WEIGHTS_ENV] = "random-bn:1234"
 os.environ[fx.DECODE_MODE_ENV] = "nvjpeg"
 records = fx.discover_image_records(tmp)
 eng = fx.get_engine(torch.device("cuda:0"), min_batch=256)
-eng.jpeg_init("auto")
+eng.jpeg_init(os.environ.get("SSIP_B200_NVJPEG_BACKEND", "auto"))
 paths = [str(r.absolute_path) for r in records]
 # phase timings of one slot, synchronously
 import ctypes
