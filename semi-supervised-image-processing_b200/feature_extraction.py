@@ -807,8 +807,24 @@ def _fan_out(argv: Optional[Sequence[str]], n_gpus: int) -> int:
         env = dict(os.environ, PYTHONPATH=pythonpath, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(n_gpus), LOCAL_WORLD_SIZE=str(n_gpus),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, "-m", "ssip_b200.feature_extraction", *map(str, args)], env=env))
-    codes = [p.wait() for p in procs]
-    return next((c for c in codes if c), 0)
+    # wait for all of them; if one fails, stop the others (they would otherwise sit in the collective until NCCL times out)
+    failed = 0
+    while True:
+        codes = [p.poll() for p in procs]
+        failed = next((c for c in codes if c), 0)
+        if failed or all(c is not None for c in codes):
+            break
+        time.sleep(0.2)
+    if failed:
+        for p in procs:
+            if p.poll() is None:
+                p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:  # noqa: BLE001
+                p.kill()
+    return failed
 
 
 def main(argv: Optional[Sequence[str]] = None) -> None:

@@ -480,8 +480,16 @@ def test_cli_fan_out_starts_one_worker_per_visible_gpu(monkeypatch, tmp_path):
             calls.append((cmd, {k: env[k] for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}, env["PYTHONPATH"]))
             self.rank = int(env["RANK"])
 
-        def wait(self):
-            return 3 if self.rank == 2 else 0
+            self.terminated = False
+
+        def poll(self):
+            return 3 if self.rank == 2 else (None if not self.terminated and self.rank == 3 else 0)  # rank 3 would hang in the collective
+
+        def terminate(self):
+            self.terminated = True
+
+        def wait(self, timeout=None):
+            return self.poll()
 
     monkeypatch.setattr(sp, "Popen", lambda cmd, env=None: FakeProc(cmd, env))
     rc = fx._fan_out(["--data-dir", str(tmp_path), "--device", "cuda", "--batch-size", "64"], 4)
