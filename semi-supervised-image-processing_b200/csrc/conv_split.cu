@@ -63,11 +63,15 @@ __device__ __forceinline__ void tmem_ld32s(uint32_t taddr, uint32_t (&v)[32]) {
 
 // BK: channels per K-block (64: SWIZZLE_128B rows; 16 / 32 narrower rows are possible but starve on TMA box issue).
 // GROUP: K-blocks accumulated in TMEM before the hand-over (1: a chain of BK / 16 k-steps).
-template <int BN, int BK, int STAGES, int GROUP>
+// PAIR: two CTAs of a cluster (launch attribute) compute one 256 x BN tile with M = 256 MMAs issued by the even CTA
+// (cta_group::2, protocol of tc2_conv_kernel): each CTA loads its own 128 activation rows (hi + lo) but only HALF of the
+// weight K-block (hi + lo) -- 48 KB instead of 64 KB per K-block by TMA and 6 KB instead of 8 KB per MMA out of shared
+// memory, on a kernel whose 3 MMAs per operand pair make the shared-memory pipe the bound.
+template <int BN, int BK, int STAGES, int GROUP, bool PAIR>
 __global__ void __launch_bounds__(kSplitThreads, 1)
 split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, const SplitParams p) {
-    constexpr int kA = 128 * BK * 2, kB = BN * BK * 2, kStage = 2 * kA + 2 * kB;
+    constexpr int kA = 128 * BK * 2, kB = (PAIR ? BN / 2 : BN) * BK * 2, kStage = 2 * kA + 2 * kB;
     constexpr int KSTEPS = BK / 16;
     constexpr int HC = BN / 2;  // accumulator columns per epilogue warp
     // hand-over buffers: the whole TMEM (512 columns), so that the tensor core can run a short-K tile ahead while the
@@ -83,6 +87,13 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < p.cout; i += kSplitThreads) bias_s[i] = __ldg(p.bias + i);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    // work units: PAIR: unit u = N tile u % n_tiles_n of the M tiles 2 * (u / n_tiles_n) + {0, 1} (one per CTA of the pair)
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
+    const int n_units = PAIR ? ((m_tiles + 1) >> 1) * p.n_tiles_n : p.total_tiles;
+    const int first_unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_ah);
@@ -92,18 +103,26 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(full0 + 8 * i, PAIR ? 2 : 1);  // PAIR: the leader's arrive.expect_tx + the peer producer's arrive
+            mbar_init(empty0 + 8 * i, 1);             // (multicast) commit
         }
         for (int i = 0; i < NBUF; ++i) {
-            mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 256);
+            mbar_init(tfull0 + 8 * i, 1);                       // (multicast) commit
+            mbar_init(tempty0 + 8 * i, PAIR ? 512 : 256);       // every accumulate thread (of both CTAs)
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tslot, 512);
+    if (warp == 2) {
+        if (PAIR)
+            tmem_alloc_2cta(tslot, 512);
+        else
+            tmem_alloc(tslot, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tslot_ptr;
     pdl_wait();
@@ -114,13 +133,13 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         // ===== TMA producer: hi and lo planes of the activation box and of the weight K-block =====
         if (elect_one_sync()) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t = first_unit; t < n_units; t += unit_step) {
                 const int n_tile = t % p.n_tiles_n;
-                int m_tile = t / p.n_tiles_n;
+                int m_tile = PAIR ? (t / p.n_tiles_n) * 2 + (int)rank : t / p.n_tiles_n;
                 const int tw = m_tile % p.tiles_w;
                 m_tile /= p.tiles_w;
                 const int th = m_tile % p.tiles_h;
-                const int tg = m_tile / p.tiles_h;
+                const int tg = m_tile / p.tiles_h;  // PAIR: >= tiles_g for the odd leftover: every load is out of bounds -> zeros
                 const int w0 = (tw << p.wt_log2) * p.cw_mul - p.pad_w;
                 const int h0 = (th << p.ht_log2) * p.ch_mul - p.pad_h;
                 const int n0 = tg << p.nt_log2;
@@ -129,12 +148,21 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
                     for (int s = 0; s < p.kw; ++s)
                         for (int cc = 0; cc < p.cchunks; ++cc, ++kb) {
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                            mbar_expect_tx(full0 + 8 * stage, kStage);
                             const uint32_t st = sbase + stage * kStage;
-                            tma_load_4d(st, &map_ah, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            tma_load_4d(st + kA, &map_al, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
-                            tma_load_2d(st + 2 * kA, &map_bh, full0 + 8 * stage, kb * BK, n_tile * BN);
-                            tma_load_2d(st + 2 * kA + kB, &map_bl, full0 + 8 * stage, kb * BK, n_tile * BN);
+                            if (PAIR) {
+                                if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * kStage);
+                                tma_load_4d_2cta(st, &map_ah, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                                tma_load_4d_2cta(st + kA, &map_al, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                                tma_load_2d_2cta(st + 2 * kA, &map_bh, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
+                                tma_load_2d_2cta(st + 2 * kA + kB, &map_bl, full0 + 8 * stage, kb * BK, n_tile * BN + (int)rank * (BN / 2));
+                                if (!leader) mbar_arrive_leader(full0 + 8 * stage);
+                            } else {
+                                mbar_expect_tx(full0 + 8 * stage, kStage);
+                                tma_load_4d(st, &map_ah, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                                tma_load_4d(st + kA, &map_al, full0 + 8 * stage, cc * BK, w0 + s, h0 + r, n0);
+                                tma_load_2d(st + 2 * kA, &map_bh, full0 + 8 * stage, kb * BK, n_tile * BN);
+                                tma_load_2d(st + 2 * kA + kB, &map_bl, full0 + 8 * stage, kb * BK, n_tile * BN);
+                            }
                             if (++stage == STAGES) {
                                 stage = 0;
                                 phase ^= 1;
@@ -144,10 +172,10 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         }
     } else if (warp == 1) {
         // ===== MMA issuer: GROUP K-blocks (KSTEPS k-steps x 3 split terms each) per TMEM buffer, then hand it over =====
-        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f32 accumulate, fp16 x fp16, M 128
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);  // f32 accumulate, fp16 x fp16
         constexpr uint64_t desc_hi = make_smem_desc_rowb<BK * 2>(0) & 0xFFFFFFFF00000000ull;
         uint32_t stage = 0, phase = 0, g = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = first_unit; leader && t < n_units; t += unit_step) {
             for (int kb = 0; kb < num_kb; ++kb) {
                 const uint32_t buf = g % NBUF, bphase = (g / NBUF) & 1;
                 const int in_group = kb % GROUP;
@@ -161,12 +189,23 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
                     const uint32_t d = tmem_base + buf * BN;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                        umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, (in_group | k) != 0);
-                        umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bl + 2 * k), idesc, 1);
-                        umma_bf16(d, desc_hi | (uint64_t)(al + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, 1);
+                        if (PAIR) {
+                            umma_bf16_2cta(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, (in_group | k) != 0);
+                            umma_bf16_2cta(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bl + 2 * k), idesc, 1);
+                            umma_bf16_2cta(d, desc_hi | (uint64_t)(al + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, 1);
+                        } else {
+                            umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, (in_group | k) != 0);
+                            umma_bf16(d, desc_hi | (uint64_t)(ah + 2 * k), desc_hi | (uint64_t)(bl + 2 * k), idesc, 1);
+                            umma_bf16(d, desc_hi | (uint64_t)(al + 2 * k), desc_hi | (uint64_t)(bh + 2 * k), idesc, 1);
+                        }
                     }
-                    umma_commit(empty0 + 8 * stage);
-                    if (hand_over) umma_commit(tfull0 + 8 * buf);
+                    if (PAIR) {
+                        umma_commit_2cta(empty0 + 8 * stage);
+                        if (hand_over) umma_commit_2cta(tfull0 + 8 * buf);
+                    } else {
+                        umma_commit(empty0 + 8 * stage);
+                        if (hand_over) umma_commit(tfull0 + 8 * buf);
+                    }
                 }
                 __syncwarp();
                 if (hand_over) ++g;
@@ -188,9 +227,9 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         // BN = 64 (layer 1, the stem): the residual of the tile is fetched into registers BEFORE the K loop, so its latency
         // hides behind the tile's MMAs; with 64 columns per warp (BN = 128) the registers are not there and it is read at the end.
         constexpr bool kPrefetchRes = HC == 32;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = first_unit; t < n_units; t += unit_step) {
             const int n_tile = t % p.n_tiles_n;
-            int m_tile = t / p.n_tiles_n;
+            int m_tile = PAIR ? (t / p.n_tiles_n) * 2 + (int)rank : t / p.n_tiles_n;
             const int tw = m_tile % p.tiles_w;
             m_tile /= p.tiles_w;
             const int th = m_tile % p.tiles_h;
@@ -225,7 +264,10 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
                     for (int j = 0; j < 32; ++j) acc[c + j] += __uint_as_float(v[j]);
                 }
                 tc_fence_before();
-                mbar_arrive(tempty0 + 8 * buf);
+                if (PAIR)
+                    mbar_arrive_leader(tempty0 + 8 * buf);
+                else
+                    mbar_arrive(tempty0 + 8 * buf);
             }
             if (!valid) continue;
 #pragma unroll
@@ -278,10 +320,16 @@ split_conv_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();  // the peer's shared memory / barriers stay alive until both CTAs are done
+    else
+        __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR)
+            tmem_dealloc_2cta(tmem_base, 512);
+        else
+            tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -345,18 +393,39 @@ int split_pack_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, s
     return s;
 }
 
-template <int BN, int BK, int STAGES, int GROUP>
+template <int BN, int BK, int STAGES, int GROUP, bool PAIR = false>
 static int launch_split(fx_engine* e, const CUtensorMap& mah, const CUtensorMap& mal, const CUtensorMap& mbh, const CUtensorMap& mbl,
                         const SplitParams& p, cudaStream_t stream) {
-    constexpr int kSmem = 1024 + STAGES * (2 * 128 * BK * 2 + 2 * BN * BK * 2) + (2 * STAGES + 2 * (512 / BN)) * 8 + 32 + 512 * 4;
+    constexpr int kSmem = 1024 + STAGES * (2 * 128 * BK * 2 + 2 * (PAIR ? BN / 2 : BN) * BK * 2) + (2 * STAGES + 2 * (512 / BN)) * 8 + 32 + 512 * 4;
     static_assert(kSmem <= 232448, "split_conv_kernel: shared memory");
+    auto kernel = split_conv_kernel<BN, BK, STAGES, GROUP, PAIR>;
     static bool attr_done[256] = {};
     if (!attr_done[e->device & 255]) {
-        FX_CUDA(e, cudaFuncSetAttribute(split_conv_kernel<BN, BK, STAGES, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        FX_CUDA(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_done[e->device & 255] = true;
     }
-    const int grid = std::min(p.total_tiles, e->sm_count);
-    FX_CUDA(e, launch_pdl(split_conv_kernel<BN, BK, STAGES, GROUP>, dim3(grid), dim3(kSplitThreads), kSmem, stream, mah, mal, mbh, mbl, p));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+    if (PAIR) {
+        const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_g;
+        const int n_units = ((m_tiles + 1) / 2) * p.n_tiles_n;
+        cfg.gridDim = dim3(2 * std::max(1, std::min(n_units, e->sm_count / 2)));
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    } else {
+        cfg.gridDim = dim3(std::min(p.total_tiles, e->sm_count));
+    }
+    cfg.blockDim = dim3(kSplitThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    FX_CUDA(e, cudaLaunchKernelEx(&cfg, kernel, mah, mal, mbh, mbl, p));
     FX_LAUNCH_CHECK(e, "split_conv_kernel");
     return FX_OK;
 }
@@ -407,11 +476,18 @@ int split_conv(fx_engine* e, const PackedLayer& L, const void* in, const void* r
     const uint64_t K = (uint64_t)g.kh * g.kw * g.cin;
     const uint64_t bd[2] = {K, (uint64_t)g.cout};
     const uint64_t bs[1] = {K * 2};
-    const uint32_t bbox[2] = {64, (uint32_t)bn};
+    // N = 128 layers run as CTA pairs (half of every weight K-block per CTA); FX_SPLIT_PAIR=0 keeps the single-CTA kernel
+    static const bool pair_on = [] {
+        const char* v = getenv("FX_SPLIT_PAIR");
+        return !(v && v[0] == '0');
+    }();
+    const bool pair = bn == 128 && pair_on;
+    const uint32_t bbox[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
     const uint32_t be[2] = {1, 1};
     if (rc == FX_OK) rc = tc_encode_map(e, &mbh, L.w_h16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "split conv W hi");
     if (rc == FX_OK) rc = tc_encode_map(e, &mbl, L.w_l16, 2, bd, bs, bbox, be, CU_TENSOR_MAP_SWIZZLE_128B, "split conv W lo");
     if (rc != FX_OK) return rc;
+    if (pair) return launch_split<128, 64, 4, 1, true>(e, mah, mal, mbh, mbl, p, stream);
     if (bn == 128) return launch_split<128, 64, 3, 1>(e, mah, mal, mbh, mbl, p, stream);
     return launch_split<64, 64, 4, 1>(e, mah, mal, mbh, mbl, p, stream);
 }
