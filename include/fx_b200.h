@@ -240,7 +240,8 @@ typedef struct fx_file_info {
     int32_t encoding;    /* SOF marker: 0xC0 baseline, 0xC2 progressive, ... */
     int32_t precision;   /* bits per sample */
     int32_t reserved;
-    uint64_t offset, length; /* position / size of the bitstream in the slot's page-locked buffer */
+    uint64_t offset, length; /* position / size of the bitstream in the slot's page-locked buffer; length 0 for files that do
+                              * not start with a JPEG SOI marker (or exceed 256 MiB): those are not read at all */
 } fx_file_info;
 
 /* Load nvJPEG and create the decoder for `backend` (idempotent; FX_ERR_UNSUPPORTED when nvJPEG cannot be had). */

@@ -159,6 +159,8 @@ int ensure_bits(fx_engine* e, JpegCtx::Slot& s, size_t need) {
     return FX_OK;
 }
 
+constexpr uint64_t kMaxJpegFileBytes = 1ull << 28;  // larger "JPEGs" go to the host decoder (a 65535 x 65535 frame would not fit the device buffers anyway)
+
 template <typename F>
 void parallel_for(int n, int threads, F&& body) {
     threads = std::max(1, std::min(threads, n));
@@ -324,14 +326,25 @@ int fx_jpeg_read_files(fx_handle e, int slot, const char* const* paths, int n, f
     }
     JpegCtx::Slot& s = jc->slots[slot];
     std::memset(info, 0, sizeof(fx_file_info) * (size_t)n);
-    // pass 1: sizes -> layout (64-byte aligned starts)
+    // pass 1: sizes -> layout (64-byte aligned starts).  Only files that start like a JPEG (SOI marker + the first byte of
+    // the next marker) get room in the bitstream buffer: a dataset directory may hold anything (the reference lists every
+    // file, src/feature_extraction.py:145-170), and a 2 GB volume or archive must not be pulled into page-locked memory just
+    // to learn that Pillow cannot identify it.
     parallel_for(n, jc->io_threads, [&](int i) {
         struct stat sb;
-        if (!paths[i] || stat(paths[i], &sb) != 0 || !S_ISREG(sb.st_mode)) {
+        const int fd = paths[i] ? open(paths[i], O_RDONLY | O_CLOEXEC) : -1;
+        if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+            if (fd >= 0) close(fd);
             info[i].status = FX_FILE_UNREADABLE;
             return;
         }
-        info[i].length = (uint64_t)sb.st_size;
+        uint8_t head[3] = {0, 0, 0};
+        const ssize_t r = pread(fd, head, 3, 0);
+        close(fd);
+        if (r == 3 && head[0] == 0xFF && head[1] == 0xD8 && head[2] == 0xFF && (uint64_t)sb.st_size <= kMaxJpegFileBytes)
+            info[i].length = (uint64_t)sb.st_size;
+        else
+            info[i].status = FX_FILE_HOST_DECODE;  // length 0: not read here, the host decoder opens it itself
     });
     size_t total = 0;
     for (int i = 0; i < n; ++i) {
@@ -343,7 +356,7 @@ int fx_jpeg_read_files(fx_handle e, int slot, const char* const* paths, int n, f
     // pass 2: read + frame header
     parallel_for(n, jc->io_threads, [&](int i) {
         fx_file_info& fi = info[i];
-        if (fi.status == FX_FILE_UNREADABLE) return;
+        if (fi.status != FX_FILE_GPU_JPEG) return;  // (0 = still a candidate) unreadable, or left to the host decoder by pass 1
         fi.status = FX_FILE_HOST_DECODE;
         const int fd = open(paths[i], O_RDONLY | O_CLOEXEC);
         if (fd < 0) {
@@ -442,9 +455,12 @@ int fx_embed_files_async(fx_handle e, int slot, const fx_file_info* info, const 
                                        cudaMemcpyHostToDevice, e->copy_stream));
         }
     }
-    if ((rc = batched_decode(e, jc, s, ptrs, lens, dests, e->copy_stream)) != FX_OK) return rc;
-    FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
-    return embed_slot_compute(e, slot, descs, n, emb_host, emb_dev);
+    if ((rc = batched_decode(e, jc, s, ptrs, lens, dests, e->copy_stream)) == FX_OK) {
+        cudaError_t ev = cudaEventRecord(hs.copied, e->copy_stream);
+        rc = ev == cudaSuccess ? embed_slot_compute(e, slot, descs, n, emb_host, emb_dev) : set_error(e, FX_ERR_CUDA, cudaGetErrorString(ev));
+    }
+    if (rc != FX_OK) cudaStreamSynchronize(e->copy_stream);  // the slot is not marked busy: host pixels / bitstreams must be free of DMA when the error returns
+    return rc;
 }
 
 }  // extern "C"

@@ -751,7 +751,9 @@ static int embed_host_submit(fx_handle e, int slot, const uint8_t* src_host, siz
         }
     }
     FX_CUDA(e, cudaEventRecord(hs.copied, e->copy_stream));
-    return embed_slot_compute(e, slot, descs, n, (dbg & 2) ? nullptr : emb_host, (dbg & 2) && !emb_dev_out ? hs.emb_dev : emb_dev_out);
+    rc = embed_slot_compute(e, slot, descs, n, (dbg & 2) ? nullptr : emb_host, (dbg & 2) && !emb_dev_out ? hs.emb_dev : emb_dev_out);
+    if (rc != FX_OK) cudaStreamSynchronize(e->copy_stream);  // the slot is not marked busy: the caller's buffer must be free of DMA when the error returns
+    return rc;
 }
 
 int fx_embed_host_async(fx_handle e, int slot, const uint8_t* src_host, size_t total_bytes, const fx_image_desc* descs, int n,

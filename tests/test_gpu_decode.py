@@ -54,6 +54,21 @@ def test_header_walk_sorts_files_into_gpu_and_host_decode(eng):
     assert eng.jpeg_probe(cases["baseline420"][0]).subsampling == 2 and eng.jpeg_probe(cases["baseline444"][0]).subsampling == 0
 
 
+def test_read_files_only_pulls_jpegs_into_the_page_locked_buffer(eng, tmp_path):
+    """A dataset directory may hold anything (the reference lists every file, src/feature_extraction.py:145-170): files that
+    do not start with a JPEG SOI marker are left to the host decoder unread (length 0), missing ones are flagged."""
+    rgb = synthetic.mri_like_images(1, 256, seed=1)[0]
+    blob = _jpeg(rgb, quality=90)
+    (tmp_path / "a.jpg").write_bytes(blob)
+    (tmp_path / "b.png").write_bytes(b"\x89PNG\r\n\x1a\n" + b"0" * 4096)
+    (tmp_path / "c.bin").write_bytes(b"")
+    (tmp_path / "d.jpg").write_bytes(blob[:2000])  # starts like a JPEG, no end-of-image marker
+    info = eng.jpeg_read_files(0, [str(tmp_path / n) for n in ("a.jpg", "b.png", "c.bin", "d.jpg", "missing.jpg")])
+    assert [i.status for i in info] == [N.FILE_GPU_JPEG, N.FILE_HOST_DECODE, N.FILE_HOST_DECODE, N.FILE_HOST_DECODE, N.FILE_UNREADABLE]
+    assert [i.length for i in info] == [len(blob), 0, 0, 2000, 0]
+    assert (info[0].height, info[0].width) == (256, 256) and info[0].offset % 64 == 0 and info[3].offset % 64 == 0
+
+
 def test_decoded_pixels_are_close_to_pillow(eng, golden_dir):
     blobs, want = [], []
     for p in sorted((golden_dir / "mri_real").rglob("*.jpg")):  # the reference's own files: 512x512, 4:2:0
