@@ -800,14 +800,19 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
             __syncwarp();
+            {  // shuffles, loads, stores in three batches: every dependent trip through the (busy) shared-memory pipe is slow
+                int prs[8];
+                uint4 vals[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + rr0;
-                const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                if (pr >= 0) {
-                    const uint4 val = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                    *reinterpret_cast<uint4*>(p.out + (size_t)pr * p.cout + ch * 8) = val;
+                for (int it = 0; it < 8; ++it) prs[it] = __shfl_sync(0xffffffffu, pix, it * 4 + rr0);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rr0;
+                    vals[it] = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
                 }
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    if (prs[it] >= 0) *reinterpret_cast<uint4*>(p.out + (size_t)prs[it] * p.cout + ch * 8) = vals[it];
             }
             __syncwarp();
             cur = nxt;
@@ -1277,13 +1282,15 @@ flat128x2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int pix = (real && mt < n_mt && x < p.W && i < rows_valid) ? ((img * p.H + y0 + i) * p.W + x) : -1;
             // the residual does not depend on the accumulator: its cp.async runs under the wait for the tile's MMAs (the
             // staging block is free: the previous tile's store-out is complete)
+            int prs[8];  // pixel index of the 8 rows this lane moves (residual in, result out), -1 = junk row
+#pragma unroll
+            for (int t = 0; t < 8; ++t) prs[t] = __shfl_sync(0xffffffffu, pix, t * 4 + rr0);
             if (has_res) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int rr = t * 4 + rr0;
-                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                    if (pr >= 0)
-                        cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8);
+                    if (prs[t] >= 0)
+                        cp_async16(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), p.residual + (size_t)prs[t] * p.cout + cbase + pass * 64 + ch * 8);
                 }
                 cp_async_commit();
             }
@@ -1343,14 +1350,16 @@ flat128x2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                 }
                 __syncwarp();
+                {
+                    uint4 vals[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int rr = t * 4 + rr0;
-                    const int pr = __shfl_sync(0xffffffffu, pix, rr);
-                    if (pr >= 0) {
-                        const uint4 val = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                        *reinterpret_cast<uint4*>(p.out + (size_t)pr * p.cout + cbase + pass * 64 + ch * 8) = val;
+                    for (int t = 0; t < 8; ++t) {
+                        const int rr = t * 4 + rr0;
+                        vals[t] = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
                     }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (prs[t] >= 0) *reinterpret_cast<uint4*>(p.out + (size_t)prs[t] * p.cout + cbase + pass * 64 + ch * 8) = vals[t];
                 }
                 __syncwarp();
             }

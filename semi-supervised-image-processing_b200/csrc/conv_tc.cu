@@ -590,15 +590,23 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_arrive_leader(tempty0 + 8 * as);
             }
             if (staged) {
+                // the shared-memory pipe is busy feeding the MMAs, so every dependent trip through it costs hundreds of cycles:
+                // the four shuffles go out together, then the four loads, then the four stores (two trips instead of eight)
                 __syncwarp();
                 const int mypix = valid ? (int)pix : -1;
                 __nv_bfloat16* obuf = (ds ? p.ds_out : p.out) + (size_t)n_tile * BN + ch0 + (lane & 3) * 8;
+                int pr[4];
+                uint4 val[4];
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) pr[i4] = __shfl_sync(0xffffffffu, mypix, i4 * 8 + (lane >> 2));
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
                     const int r = i4 * 8 + (lane >> 2);
-                    const int pr = __shfl_sync(0xffffffffu, mypix, r);
-                    if (pr >= 0) *reinterpret_cast<uint4*>(obuf + (size_t)pr * p.cout) = lds128(stg + r * 64 + ((((lane & 3) ^ (r >> 1)) & 3) << 4));
+                    val[i4] = lds128(stg + r * 64 + ((((lane & 3) ^ (r >> 1)) & 3) << 4));
                 }
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4)
+                    if (pr[i4] >= 0) *reinterpret_cast<uint4*>(obuf + (size_t)pr[i4] * p.cout) = val[i4];
                 __syncwarp();
             }
             }  // pass
