@@ -58,6 +58,24 @@ def test_bf16_batch_256_512_1024_rows_equal_batch_64_and_the_oracle():
     eng.close()
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_odd_batch_sizes_give_the_rows_of_batch_8(precision):
+    """Ragged last batches (and any rank's shard under torchrun) run at whatever size is left: odd leftover image of a CTA pair,
+    partial M-tiles, other split-tail decisions.  Row i must not depend on how many images travel with it."""
+    n = 1000 if precision == "bf16" else 200
+    x = synthetic.noise_images(n, 224, 224, seed=123)
+    dev = torch.from_numpy(x.reshape(-1)).cuda()
+    eng = Engine(0, max_batch=1024 if precision == "bf16" else 256, precision=precision)
+    eng.load_state_dict(rp.make_backbone(randomize_bn=True).state_dict())
+    base = _run(eng, dev[: (n // 8) * 8 * 150528], (n // 8) * 8, 8)  # n is a multiple of 8
+    sizes = (1, 2, 3, 5, 37, 63, 65, 100, 129, 255, 257, 511, 777, 1000) if precision == "bf16" else (1, 3, 37, 65, 129, 200)
+    for b in sizes:
+        out = eng.embed_device(dev[: b * 150528], uniform_descs(b, 224, 224), b)
+        torch.cuda.synchronize()
+        assert torch.equal(out, base[:b]), f"{precision} batch {b}: differs from the batch-8 rows by up to {(out - base[:b]).abs().max().item():.3e}"
+    eng.close()
+
+
 def test_bf16_batch_512_ragged_sources_equal_batch_32():
     # 512x512 sources (the C4 geometry) at batch 512: the preprocess takes the 4-tap path, the trunk the batch-512 tilings
     n = 512
