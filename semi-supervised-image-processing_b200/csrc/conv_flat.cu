@@ -532,6 +532,309 @@ flat_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// stemw: the pooled stem with TWO output columns per accumulator row (N = 128).
+//
+// flat_conv_kernel<32, 4, 4, true> spends its time on the 128 B/clk shared-memory pipe: every M128 x N64 x K16 MMA pulls
+// 4 KB of A and 2 KB of B through it (48 cycles for 32 cycles of math), 16 of them per 128 conv outputs, and the ring
+// writes / pool reads of the fused max-pool travel the same pipe.  Here the staging tensor is viewed as
+// PAIRS of s2d pixels -- [n][115][58][32 ch], 64-byte rows, SWIZZLE_64B -- and accumulator row (i, j') holds BOTH conv
+// outputs of the pair, (i, 2j') in columns 0..63 and (i, 2j'+1) in columns 64..127.  Output 2j' reads s2d columns
+// 2j'..2j'+3, output 2j'+1 reads 2j'+1..2j'+4: the union is five s2d columns t = 0..4 = pairs j', j'+1, j'+2 (first half),
+// so one filter row is five K = 16 steps instead of 2 x 4, and the A fetch per conv output is 5/8 of what it was:
+//   t = 1, 2, 3   N = 128   B rows = [tap t weights (output 2j') | tap t-1 weights (output 2j'+1)]
+//   t = 0         N = 64    tap 0 into columns 0..63          (the very first step is N = 128 with a ZERO second half:
+//   t = 4         N = 64    tap 3 into columns 64..127         it initialises both halves of the accumulator)
+// With the 16 tap tiles stored in DESCENDING tap order, [tap t | tap t-1] is simply the 128-row window that starts at tap
+// t: the resident weights stay 32 KB (+ one zero tile).  Every output still sums its 16 taps in the old order (adding an
+// exact zero first changes nothing), so the pooled rows are bit-identical to flat_conv_kernel's (knob test, FX_STEMW=0).
+// Row pitch: 57 pairs, not 58 -- the tap that would read pair 57 (s2d columns 114 / 115: conv padding and the dead column,
+// all zero) reads pair 0 of the next row instead, first half = s2d column 0 = padded pixels 0 / 1 = zero as well.  A work
+// tile (9 conv rows = 4 pooled rows) is then exactly 8 * 57 + 56 = 512 positions = 4 M-tiles, none wasted.
+// Epilogue: all eight warps drain one M-tile (lane quarter x 32-channel half); a thread holds both outputs of its pair,
+// so it stores max(even, odd) and the odd one -- pooled column w is max(odd[w-1], maxpair[w]) over three rows: two ring
+// reads per row instead of three.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue, 12..19 = pool.
+// ------------------------------------------------------------------------------------------
+constexpr int kStemwThreads = 128 + 16 * 32;
+constexpr int kStemwRing = 7;                 // conv rows kept for the pool
+constexpr int kStemwSlots = 4;                // 4 x 128 fp32 columns = the whole TMEM
+constexpr int kStemwP = 57, kStemwPairs = 56;  // smem row pitch in pairs / valid pairs per conv row
+constexpr int kStemwR = 9;                    // conv rows per work tile (8t-1 .. 8t+7)
+constexpr int kStemwBoxBytes = (kStemwR + 3) * kStemwP * 64;
+constexpr int kStemwStage = (kStemwBoxBytes + 1023) & ~1023;
+constexpr int kStemwRowBytes = kStemwPairs * 256;  // ring row: [pair][max(even, odd) | odd][64 ch] bf16
+constexpr int kStemwWBytes = 17 * 2048;            // 16 tap tiles (64 cout x 16 ch) + the zero tile
+static_assert(kStemwStage - kStemwBoxBytes >= 64, "the last M-tile's deepest tap reads one row past the box: it must be padding");
+static_assert((kStemwR - 1) * kStemwP + kStemwPairs == 4 * 128, "a work tile is exactly four M-tiles");
+
+struct StemwParams {
+    int n_work, tiles_per_img, Hp, Wp;  // pooled output height / width
+    float bias_v[64];
+    __nv_bfloat16* out;
+    int sched;
+};
+
+__global__ void __launch_bounds__(kStemwThreads, 1)
+stemw_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const StemwParams p) {
+    constexpr int P = kStemwP, R = kStemwR, NMT = 4;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sW = sbase;
+    const uint32_t sA = sW + kStemwWBytes;
+    const uint32_t ring0 = sA + 2 * kStemwStage;
+    const uint32_t bias0 = ring0 + kStemwRing * kStemwRowBytes;
+    const uint32_t bars = bias0 + 256;
+    const uint32_t full0 = bars, empty0 = full0 + 16, tfull0 = empty0 + 16, tempty0 = tfull0 + 8 * kStemwSlots;
+    const uint32_t mdone0 = tempty0 + 8 * kStemwSlots, wbar = mdone0 + 8 * kStemwSlots, tslot = wbar + 8, pool_sync0 = tslot + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    const TileWalk walk(p.n_work, blockIdx.x, gridDim.x, p.sched);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < kStemwSlots; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 256);
+            mbar_init(mdone0 + 8 * i, 256);
+        }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tslot, 512);
+    if (warp == 3) {
+        if (lane == 0) *reinterpret_cast<int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw))) = 0;
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        bs[lane] = p.bias_v[lane];
+        bs[lane + 32] = p.bias_v[lane + 32];
+    }
+    {  // the zero tile behind tap (0, 0) and the padding behind each A stage: written once, read by the MMAs (async proxy)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < 2048 / 16; i += kStemwThreads) sts128(sW + 16 * 2048 + i * 16, z);
+        constexpr int kPad16 = (kStemwStage - kStemwBoxBytes) / 16;
+        for (int i = threadIdx.x; i < 2 * kPad16; i += kStemwThreads)
+            sts128(sA + (i / kPad16) * kStemwStage + kStemwBoxBytes + (i % kPad16) * 16, z);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    // resident weights, tap tiles in descending order (constant data: fetched before waiting for the previous kernel)
+    if (warp == 0 && elect_one_sync()) {
+        mbar_expect_tx(wbar, 16 * 2048);
+        for (int ty = 0; ty < 4; ++ty)
+            for (int tx = 0; tx < 4; ++tx) tma_load_2d(sW + ((3 - ty) * 4 + (3 - tx)) * 2048, &map_b, wbar, (ty * 4 + tx) * 16, 0);
+    }
+    __syncwarp();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer: one 12-row box of pairs per work tile =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int wi = 0, w = walk.begin; wi < walk.count; ++wi, w += walk.step) {
+                const int img = w / p.tiles_per_img;
+                const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                mbar_expect_tx(full0 + 8 * stage, kStemwBoxBytes);
+                tma_load_4d(sA + stage * kStemwStage, &map_a, full0 + 8 * stage, 0, 0, y0, img);
+                if (++stage == 2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc_w = make_idesc<128>(), idesc_n = make_idesc<64>();
+        constexpr uint64_t adesc_hi = make_smem_desc_rowb<64>(0) & 0xFFFFFFFF00000000ull;
+        constexpr uint64_t bdesc_hi = make_smem_desc_rowb<32>(0) & 0xFFFFFFFF00000000ull;
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0, g_base = 0;
+        const uint32_t w_lo = sW >> 4;
+        for (int wi = 0; wi < walk.count; ++wi) {
+            mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a_lo_stage = (sA + stage * kStemwStage) >> 4;
+            // two M-tiles at a time, K steps interleaved over the two accumulators (flat_conv_kernel)
+            for (int mt = 0; mt < NMT; mt += 2) {
+                const uint32_t g0 = g_base + mt, slot0 = g0 & (kStemwSlots - 1), use0 = g0 / kStemwSlots;
+                const uint32_t g1 = g0 + 1, slot1 = g1 & (kStemwSlots - 1), use1 = g1 / kStemwSlots;
+                mbar_wait(tempty0 + 8 * slot0, (use0 & 1) ^ 1);
+                mbar_wait(tempty0 + 8 * slot1, (use1 & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d0 = tmem_base + slot0 * 128, d1 = tmem_base + slot1 * 128;
+                    const uint32_t a_lo_mt = a_lo_stage + (uint32_t)(mt * 128) * 4;  // 64-byte rows = 4 descriptor units
+#pragma unroll
+                    for (int ty = 0; ty < 4; ++ty) {
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) {
+                            const uint32_t a_lo = a_lo_mt + (uint32_t)(ty * P + (t >> 1)) * 4 + (uint32_t)(t & 1) * 2;
+                            const int tile = (3 - ty) * 4 + (3 - (t == 4 ? 3 : t));  // window start: tap t (tap 3 for the odd-only step)
+                            const uint32_t b_lo = w_lo + (uint32_t)tile * (2048 / 16);
+                            const bool wide = (t >= 1 && t <= 3) || (ty == 0 && t == 0);
+                            const uint32_t idesc = wide ? idesc_w : idesc_n;
+                            const uint32_t dcol = t == 4 ? 64u : 0u;
+                            const uint32_t acc = (ty | t) != 0;
+                            umma_bf16(d0 + dcol, adesc_hi | (uint64_t)a_lo, bdesc_hi | (uint64_t)b_lo, idesc, acc);
+                            umma_bf16(d1 + dcol, adesc_hi | (uint64_t)(a_lo + 128 * 4), bdesc_hi | (uint64_t)b_lo, idesc, acc);
+                        }
+                    }
+                    umma_commit(tfull0 + 8 * slot0);
+                    umma_commit(tfull0 + 8 * slot1);
+                }
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit(empty0 + 8 * stage);
+            __syncwarp();
+            if (++stage == 2) {
+                stage = 0;
+                phase ^= 1;
+            }
+            g_base += NMT;
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== epilogue: TMEM -> (+bias, ReLU) -> bf16 [max(even, odd) | odd] per pair into the conv-row ring =====
+        const int q = warp & 3;
+        const int chalf = (warp - 4) >> 2;  // which 32 of the 64 output channels
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw))) + chalf * 32;
+        volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        uint32_t g = 0;
+        int tile_idx = 0;
+        for (int w = walk.begin; tile_idx < walk.count; w += walk.step, ++tile_idx) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
+            for (int mt = 0; mt < NMT; ++mt, ++g) {
+                const uint32_t slot = g & (kStemwSlots - 1), use = g / kStemwSlots;
+                const int m = mt * 128 + q * 32 + lane;
+                const int i = m / P, jp = m - i * P;
+                const bool valid = jp < kStemwPairs;
+                const int gr = tile_idx * R + i;  // CTA-wide conv row number
+                if (valid) {
+                    while (*rows_released < gr - kStemwRing + 1) __nanosleep(64);
+                }
+                __syncwarp();
+                mbar_wait(tfull0 + 8 * slot, use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + slot * 128 + chalf * 32 + ((uint32_t)(q * 32) << 16);
+                const uint32_t srow = ring0 + (uint32_t)(gr % kStemwRing) * kStemwRowBytes + (uint32_t)jp * 256;
+                const bool keep = y0 + i >= 0;  // conv row -1 is stored as zeros: neutral for a max over post-ReLU values
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t ve[16], vo[16];
+                    tmem_ld16(taddr + h * 16, ve);
+                    tmem_ld16(taddr + 64 + h * 16, vo);
+                    tmem_ld_wait();
+                    if (h == 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty0 + 8 * slot);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8 + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            uint4 om, oo;
+                            unsigned* um = &om.x;
+                            unsigned* uo = &oo.x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float e0 = fmaxf(__uint_as_float(ve[8 * j + 2 * k]) + bb[2 * k], 0.f);
+                                const float e1 = fmaxf(__uint_as_float(ve[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
+                                const float o0 = fmaxf(__uint_as_float(vo[8 * j + 2 * k]) + bb[2 * k], 0.f);
+                                const float o1 = fmaxf(__uint_as_float(vo[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
+                                const __nv_bfloat162 hm = __floats2bfloat162_rn(fmaxf(e0, o0), fmaxf(e1, o1));
+                                const __nv_bfloat162 ho = __floats2bfloat162_rn(o0, o1);
+                                um[k] = keep ? *reinterpret_cast<const unsigned*>(&hm) : 0u;
+                                uo[k] = keep ? *reinterpret_cast<const unsigned*>(&ho) : 0u;
+                            }
+                            const uint32_t chunk = (uint32_t)((chalf * 4 + h * 2 + j) ^ (jp & 7)) << 4;
+                            sts128(srow + chunk, om);
+                            sts128(srow + 128 + chunk, oo);
+                        }
+                    }
+                }
+                mbar_arrive(mdone0 + 8 * slot);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== pool: 3x3 / stride-2 / pad-1 max over the ring -> NHWC [n][56][56][64] =====
+        const int te = threadIdx.x - 12 * 32;  // 0..255
+        volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        uint32_t g = 0;
+        int tile_idx = 0;
+        for (int w = walk.begin; tile_idx < walk.count; w += walk.step, ++tile_idx) {
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
+            int jnext = 0;
+            for (int mt = 0; mt < NMT; ++mt, ++g) {
+                const uint32_t slot = g & (kStemwSlots - 1), use = g / kStemwSlots;
+                mbar_wait(mdone0 + 8 * slot, use & 1);
+                // pooled rows whose last conv row (2j+2) ends inside this M-tile
+                while (2 * jnext + 2 < R && ((2 * jnext + 2) * P + kStemwPairs - 1) / 128 <= mt) {
+                    const int j = jnext++;
+                    const int prow = (y0 + 1) / 2 + j;
+                    const int gr0 = tile_idx * R + 2 * j;
+                    const uint32_t r0 = ring0 + (uint32_t)(gr0 % kStemwRing) * kStemwRowBytes;
+                    const uint32_t r1 = ring0 + (uint32_t)((gr0 + 1) % kStemwRing) * kStemwRowBytes;
+                    const uint32_t r2 = ring0 + (uint32_t)((gr0 + 2) % kStemwRing) * kStemwRowBytes;
+                    for (int item = te; item < p.Wp * 8; item += 256) {
+                        const int pw = item >> 3, ch = item & 7;
+                        // conv columns 2pw-1, 2pw, 2pw+1 = odd of pair pw-1, max(even, odd) of pair pw
+                        const uint32_t offm = (uint32_t)pw * 256 + ((uint32_t)(ch ^ (pw & 7)) << 4);
+                        const uint4 a = lds128(r0 + offm), bq = lds128(r1 + offm), cq = lds128(r2 + offm);
+                        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&bq);
+                        const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&cq);
+                        __nv_bfloat162 acc[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) acc[k] = __hmax2(ha[k], __hmax2(hb[k], hc[k]));
+                        if (pw > 0) {
+                            const uint32_t offo = (uint32_t)(pw - 1) * 256 + 128 + ((uint32_t)(ch ^ ((pw - 1) & 7)) << 4);
+                            const uint4 a2 = lds128(r0 + offo), b2 = lds128(r1 + offo), c2 = lds128(r2 + offo);
+                            const __nv_bfloat162* ga = reinterpret_cast<const __nv_bfloat162*>(&a2);
+                            const __nv_bfloat162* gb = reinterpret_cast<const __nv_bfloat162*>(&b2);
+                            const __nv_bfloat162* gc = reinterpret_cast<const __nv_bfloat162*>(&c2);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], __hmax2(ga[k], __hmax2(gb[k], gc[k])));
+                        }
+                        if (prow < p.Hp)
+                            *reinterpret_cast<uint4*>(p.out + (((size_t)img * p.Hp + prow) * p.Wp + pw) * 64 + ch * 8) =
+                                *reinterpret_cast<const uint4*>(acc);
+                    }
+                    // rows gr0 and gr0+1 are not needed by later pooled rows (row gr0+2 is: it is row 2(j+1))
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (te == 0) {
+                        const bool last = 2 * (j + 1) + 2 >= R;  // last pooled row of the tile: its third row is free too
+                        *rows_released = gr0 + (last ? 3 : 2);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // flat2: the layer-1 kernel (3x3 / stride 1, Cin = Cout = 64) as a CTA PAIR (cta_group::2).
 //
 // Why: flat_conv_kernel's N = 64 MMAs are bound by the 128 B/clk shared-memory pipe -- every M128 x N64 x K16 MMA
@@ -1413,6 +1716,54 @@ static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& m
     return FX_OK;
 }
 
+// The pooled stem on stemw_conv_kernel (two conv outputs per accumulator row); FX_STEMW=0 keeps flat_conv_kernel<32, 4, 4, true>.
+static bool stemw_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("FX_STEMW");
+        return !(v && v[0] == '0');
+    }();
+    return on;
+}
+
+static int stemw_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, __nv_bfloat16* out, int n, cudaStream_t stream, int sched) {
+    const LayerGeom& g = L.g;
+    static_assert(kS2dW % 2 == 0 && kS2dW / 2 >= kStemwP && kS2dC == 16, "stemw: the staging tensor is read as pairs of s2d pixels");
+    if (g.cout != 64 || L.host_b.size() != 64 || g.hout != 112 || g.wout != 2 * kStemwPairs || L.k_bf16 != 256)
+        return set_error(e, FX_ERR_UNSUPPORTED, "stemw_conv: not the 7x7 / stride-2 stem on a 224 x 224 crop");
+    StemwParams p;
+    std::memset(&p, 0, sizeof(p));
+    std::memcpy(p.bias_v, L.host_b.data(), sizeof(p.bias_v));
+    p.out = out;
+    p.sched = sched;
+    p.tiles_per_img = g.hout / 8;
+    p.n_work = n * p.tiles_per_img;
+    p.Hp = g.hout / 2;
+    p.Wp = g.wout / 2;
+    CUtensorMap ma, mb;
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    const uint64_t dims[4] = {2 * kS2dC, kS2dW / 2, (uint64_t)kS2dH, (uint64_t)n};
+    const uint64_t strides[3] = {2 * kS2dC * 2, (uint64_t)kS2dW * kS2dC * 2, (uint64_t)kS2dH * kS2dW * kS2dC * 2};
+    const uint32_t box[4] = {2 * kS2dC, kStemwP, kStemwR + 3, 1};
+    int rc = tc_encode_map(e, &ma, in, 4, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_64B, "stemw A");
+    if (rc != FX_OK) return rc;
+    const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+    const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+    const uint32_t bbox[2] = {16, 64};
+    rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stemw B");
+    if (rc != FX_OK) return rc;
+    constexpr int kSmem = 1024 + kStemwWBytes + 2 * kStemwStage + kStemwRing * kStemwRowBytes + 256 + 8 * (4 + 3 * kStemwSlots + 3) + 64;
+    static_assert(kSmem <= kSmemMax, "stemw_conv_kernel: shared memory");
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
+        FX_CUDA(e, cudaFuncSetAttribute(stemw_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_done[e->device & 255] = true;
+    }
+    const int grid = std::max(1, std::min(e->sm_count, p.n_work));
+    FX_CUDA(e, launch_pdl(stemw_conv_kernel, dim3(grid), dim3(kStemwThreads), kSmem, stream, ma, mb, p));
+    FX_LAUNCH_CHECK(e, "stemw_conv_kernel");
+    return FX_OK;
+}
+
 // flat128 on CTA pairs (flat128x2_conv_kernel); FX_FLAT128X2=0 keeps the single-CTA kernel.
 static bool flat128x2_enabled() {
     static const bool on = [] {
@@ -1596,6 +1947,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
         p.ypad = 0;
         if (pool) {
             if (!relu || residual) return set_error(e, FX_ERR_INVALID, "flat_conv: the pooled stem is conv+bn+relu+maxpool");
+            if (stemw_enabled()) return stemw_conv(e, L, in, out, n, stream, sched);
             p.R = 9;  // 4 pooled rows need conv rows 8t-1 .. 8t+7
             p.rstep = 8;
             p.yfirst = -1;
