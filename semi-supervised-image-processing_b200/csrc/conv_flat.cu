@@ -780,6 +780,7 @@ stemw_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int img = w / p.tiles_per_img;
             const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
             int jnext = 0;
+            __nv_bfloat162 carry[2][4];
             for (int mt = 0; mt < NMT; ++mt, ++g) {
                 const uint32_t slot = g & (kStemwSlots - 1), use = g / kStemwSlots;
                 mbar_wait(mdone0 + 8 * slot, use & 1);
@@ -791,29 +792,43 @@ stemw_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const uint32_t r0 = ring0 + (uint32_t)(gr0 % kStemwRing) * kStemwRowBytes;
                     const uint32_t r1 = ring0 + (uint32_t)((gr0 + 1) % kStemwRing) * kStemwRowBytes;
                     const uint32_t r2 = ring0 + (uint32_t)((gr0 + 2) % kStemwRing) * kStemwRowBytes;
-                    for (int item = te; item < p.Wp * 8; item += 256) {
-                        const int pw = item >> 3, ch = item & 7;
-                        // conv columns 2pw-1, 2pw, 2pw+1 = odd of pair pw-1, max(even, odd) of pair pw
-                        const uint32_t offm = (uint32_t)pw * 256 + ((uint32_t)(ch ^ (pw & 7)) << 4);
-                        const uint4 a = lds128(r0 + offm), bq = lds128(r1 + offm), cq = lds128(r2 + offm);
-                        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-                        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&bq);
-                        const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&cq);
-                        __nv_bfloat162 acc[4];
+                    // a thread keeps its (column, channel chunk) items for the whole tile: the horizontal max of conv row 2j+2 is
+                    // carried in registers to pooled row j+1, whose first row it is (two ring rows read per pooled row, not three)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) acc[k] = __hmax2(ha[k], __hmax2(hb[k], hc[k]));
-                        if (pw > 0) {
-                            const uint32_t offo = (uint32_t)(pw - 1) * 256 + 128 + ((uint32_t)(ch ^ ((pw - 1) & 7)) << 4);
-                            const uint4 a2 = lds128(r0 + offo), b2 = lds128(r1 + offo), c2 = lds128(r2 + offo);
-                            const __nv_bfloat162* ga = reinterpret_cast<const __nv_bfloat162*>(&a2);
-                            const __nv_bfloat162* gb = reinterpret_cast<const __nv_bfloat162*>(&b2);
-                            const __nv_bfloat162* gc = reinterpret_cast<const __nv_bfloat162*>(&c2);
+                    for (int it = 0; it < 2; ++it) {
+                        const int item = te + it * 256;
+                        if (item < p.Wp * 8) {
+                            const int pw = item >> 3, ch = item & 7;
+                            // conv columns 2pw-1, 2pw, 2pw+1 = odd of pair pw-1, max(even, odd) of pair pw
+                            const uint32_t offm = (uint32_t)pw * 256 + ((uint32_t)(ch ^ (pw & 7)) << 4);
+                            const uint32_t offo = (uint32_t)max(pw - 1, 0) * 256 + 128 + ((uint32_t)(ch ^ (max(pw - 1, 0) & 7)) << 4);
+                            auto hrow = [&](uint32_t rb, __nv_bfloat162 (&h)[4]) {
+                                const uint4 a = lds128(rb + offm);
+                                const uint4 o = lds128(rb + (pw > 0 ? offo : offm));  // column -1 is padding: the pair's own max again
+                                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                                const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&o);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) acc[k] = __hmax2(acc[k], __hmax2(ga[k], __hmax2(gb[k], gc[k])));
+                                for (int k = 0; k < 4; ++k) h[k] = __hmax2(ha[k], ho[k]);
+                            };
+                            __nv_bfloat162 h0[4], h1[4], h2[4];
+                            if (j == 0) {
+                                hrow(r0, h0);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) h0[k] = carry[it][k];
+                            }
+                            hrow(r1, h1);
+                            hrow(r2, h2);
+                            __nv_bfloat162 acc[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                acc[k] = __hmax2(h0[k], __hmax2(h1[k], h2[k]));
+                                carry[it][k] = h2[k];
+                            }
+                            if (prow < p.Hp)
+                                *reinterpret_cast<uint4*>(p.out + (((size_t)img * p.Hp + prow) * p.Wp + pw) * 64 + ch * 8) =
+                                    *reinterpret_cast<const uint4*>(acc);
                         }
-                        if (prow < p.Hp)
-                            *reinterpret_cast<uint4*>(p.out + (((size_t)img * p.Hp + prow) * p.Wp + pw) * 64 + ch * 8) =
-                                *reinterpret_cast<const uint4*>(acc);
                     }
                     // rows gr0 and gr0+1 are not needed by later pooled rows (row gr0+2 is: it is row 2(j+1))
                     asm volatile("bar.sync 3, 256;" ::: "memory");
