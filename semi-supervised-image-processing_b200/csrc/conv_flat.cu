@@ -1148,6 +1148,287 @@ flat2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// flat2w: layer 1 with TWO output columns per accumulator row (the stemw idea on flat2's CTA pair).
+//
+// flat2_conv_kernel is bound by the shared-memory pipe: per M256 x N64 x K16 MMA each CTA fetches 4 KB of A and 1 KB of B
+// (40 cycles for 32 cycles of math), nine taps x four K-steps per M-tile.  Here accumulator row (i, j') holds the outputs
+// (i, 2j') in columns 0..63 and (i, 2j'+1) in columns 64..127.  Together they read input columns 2j'-1 .. 2j'+2: four
+// column steps t per filter row instead of 2 x 3, so the A bytes per output fall by a third:
+//   t = 1, 2   N = 128   even output: tap dx = t,  odd output: tap dx = t-1   (each CTA supplies one of the two halves of B)
+//   t = 0      N = 64    even output only, tap dx = 0 -> columns 0..63        (filter row 0: N = 128 with a ZERO odd half, so
+//   t = 3      N = 64    odd output only,  tap dx = 2 -> columns 64..127       that the first MMA initialises all 128 columns)
+// The input is staged as two column-parity planes (E: columns 0, 2, ..; O: columns -1, 1, ..; one 5-D map over
+// [64][W/2][parity][H][n], unit-stride boxes), each a flat list of 128-byte rows with pitch P = W/2 + 1; input column
+// 2j' + t - 1 of filter row dy is plane (t odd ? E : O) viewed dy * P + (t >> 1) rows further down.  A work tile is R = 4
+// output rows = 3 * 29 + 28 = 115 positions = ONE M-tile per CTA; all eight epilogue warps drain it (lane quarter x even /
+// odd output).  Every output sums its nine taps in flat2's order: rows are bit-identical (knob test, FX_FLAT2W=0).
+// ------------------------------------------------------------------------------------------
+constexpr int kF2wSlots = 4;          // 4 x 128 fp32 columns
+constexpr int kF2wUnit = 32 * 128;    // weight storage unit: 32 output channels x 64 input channels (one box)
+constexpr int kF2wUnits = 19;         // per CTA: filter row 0: 2 + 2 + 2 + 1, rows 1 and 2: 1 + 2 + 2 + 1
+
+struct Flat2wParams {
+    int P, Wp, W, H, R, tiles_per_img, n_work, batch, cout;
+    int nstages, stage_bytes, plane_bytes, box_bytes;
+    float bias_v[64];
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    int relu;
+    int sched;
+};
+
+__device__ __forceinline__ constexpr int f2w_unit_of(int dy, int t) {
+    return dy == 0 ? 2 * t : 7 + (dy - 1) * 6 + (t == 0 ? 0 : 2 * t - 1);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFlat2Threads, 1)
+flat2w_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Flat2wParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sW = sbase;
+    const uint32_t sA = sW + kF2wUnits * kF2wUnit;
+    const uint32_t stage0 = sA + p.nstages * p.stage_bytes;  // epilogue staging: 8 warps x 4 KB (the junk rows of the last A stage over-read into it)
+    const uint32_t bars = stage0 + 8 * 4096;
+    const uint32_t full0 = bars, empty0 = full0 + 8 * p.nstages, tfull0 = empty0 + 8 * p.nstages;
+    const uint32_t tempty0 = tfull0 + 8 * kF2wSlots, wbar = tempty0 + 8 * kF2wSlots, tslot = wbar + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_units = (p.n_work + 1) >> 1;
+    const TileWalk walk(n_units, pair, n_pairs, p.sched);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.nstages; ++i) {
+            mbar_init(full0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
+            mbar_init(empty0 + 8 * i, 1);  // multicast commit
+        }
+        for (int i = 0; i < kF2wSlots; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);        // multicast commit
+            mbar_init(tempty0 + 8 * i, 2 * 256);  // the eight epilogue warps of both CTAs
+        }
+        mbar_init(wbar, 2);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tslot, 512);
+    if (!leader) {  // the odd outputs' half of the very first column step is zero (it only initialises the accumulator)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < 2 * kF2wUnit / 16; i += kFlat2Threads) sts128(sW + i * 16, z);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    // this CTA's halves of the folded weights are constant data: fetched before waiting for the previous kernel (PDL)
+    if (warp == 0 && elect_one_sync()) {
+        if (leader) mbar_expect_tx(wbar, (2 * kF2wUnits - 2) * kF2wUnit);
+        for (int dy = 0; dy < 3; ++dy)
+            for (int t = 0; t < 4; ++t) {
+                const bool wide = t == 1 || t == 2 || (dy == 0 && t == 0);
+                const uint32_t dst = sW + f2w_unit_of(dy, t) * kF2wUnit;
+                if (wide) {
+                    const int dx = leader ? t : t - 1;  // even outputs: tap t, odd outputs: tap t - 1
+                    if (dx >= 0) {
+                        tma_load_2d_2cta(dst, &map_b, wbar, (dy * 3 + dx) * 64, 0);
+                        tma_load_2d_2cta(dst + kF2wUnit, &map_b, wbar, (dy * 3 + dx) * 64, 32);
+                    }
+                } else {
+                    tma_load_2d_2cta(dst, &map_b, wbar, (dy * 3 + (t == 0 ? 0 : 2)) * 64, (int)rank * 32);
+                }
+            }
+        if (!leader) mbar_arrive_leader(wbar);
+    }
+    __syncwarp();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): the two parity planes of this CTA's tile =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int ui = 0, u = walk.begin; ui < walk.count; ++ui, u += walk.step) {
+                const int w = 2 * u + (int)rank;
+                const int img = w < p.n_work ? w / p.tiles_per_img : p.batch;  // the odd leftover: out of bounds -> zeros
+                const int y0 = w < p.n_work ? (w - img * p.tiles_per_img) * p.R : 0;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (leader) mbar_expect_tx(full0 + 8 * stage, 4 * p.box_bytes);
+                const uint32_t dst = sA + stage * p.stage_bytes;
+                tma_load_5d_2cta(dst, &map_a, full0 + 8 * stage, 0, 0, 0, y0 - 1, img);                   // E: columns 0, 2, .., W
+                tma_load_5d_2cta(dst + p.plane_bytes, &map_a, full0 + 8 * stage, 0, -1, 1, y0 - 1, img);  // O: columns -1, 1, .., W-1
+                if (!leader) mbar_arrive_leader(full0 + 8 * stage);
+                if (++stage == (uint32_t)p.nstages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only): M = 256 (both CTAs' tiles) =====
+        if (leader) {
+            constexpr uint32_t idesc_w = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            constexpr uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            constexpr uint64_t desc_hi = make_smem_desc_rowb<128>(0) & 0xFFFFFFFF00000000ull;
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0;
+            const uint32_t w_lo = sW >> 4;
+            for (int ui = 0; ui < walk.count; ++ui) {
+                const uint32_t slot = ui & (kF2wSlots - 1), use = ui / kF2wSlots;
+                mbar_wait(full0 + 8 * stage, phase);
+                mbar_wait(tempty0 + 8 * slot, (use & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d = tmem_base + slot * 128;
+                    const uint32_t a_e = (sA + stage * p.stage_bytes) >> 4, a_o = a_e + ((uint32_t)p.plane_bytes >> 4);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const bool wide = t == 1 || t == 2 || (dy == 0 && t == 0);
+                            const uint32_t a_lo = ((t & 1) ? a_e : a_o) + (uint32_t)(dy * p.P + (t >> 1)) * 8;
+                            const uint32_t b_lo = w_lo + (uint32_t)f2w_unit_of(dy, t) * (kF2wUnit / 16);
+                            const uint32_t dd = d + ((!wide && t == 3) ? 64u : 0u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_2cta(dd, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), wide ? idesc_w : idesc_n,
+                                               (dy | t | k) != 0);
+                        }
+                    }
+                    umma_commit_2cta(empty0 + 8 * stage);
+                    umma_commit_2cta(tfull0 + 8 * slot);
+                }
+                __syncwarp();
+                if (++stage == (uint32_t)p.nstages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): lane quarter q x (even | odd) output of the pair =====
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
+        const int rr0 = lane >> 3, ch = lane & 7;
+        const bool has_res = p.residual != nullptr;
+        const int m = q * 32 + lane;
+        const int mi = m / p.P, mj = m - mi * p.P;
+        auto pix_of = [&](int u) {
+            const int w = 2 * u + (int)rank;
+            if (w >= p.n_work) return -1;
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * p.R;
+            return (mj < p.Wp && mi < min(p.R, p.H - y0)) ? ((img * p.H + y0 + mi) * p.W + 2 * mj + half) : -1;
+        };
+        uint4 rres[8];
+        auto load_res = [&](int px) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int pr = __shfl_sync(0xffffffffu, px, it * 4 + rr0);
+                rres[it] = ldg_stream128(p.residual + (size_t)max(pr, 0) * p.cout + ch * 8);  // junk rows read pixel 0, unused
+            }
+        };
+        auto stash_res = [&]() {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rr0;
+                sts128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4), rres[it]);
+            }
+        };
+        int pix = walk.count > 0 ? pix_of(walk.begin) : -1;
+        if (walk.count > 0 && has_res) load_res(pix);
+        for (int ui = 0, u = walk.begin; ui < walk.count; ++ui, u += walk.step) {
+            const bool nlive = ui + 1 < walk.count;
+            const int npix = nlive ? pix_of(u + walk.step) : -1;
+            if (has_res) {
+                stash_res();
+                if (nlive) load_res(npix);
+            }
+            const uint32_t slot = ui & (kF2wSlots - 1), use = ui / kF2wSlots;
+            __syncwarp();
+            mbar_wait(tfull0 + 8 * slot, use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + slot * 128 + half * 64 + ((uint32_t)(q * 32) << 16);
+            const uint32_t srow = stg + lane * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
+                tmem_ld_wait();
+                if (h == 1) {
+                    tc_fence_before();
+                    mbar_arrive_leader(tempty0 + 8 * slot);  // accumulator is in registers: hand the slot back to the leader
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t sa = srow + (((h * 4 + j) ^ (lane & 7)) << 4);
+                    const float* bv = p.bias_v + h * 32 + j * 8;  // compile-time offsets: constant-bank operands
+                    const float4 b0 = make_float4(bv[0], bv[1], bv[2], bv[3]);
+                    const float4 b1 = make_float4(bv[4], bv[5], bv[6], bv[7]);
+                    float f[8] = {__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y,
+                                  __uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w,
+                                  __uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y,
+                                  __uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w};
+                    if (has_res && pix >= 0) {
+                        const uint4 rv = lds128(sa);
+                        const unsigned uu[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            f[2 * k] += __uint_as_float(uu[k] << 16);
+                            f[2 * k + 1] += __uint_as_float(uu[k] & 0xffff0000u);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+                    }
+                    uint4 o;
+                    unsigned* ou = &o.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+                        ou[k] = *reinterpret_cast<const unsigned*>(&h2);
+                    }
+                    sts128(sa, o);
+                }
+            }
+            __syncwarp();
+            {
+                int prs[8];
+                uint4 vals[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) prs[it] = __shfl_sync(0xffffffffu, pix, it * 4 + rr0);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rr0;
+                    vals[it] = lds128(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    if (prs[it] >= 0) *reinterpret_cast<uint4*>(p.out + (size_t)prs[it] * p.cout + ch * 8) = vals[it];
+            }
+            __syncwarp();
+            pix = npix;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory / barriers stay alive until both CTAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // flat128: the same halo-tile / shifted-view A operand, but 128 output channels per MMA (N=128 issues at
 // the tensor floor, 64 cycles, where two N=64 MMAs cost 96) and the weights STREAMED per (tap, chunk)
 // K-block through a ring, because a 128-channel slice of a 3x3x128 filter bank (288 KB) does not fit in
@@ -1918,6 +2199,71 @@ static int flat2_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
     return FX_OK;
 }
 
+// layer 1 on flat2w_conv_kernel (two outputs per accumulator row); FX_FLAT2W=0 keeps flat2_conv_kernel.
+static bool flat2w_supported(const LayerGeom& g) {
+    static const bool on = [] {
+        const char* v = getenv("FX_FLAT2W");
+        return !(v && v[0] == '0');
+    }();
+    return on && flat2_mode() >= 1 && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin == 64 && g.cout == 64 && g.win % 2 == 0 &&
+           g.win >= 8 && g.win / 2 + 1 <= 128 - g.win / 2 && g.hin == g.hout && g.win == g.wout;
+}
+
+static int flat2w_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                       int n, int relu, cudaStream_t stream, int sched) {
+    const LayerGeom& g = L.g;
+    Flat2wParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.sched = sched;
+    if (L.host_b.size() != 64) return set_error(e, FX_ERR_UNSUPPORTED, "flat2w_conv: cout must be 64");
+    std::memcpy(p.bias_v, L.host_b.data(), sizeof(p.bias_v));
+    p.residual = residual;
+    p.out = out;
+    p.relu = relu;
+    p.cout = g.cout;
+    p.batch = n;
+    p.W = g.wout;
+    p.H = g.hout;
+    p.Wp = g.wout / 2;
+    p.P = p.Wp + 1;
+    p.R = std::max(1, std::min(g.hout, (128 - p.Wp) / p.P + 1));  // (R - 1) * P + Wp <= 128: one M-tile per work tile
+    p.tiles_per_img = (p.H + p.R - 1) / p.R;
+    p.n_work = n * p.tiles_per_img;
+    p.box_bytes = (p.R + 2) * p.P * 128;
+    p.plane_bytes = (p.box_bytes + 1023) & ~1023;
+    p.stage_bytes = 2 * p.plane_bytes;
+    const int bar_bytes = 8 * (2 * 4 + 2 * kF2wSlots + 2) + 64;
+    const int fixed = 1024 + kF2wUnits * kF2wUnit + 8 * 4096 + bar_bytes;
+    p.nstages = std::min(4, (kSmemMax - fixed) / p.stage_bytes);
+    // the junk rows of a plane read up to 127 + 2P + 1 rows in: the last plane's over-read must stay inside the staging block
+    if (p.nstages < 2 || (128 + 2 * p.P + 2) * 128 > p.plane_bytes + 8 * 4096)
+        return set_error(e, FX_ERR_UNSUPPORTED, "flat2w_conv: tile does not fit");
+    const int smem = fixed + p.nstages * p.stage_bytes;
+    CUtensorMap ma, mb;
+    const uint32_t ones[5] = {1, 1, 1, 1, 1};
+    const uint64_t rowb = (uint64_t)g.win * g.cin * 2;
+    const uint64_t dims[5] = {(uint64_t)g.cin, (uint64_t)g.win / 2, 2, (uint64_t)g.hin, (uint64_t)n};
+    const uint64_t strides[4] = {(uint64_t)g.cin * 4, (uint64_t)g.cin * 2, rowb, (uint64_t)g.hin * rowb};
+    const uint32_t box[5] = {64, (uint32_t)p.P, 1, (uint32_t)(p.R + 2), 1};
+    int rc = tc_encode_map(e, &ma, in, 5, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat2w A (column-parity planes)");
+    if (rc != FX_OK) return rc;
+    const uint64_t bd[2] = {(uint64_t)L.k_bf16, (uint64_t)g.cout};
+    const uint64_t bs[1] = {(uint64_t)L.k_bf16 * 2};
+    const uint32_t bbox[2] = {64, 32};  // one tap's K-block of 32 output channels
+    rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_128B, "flat2w B");
+    if (rc != FX_OK) return rc;
+    static bool attr_done[256] = {};  // per device ordinal
+    if (!attr_done[e->device & 255]) {
+        FX_CUDA(e, cudaFuncSetAttribute(flat2w_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_done[e->device & 255] = true;
+    }
+    const int n_units = (p.n_work + 1) / 2;
+    const int pairs = std::max(1, std::min(e->sm_count / 2, n_units));
+    FX_CUDA(e, launch_pdl(flat2w_conv_kernel, dim3(2 * pairs), dim3(kFlat2Threads), smem, stream, ma, mb, p));  // cluster dims are a kernel attribute
+    FX_LAUNCH_CHECK(e, "flat2w_conv_kernel");
+    return FX_OK;
+}
+
 static bool flat2_supported(const LayerGeom& g, bool has_residual) {
     return flat2_mode() >= (has_residual ? 2 : 1) && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin == 64 && g.cout == 64 && g.win + 2 <= 128 && g.win >= 8;
 }
@@ -1990,6 +2336,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     }
     if (pool) return set_error(e, FX_ERR_INVALID, "flat_conv: only the stem has a fused max-pool");
     if (flat128_supported(g)) return flat128_conv(e, L, in, residual, out, n, relu, stream);
+    if (flat2w_supported(g)) return flat2w_conv(e, L, in, residual, out, n, relu, stream, sched);
     if (flat2_supported(g, residual != nullptr)) return flat2_conv(e, L, in, residual, out, n, relu, stream, sched);
     p.P = g.win + 2;
     p.chunks = g.cin / 64;
