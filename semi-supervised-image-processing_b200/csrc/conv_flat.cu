@@ -849,6 +849,312 @@ stemw_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
 }
 
+// stemw2: stemw_conv_kernel as a CTA PAIR (cta_group::2): one M = 256 MMA per step covers the same M-tile of both CTAs' work
+// tiles, and each CTA supplies HALF of the step's B operand -- an N = 128 step costs 4 KB of A + 2 KB of B per CTA instead of
+// 4 + 4 (48 cycles of the shared-memory pipe for 64 cycles of math), an N = 64 step 4 + 1.  The leader's half is always the
+// even output's weights, the peer's the odd output's, so no tile is stored twice: 33 KB per CTA.  Protocol as flat2_conv_kernel.
+constexpr int kStemw2WBytes = 33 * 1024;
+__host__ __device__ constexpr uint32_t stemw2_w_off(int ty, int t) {  // byte offset of step (ty, t)'s half operand in issue order
+    return (uint32_t)((ty == 0 ? 2 * t : 9 + (ty - 1) * 8 + (t == 0 ? 0 : 2 * t - 1)) * 1024);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStemwThreads, 1)
+stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bn,
+                   const StemwParams p) {
+    constexpr int P = kStemwP, R = kStemwR, NMT = 4;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sW = sbase;
+    const uint32_t sA = sW + kStemw2WBytes;
+    const uint32_t ring0 = sA + 2 * kStemwStage;
+    const uint32_t bias0 = ring0 + kStemwRing * kStemwRowBytes;
+    const uint32_t bars = bias0 + 256;
+    const uint32_t full0 = bars, empty0 = full0 + 16, tfull0 = empty0 + 16, tempty0 = tfull0 + 8 * kStemwSlots;
+    const uint32_t mdone0 = tempty0 + 8 * kStemwSlots, wbar = mdone0 + 8 * kStemwSlots, tslot = wbar + 8, pool_sync0 = tslot + 8;
+    uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const TileWalk walk(p.n_work >> 1, blockIdx.x >> 1, gridDim.x >> 1, p.sched);  // unit u = work tiles 2u (leader) and 2u + 1 (peer); n_work is even
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_bn);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(full0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
+            mbar_init(empty0 + 8 * i, 1);  // multicast commit
+        }
+        for (int i = 0; i < kStemwSlots; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);         // multicast commit
+            mbar_init(tempty0 + 8 * i, 2 * 256);  // the eight epilogue warps of both CTAs
+            mbar_init(mdone0 + 8 * i, 256);
+        }
+        mbar_init(wbar, 2);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tslot, 512);
+    if (warp == 3) {
+        if (lane == 0) *reinterpret_cast<int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw))) = 0;
+        float* bs = reinterpret_cast<float*>(smem_raw + (bias0 - smem_u32(smem_raw)));
+        bs[lane] = p.bias_v[lane];
+        bs[lane + 32] = p.bias_v[lane + 32];
+    }
+    {  // the odd outputs' (= the peer's) half of the very first step and the padding behind each A stage: written once, read
+       // by the MMAs (async proxy)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        if (!leader)
+            for (int i = threadIdx.x; i < 2048 / 16; i += kStemwThreads) sts128(sW + i * 16, z);
+        constexpr int kPad16 = (kStemwStage - kStemwBoxBytes) / 16;
+        for (int i = threadIdx.x; i < 2 * kPad16; i += kStemwThreads)
+            sts128(sA + (i / kPad16) * kStemwStage + kStemwBoxBytes + (i % kPad16) * 16, z);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tslot_ptr;
+
+    // resident weights: this CTA's half of every step's B operand, in issue order (constant data: fetched before waiting for
+    // the previous kernel).  N = 128 steps: all 64 output channels of ONE of the two outputs (leader: even output = tap t,
+    // peer: odd output = tap t - 1); N = 64 steps: 32 of the 64 channels of the single output the step feeds.
+    if (warp == 0 && elect_one_sync()) {
+        if (leader) mbar_expect_tx(wbar, 2 * kStemw2WBytes - 2048);
+        for (int ty = 0; ty < 4; ++ty)
+            for (int t = 0; t < 5; ++t) {
+                const bool wide = (t >= 1 && t <= 3) || (ty == 0 && t == 0);
+                const uint32_t dst = sW + stemw2_w_off(ty, t);
+                if (wide) {
+                    const int tx = leader ? t : t - 1;
+                    if (tx >= 0) tma_load_2d_2cta(dst, &map_b, wbar, (ty * 4 + tx) * 16, 0);
+                } else {
+                    tma_load_2d_2cta(dst, &map_bn, wbar, (ty * 4 + (t == 0 ? 0 : 3)) * 16, (int)rank * 32);
+                }
+            }
+        if (!leader) mbar_arrive_leader(wbar);
+    }
+    __syncwarp();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer: one 12-row box of pairs per work tile =====
+        if (elect_one_sync()) {
+            uint32_t stage = 0, phase = 0;
+            for (int wi = 0, u = walk.begin; wi < walk.count; ++wi, u += walk.step) {
+                const int w = 2 * u + (int)rank;
+                const int img = w / p.tiles_per_img;
+                const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * kStemwBoxBytes);
+                tma_load_4d_2cta(sA + stage * kStemwStage, &map_a, full0 + 8 * stage, 0, 0, y0, img);
+                if (!leader) mbar_arrive_leader(full0 + 8 * stage);
+                if (++stage == 2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===== MMA issuer (leader CTA only): M = 256 = the same M-tile of both CTAs' work tiles =====
+        constexpr uint32_t idesc_w = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        constexpr uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        constexpr uint64_t adesc_hi = make_smem_desc_rowb<64>(0) & 0xFFFFFFFF00000000ull;
+        constexpr uint64_t bdesc_hi = make_smem_desc_rowb<32>(0) & 0xFFFFFFFF00000000ull;
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0, g_base = 0;
+        const uint32_t w_lo = sW >> 4;
+        for (int wi = 0; wi < walk.count; ++wi) {
+            mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a_lo_stage = (sA + stage * kStemwStage) >> 4;
+            // two M-tiles at a time, K steps interleaved over the two accumulators (flat_conv_kernel)
+            for (int mt = 0; mt < NMT; mt += 2) {
+                const uint32_t g0 = g_base + mt, slot0 = g0 & (kStemwSlots - 1), use0 = g0 / kStemwSlots;
+                const uint32_t g1 = g0 + 1, slot1 = g1 & (kStemwSlots - 1), use1 = g1 / kStemwSlots;
+                mbar_wait(tempty0 + 8 * slot0, (use0 & 1) ^ 1);
+                mbar_wait(tempty0 + 8 * slot1, (use1 & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d0 = tmem_base + slot0 * 128, d1 = tmem_base + slot1 * 128;
+                    const uint32_t a_lo_mt = a_lo_stage + (uint32_t)(mt * 128) * 4;  // 64-byte rows = 4 descriptor units
+#pragma unroll
+                    for (int ty = 0; ty < 4; ++ty) {
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) {
+                            const uint32_t a_lo = a_lo_mt + (uint32_t)(ty * P + (t >> 1)) * 4 + (uint32_t)(t & 1) * 2;
+                            const uint32_t b_lo = w_lo + (uint32_t)stemw2_w_off(ty, t) / 16;
+                            const bool wide = (t >= 1 && t <= 3) || (ty == 0 && t == 0);
+                            const uint32_t idesc = wide ? idesc_w : idesc_n;
+                            const uint32_t dcol = t == 4 ? 64u : 0u;
+                            const uint32_t acc = (ty | t) != 0;
+                            umma_bf16_2cta(d0 + dcol, adesc_hi | (uint64_t)a_lo, bdesc_hi | (uint64_t)b_lo, idesc, acc);
+                            umma_bf16_2cta(d1 + dcol, adesc_hi | (uint64_t)(a_lo + 128 * 4), bdesc_hi | (uint64_t)b_lo, idesc, acc);
+                        }
+                    }
+                    umma_commit_2cta(tfull0 + 8 * slot0);
+                    umma_commit_2cta(tfull0 + 8 * slot1);
+                }
+                __syncwarp();
+            }
+            if (elect_one_sync()) umma_commit_2cta(empty0 + 8 * stage);
+            __syncwarp();
+            if (++stage == 2) {
+                stage = 0;
+                phase ^= 1;
+            }
+            g_base += NMT;
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===== epilogue: TMEM -> (+bias, ReLU) -> bf16 [max(even, odd) | odd] per pair into the conv-row ring =====
+        const int q = warp & 3;
+        const int chalf = (warp - 4) >> 2;  // which 32 of the 64 output channels
+        const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias0 - smem_u32(smem_raw))) + chalf * 32;
+        volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        uint32_t g = 0;
+        int tile_idx = 0;
+        for (int u = walk.begin; tile_idx < walk.count; u += walk.step, ++tile_idx) {
+            const int w = 2 * u + (int)rank;
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
+            for (int mt = 0; mt < NMT; ++mt, ++g) {
+                const uint32_t slot = g & (kStemwSlots - 1), use = g / kStemwSlots;
+                const int m = mt * 128 + q * 32 + lane;
+                const int i = m / P, jp = m - i * P;
+                const bool valid = jp < kStemwPairs;
+                const int gr = tile_idx * R + i;  // CTA-wide conv row number
+                if (valid) {
+                    while (*rows_released < gr - kStemwRing + 1) __nanosleep(64);
+                }
+                __syncwarp();
+                mbar_wait(tfull0 + 8 * slot, use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + slot * 128 + chalf * 32 + ((uint32_t)(q * 32) << 16);
+                const uint32_t srow = ring0 + (uint32_t)(gr % kStemwRing) * kStemwRowBytes + (uint32_t)jp * 256;
+                const bool keep = y0 + i >= 0;  // conv row -1 is stored as zeros: neutral for a max over post-ReLU values
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t ve[16], vo[16];
+                    tmem_ld16(taddr + h * 16, ve);
+                    tmem_ld16(taddr + 64 + h * 16, vo);
+                    tmem_ld_wait();
+                    if (h == 1) {
+                        tc_fence_before();
+                        mbar_arrive_leader(tempty0 + 8 * slot);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8 + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            uint4 om, oo;
+                            unsigned* um = &om.x;
+                            unsigned* uo = &oo.x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float e0 = fmaxf(__uint_as_float(ve[8 * j + 2 * k]) + bb[2 * k], 0.f);
+                                const float e1 = fmaxf(__uint_as_float(ve[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
+                                const float o0 = fmaxf(__uint_as_float(vo[8 * j + 2 * k]) + bb[2 * k], 0.f);
+                                const float o1 = fmaxf(__uint_as_float(vo[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
+                                const __nv_bfloat162 hm = __floats2bfloat162_rn(fmaxf(e0, o0), fmaxf(e1, o1));
+                                const __nv_bfloat162 ho = __floats2bfloat162_rn(o0, o1);
+                                um[k] = keep ? *reinterpret_cast<const unsigned*>(&hm) : 0u;
+                                uo[k] = keep ? *reinterpret_cast<const unsigned*>(&ho) : 0u;
+                            }
+                            const uint32_t chunk = (uint32_t)((chalf * 4 + h * 2 + j) ^ (jp & 7)) << 4;
+                            sts128(srow + chunk, om);
+                            sts128(srow + 128 + chunk, oo);
+                        }
+                    }
+                }
+                mbar_arrive(mdone0 + 8 * slot);
+            }
+        }
+    } else if (warp >= 12) {
+        // ===== pool: 3x3 / stride-2 / pad-1 max over the ring -> NHWC [n][56][56][64] =====
+        const int te = threadIdx.x - 12 * 32;  // 0..255
+        volatile int* rows_released = reinterpret_cast<volatile int*>(smem_raw + (pool_sync0 - smem_u32(smem_raw)));
+        uint32_t g = 0;
+        int tile_idx = 0;
+        for (int u = walk.begin; tile_idx < walk.count; u += walk.step, ++tile_idx) {
+            const int w = 2 * u + (int)rank;
+            const int img = w / p.tiles_per_img;
+            const int y0 = (w - img * p.tiles_per_img) * 8 - 1;
+            int jnext = 0;
+            __nv_bfloat162 carry[2][4];
+            for (int mt = 0; mt < NMT; ++mt, ++g) {
+                const uint32_t slot = g & (kStemwSlots - 1), use = g / kStemwSlots;
+                mbar_wait(mdone0 + 8 * slot, use & 1);
+                // pooled rows whose last conv row (2j+2) ends inside this M-tile
+                while (2 * jnext + 2 < R && ((2 * jnext + 2) * P + kStemwPairs - 1) / 128 <= mt) {
+                    const int j = jnext++;
+                    const int prow = (y0 + 1) / 2 + j;
+                    const int gr0 = tile_idx * R + 2 * j;
+                    const uint32_t r0 = ring0 + (uint32_t)(gr0 % kStemwRing) * kStemwRowBytes;
+                    const uint32_t r1 = ring0 + (uint32_t)((gr0 + 1) % kStemwRing) * kStemwRowBytes;
+                    const uint32_t r2 = ring0 + (uint32_t)((gr0 + 2) % kStemwRing) * kStemwRowBytes;
+                    // a thread keeps its (column, channel chunk) items for the whole tile: the horizontal max of conv row 2j+2 is
+                    // carried in registers to pooled row j+1, whose first row it is (two ring rows read per pooled row, not three)
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const int item = te + it * 256;
+                        if (item < p.Wp * 8) {
+                            const int pw = item >> 3, ch = item & 7;
+                            // conv columns 2pw-1, 2pw, 2pw+1 = odd of pair pw-1, max(even, odd) of pair pw
+                            const uint32_t offm = (uint32_t)pw * 256 + ((uint32_t)(ch ^ (pw & 7)) << 4);
+                            const uint32_t offo = (uint32_t)max(pw - 1, 0) * 256 + 128 + ((uint32_t)(ch ^ (max(pw - 1, 0) & 7)) << 4);
+                            auto hrow = [&](uint32_t rb, __nv_bfloat162 (&h)[4]) {
+                                const uint4 a = lds128(rb + offm);
+                                const uint4 o = lds128(rb + (pw > 0 ? offo : offm));  // column -1 is padding: the pair's own max again
+                                const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+                                const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) h[k] = __hmax2(ha[k], ho[k]);
+                            };
+                            __nv_bfloat162 h0[4], h1[4], h2[4];
+                            if (j == 0) {
+                                hrow(r0, h0);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) h0[k] = carry[it][k];
+                            }
+                            hrow(r1, h1);
+                            hrow(r2, h2);
+                            __nv_bfloat162 acc[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                acc[k] = __hmax2(h0[k], __hmax2(h1[k], h2[k]));
+                                carry[it][k] = h2[k];
+                            }
+                            if (prow < p.Hp)
+                                *reinterpret_cast<uint4*>(p.out + (((size_t)img * p.Hp + prow) * p.Wp + pw) * 64 + ch * 8) =
+                                    *reinterpret_cast<const uint4*>(acc);
+                        }
+                    }
+                    // rows gr0 and gr0+1 are not needed by later pooled rows (row gr0+2 is: it is row 2(j+1))
+                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    if (te == 0) {
+                        const bool last = 2 * (j + 1) + 2 >= R;  // last pooled row of the tile: its third row is free too
+                        *rows_released = gr0 + (last ? 3 : 2);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory / barriers stay alive until both CTAs are done
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // flat2: the layer-1 kernel (3x3 / stride 1, Cin = Cout = 64) as a CTA PAIR (cta_group::2).
 //
@@ -2012,13 +2318,14 @@ static int launch_flat(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& m
     return FX_OK;
 }
 
-// The pooled stem on stemw_conv_kernel (two conv outputs per accumulator row); FX_STEMW=0 keeps flat_conv_kernel<32, 4, 4, true>.
-static bool stemw_enabled() {
-    static const bool on = [] {
+// The pooled stem with two conv outputs per accumulator row: FX_STEMW = 2 (default) the CTA-pair kernel stemw2_conv_kernel,
+// 1 the single-CTA stemw_conv_kernel, 0 flat_conv_kernel<32, 4, 4, true>.
+static int stemw_mode() {
+    static const int mode = [] {
         const char* v = getenv("FX_STEMW");
-        return !(v && v[0] == '0');
+        return v ? atoi(v) : 2;
     }();
-    return on;
+    return mode;
 }
 
 static int stemw_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, __nv_bfloat16* out, int n, cudaStream_t stream, int sched) {
@@ -2052,7 +2359,18 @@ static int stemw_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
     static bool attr_done[256] = {};  // per device ordinal
     if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(stemw_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        FX_CUDA(e, cudaFuncSetAttribute(stemw2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_done[e->device & 255] = true;
+    }
+    if (stemw_mode() >= 2 && p.n_work % 2 == 0) {  // CTA pairs: unit = two work tiles
+        CUtensorMap mbn;
+        const uint32_t nbox[2] = {16, 32};
+        rc = tc_encode_map(e, &mbn, L.w_bf16, 2, bd, bs, nbox, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stemw B (32 channels)");
+        if (rc != FX_OK) return rc;
+        const int pairs = std::max(1, std::min(e->sm_count / 2, p.n_work / 2));
+        FX_CUDA(e, launch_pdl(stemw2_conv_kernel, dim3(2 * pairs), dim3(kStemwThreads), kSmem, stream, ma, mb, mbn, p));  // cluster dims are a kernel attribute
+        FX_LAUNCH_CHECK(e, "stemw2_conv_kernel");
+        return FX_OK;
     }
     const int grid = std::max(1, std::min(e->sm_count, p.n_work));
     FX_CUDA(e, launch_pdl(stemw_conv_kernel, dim3(grid), dim3(kStemwThreads), kSmem, stream, ma, mb, p));
@@ -2308,7 +2626,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
         p.ypad = 0;
         if (pool) {
             if (!relu || residual) return set_error(e, FX_ERR_INVALID, "flat_conv: the pooled stem is conv+bn+relu+maxpool");
-            if (stemw_enabled()) return stemw_conv(e, L, in, out, n, stream, sched);
+            if (stemw_mode() >= 1) return stemw_conv(e, L, in, out, n, stream, sched);
             p.R = 9;  // 4 pooled rows need conv rows 8t-1 .. 8t+7
             p.rstep = 8;
             p.yfirst = -1;

@@ -393,7 +393,7 @@ np.save(sys.argv[2], eng.embed_host(buf, descs, len(imgs), total))
 eng.close()
 """
 _KNOBS = [{}, {"FX_SCHED": "0"}, {"FX_SCHED": "1"}, {"FX_FLAT2": "0"}, {"FX_FLAT2": "1"}, {"FX_FLAT128X2": "0"}, {"FX_TC_RESB": "0"},
-          {"FX_TC_S2PLANES": "0"}, {"FX_GRAPHS": "0"}, {"FX_TC_FUSEDS": "0"}, {"FX_STEMW": "0"}, {"FX_FLAT2W": "0"}]
+          {"FX_TC_S2PLANES": "0"}, {"FX_GRAPHS": "0"}, {"FX_TC_FUSEDS": "0"}, {"FX_STEMW": "0"}, {"FX_STEMW": "1"}, {"FX_FLAT2W": "0"}]
 
 
 def test_kernel_selection_knobs_do_not_change_the_embeddings(tmp_path):
