@@ -49,7 +49,7 @@ WEIGHT_SEED = 1234
 _M = 115_605_504
 LAYER_MACS = [118_013_952, _M, _M, _M, _M, _M // 2, _M, 6_422_528, _M, _M, _M // 2, _M, 6_422_528, _M, _M, _M // 2, _M, 6_422_528, _M, _M]
 assert sum(LAYER_MACS) == 1_813_561_344
-LAYER_FAMILY = (["flat_conv_kernel<32,4,4,pool> (stem conv1+bn+relu+maxpool, s2d 4x4, N=64)"] + ["flat2_conv_kernel<cta_group::2> (layer1 3x3/s1, N=64; residual prefetched into registers)"] * 4 +
+LAYER_FAMILY = (["stemw2_conv_kernel<cta_group::2> (stem conv1+bn+relu+maxpool, s2d 4x4, two outputs per accumulator row, N=128)"] + ["flat2w_conv_kernel<cta_group::2> (layer1 3x3/s1, two outputs per accumulator row, N=128; residual prefetched into registers)"] * 4 +
                 ["tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128x2_conv_kernel<cta_group::2> (layer2 3x3/s1, N=128)",
                  "tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)", "flat128x2_conv_kernel<cta_group::2> (layer2 3x3/s1, N=128)",
                  "flat128x2_conv_kernel<cta_group::2> (layer2 3x3/s1, N=128)"] + ["tc_conv_kernel + tc2_conv_kernel<cta_group::2> (stride-2 3x3, 1x1/s2, layer3, layer4; per-tap TMA)"] * 10)

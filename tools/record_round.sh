@@ -8,7 +8,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > ${o}_pytest.log 2>&1; echo "py
 timeout 600 python bench.py > ${o}_bench_n1.json 2> ${o}_bench_n1.err; echo "bench rc=$?"
 timeout 300 python bench.py --lanes 1 --no-cpu-baseline > ${o}_bench_n1_lanes1.json 2> ${o}_bench_n1_lanes1.err; echo "bench lanes1 rc=$?"
 timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > ${o}_bench_reference_arm.json 2> ${o}_bench_reference_arm.err; echo "reference arm rc=$?"
-K='regex:preprocess|flat|tc_conv|tc2_conv|avgpool'
+K='regex:preprocess|flat|stemw|tc_conv|tc2_conv|avgpool'
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
   --clock-control none -k "$K" -s 57 -c 19 --csv --log-file ${o}_launches.csv \
   python bench.py --steps 2 --warmup 3 --pool 2048 --no-cpu-baseline --lanes 1 > ${o}_launches.log 2>&1; echo "ncu list rc=$?"
