@@ -62,6 +62,7 @@ struct TcConvParams {
     // with elementStrides = 2 costs the TMA unit a walk over its whole bounding box (measured: ~1000 cycles per
     // 128-pixel box, four times the MMAs it feeds; the traffic itself was never the problem).
     int s2planes;
+    int staged256;  // BN = 256 epilogue through per-warp staging blocks (FX_TC_STAGED256=0: direct per-lane stores / loads)
 };
 
 constexpr int kTcThreads = 128 + 16 * 32;  // 4 control warps + 16 epilogue warps (4 TMEM lane quarters x 4 column groups)
@@ -89,6 +90,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tslot = tempty0 + 16;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
+    constexpr bool kBiasSmem = true;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -229,10 +231,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(bias_s + (ds ? 512 : 0) + n_tile * BN + c0);
+                    const float4* bp = kBiasSmem ? reinterpret_cast<const float4*>(bias_s + (ds ? 512 : 0) + n_tile * BN + c0)
+                                                 : reinterpret_cast<const float4*>((ds ? p.ds_bias : p.bias) + n_tile * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 b = bp[j];
+                        const float4 b = kBiasSmem ? bp[j] : __ldg(bp + j);
                         f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
                         f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
                         f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
@@ -300,6 +303,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // activations only.  That kernel is bound by L2 -> SM delivery (24 KB per K-block and CTA against 256 MMA cycles);
 // without the weight reloads it is 16 KB.
 constexpr int kResKb = 10;
+// BN = 256: five 32 KB stages; six leave no room for the epilogue's 16 x 2 KB staging blocks.  Measured per launch: direct
+// epilogue 6 stages 47.6 us, 5 stages 49.9; staged epilogue 5 stages 45.6 .. 47.6 (stride-2 launches 43.4 -> 39.3); six stages
+// bought by reading the bias through L1 instead of shared memory: slower again (the short units are paced by the epilogue).
+constexpr int kTc2Stages256 = 5;
 template <int BN, int BK, int STAGES, bool RESB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a1,
@@ -317,12 +324,15 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tslot + 16 - smem_u32(smem_raw)));
     // RESB: 2 KB per epilogue warp (32 rows x 64 B) to turn the accumulator layout (one pixel per lane) into whole
     // 64-byte pieces of pixel rows before they go to global memory
-    const uint32_t stage_out0 = (tslot + 16 + 2 * 512 * 4 + 127u) & ~127u;
+    constexpr bool kBiasSmem = true;  // (BN = 256 without the copy, bias through L1, to make room for a sixth stage: measured slower)
+    const uint32_t stage_out0 = (tslot + 16 + (kBiasSmem ? 2 * 512 * 4 : 0) + 127u) & ~127u;
     const bool fused = RESB && p.ds_fused;
-    for (int i = threadIdx.x; i < p.cout; i += kTcThreads) {
-        bias_s[i] = __ldg(p.bias + i);
-        if (p.ds_tiles || fused) bias_s[512 + i] = __ldg(p.ds_bias + i);
-    }
+    const bool staged256_on = p.staged256 != 0;
+    if (kBiasSmem)
+        for (int i = threadIdx.x; i < p.cout; i += kTcThreads) {
+            bias_s[i] = __ldg(p.bias + i);
+            if (p.ds_tiles || fused) bias_s[512 + i] = __ldg(p.ds_bias + i);
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -502,6 +512,110 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
             const size_t obase = pix * p.cout + (size_t)n_tile * BN;
 
+            if (BN == 256 && STAGES == kTc2Stages256 && !RESB && (nci & 1) == 0 && !(p.out_f32 && !ds_unit) && staged256_on) {
+                // ===== staged epilogue (BN = 256): the accumulator layout is one pixel row per lane, so a direct 16-byte store (or
+                // residual load) per lane touches 32 different lines per instruction -- 32 wavefronts on the shared-memory / L1
+                // data pipe that the MMA operand fetch and the TMA writes already fill.  Rounds of 32 channels go through a 2 KB
+                // block per warp instead (32 rows x 64 B, chunk c of row r at (c ^ (r >> 1)) & 3): residual in (8 rows x 64
+                // contiguous bytes per instruction), result out the same way. =====
+                const bool res_unit = !ds_unit && p.residual != nullptr;
+                const uint32_t stg = stage_out0 + (uint32_t)(warp - 4) * 2048;
+                const int mypix = valid ? (int)pix : -1;
+                int prs[4];
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) prs[i4] = __shfl_sync(0xffffffffu, mypix, i4 * 8 + (lane >> 2));
+                const size_t cb = (size_t)n_tile * BN + ch0 + (lane & 3) * 8;  // this lane's 8 channels of a round's 32 in the store-out role
+                uint4 rres[4];  // the residual of the coming round (round 1's loads fly while round 0 is computed)
+                if (res_unit) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4)  // unpredicated, clamped: a predicated load is waited for at once
+                        rres[i4] = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)max(prs[i4], 0) * p.cout + cb));
+                }
+                mbar_wait(tfull0 + 8 * as, aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + as * kAccStride + ((uint32_t)(q * 32) << 16);
+                __nv_bfloat16* obase_p = (ds_unit ? p.ds_out : p.out);
+#pragma unroll
+                for (int rd = 0; rd < 2; ++rd) {
+                    if (rd * 2 >= nci) break;
+                    if (res_unit) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const int r = i4 * 8 + (lane >> 2);
+                            sts128(stg + r * 64 + ((((lane & 3) ^ (r >> 1)) & 3) << 4), rres[i4]);
+                        }
+                        if (rd == 0 && nci > 2) {
+#pragma unroll
+                            for (int i4 = 0; i4 < 4; ++i4)
+                                rres[i4] = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)max(prs[i4], 0) * p.cout + cb + 32));
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int ci = rd * 2 + c2;
+                        const int c0 = ch0 + ci * 16;
+                        uint32_t v[16];
+                        tmem_ld16(taddr + tc0 + ci * 16, v);
+                        tmem_ld_wait();
+                        if (ci == nci - 1) {
+                            tc_fence_before();
+                            mbar_arrive_leader(tempty0 + 8 * as);
+                        }
+                        if (valid) {
+                            float f[16];
+                            const float4* bp = reinterpret_cast<const float4*>(bias_s + (ds_unit ? 512 : 0) + n_tile * BN + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b = bp[j];
+                                f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+                                f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                                f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                                f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint32_t sa = stg + lane * 64 + ((((c2 * 2 + j) ^ (lane >> 1)) & 3) << 4);
+                                if (res_unit) {
+                                    const uint4 rv = lds128(sa);
+                                    const unsigned u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        f[8 * j + 2 * k] += __uint_as_float(u[k] << 16);
+                                        f[8 * j + 2 * k + 1] += __uint_as_float(u[k] & 0xffff0000u);
+                                    }
+                                }
+                                if (p.relu && !ds_unit) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) f[8 * j + k] = fmaxf(f[8 * j + k], 0.f);
+                                }
+                                uint4 o;
+                                unsigned* u2 = &o.x;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 2 * k], f[8 * j + 2 * k + 1]);
+                                    u2[k] = *reinterpret_cast<const unsigned*>(&h2);
+                                }
+                                sts128(sa, o);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    {
+                        uint4 val[4];
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const int r = i4 * 8 + (lane >> 2);
+                            val[i4] = lds128(stg + r * 64 + ((((lane & 3) ^ (r >> 1)) & 3) << 4));
+                        }
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4)
+                            if (prs[i4] >= 0) *reinterpret_cast<uint4*>(obase_p + (size_t)prs[i4] * p.cout + cb + rd * 32) = val[i4];
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             // fused downsample: pass 0 drains the conv1 accumulator, pass 1 the downsample one beside it
             const int n_pass = (RESB && fused) ? 2 : 1;
             for (int pass = 0; pass < n_pass; ++pass) {
@@ -537,10 +651,11 @@ tc2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
-                    const float4* bp = reinterpret_cast<const float4*>(bias_s + (ds ? 512 : 0) + n_tile * BN + c0);
+                    const float4* bp = kBiasSmem ? reinterpret_cast<const float4*>(bias_s + (ds ? 512 : 0) + n_tile * BN + c0)
+                                                 : reinterpret_cast<const float4*>((ds ? p.ds_bias : p.bias) + n_tile * BN + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 b = bp[j];
+                        const float4 b = kBiasSmem ? bp[j] : __ldg(bp + j);
                         f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
                         f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
                         f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
@@ -749,7 +864,7 @@ static int launch_tc2(fx_engine* e, const CUtensorMap& ma, const CUtensorMap& ma
                       const CUtensorMap& mbh, TcConvParams p, cudaStream_t stream) {
     constexpr int kBBytes = (BN / 2) * BK * 2;
     constexpr int kSmem = 1024 + STAGES * 128 * BK * 2 + (RESB ? kResKb : STAGES) * kBBytes + (2 * STAGES + 4) * 8 + 32 + 2 * 512 * 4 +
-                          (RESB ? 128 + 16 * 2048 : 0);
+                          ((RESB || (BN == 256 && STAGES == kTc2Stages256)) ? 128 + 16 * 2048 : 0);
     static_assert(!RESB || BN == 128, "the fused downsample accumulator needs 4 * BN <= 512 TMEM columns");
     static_assert(kSmem <= 232448, "tc2_conv_kernel: shared memory");
     static bool attr_done[256] = {};  // per device ordinal
@@ -854,6 +969,11 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
     }();
     // stride-2 layers on the CTA-pair kernel: parity-plane maps (TcConvParams::s2planes)
     p.s2planes = planes_on && bn >= 128 && g.stride == 2 && g.hin % 2 == 0 && g.win % 2 == 0 && g.kh == 3 && g.kw == 3 && g.pad == 1;
+    static const bool staged256 = [] {
+        const char* v = getenv("FX_TC_STAGED256");
+        return !(v && v[0] == '0');
+    }();
+    p.staged256 = staged256;
     if (p.s2planes) {
         const uint64_t rowb = (uint64_t)g.win * g.cin * 2;
         const uint64_t dims[5] = {(uint64_t)g.cin, (uint64_t)g.win / 2, 2, (uint64_t)g.hin / 2, (uint64_t)n};
@@ -926,7 +1046,9 @@ int tc_conv_packed(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, 
         default:
             // (a 4-CTA-cluster variant with the weight K-blocks multicast to two pairs was measured on B200 in round 2:
             // byte-identical rows, 64 us instead of 47.5 us per layer3 / layer4 launch -- removed)
-            return launch_tc2<256, 64, 6>(e, ma, ma1, mb, mb2, mbh, p, stream);
+            // fp32 output (the last conv before the average pool) and FX_TC_STAGED256=0: direct epilogue, six stages
+            if (p.out_f32 || !p.staged256) return launch_tc2<256, 64, 6>(e, ma, ma1, mb, mb2, mbh, p, stream);
+            return launch_tc2<256, 64, kTc2Stages256>(e, ma, ma1, mb, mb2, mbh, p, stream);
     }
 }
 

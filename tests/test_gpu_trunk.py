@@ -393,7 +393,7 @@ np.save(sys.argv[2], eng.embed_host(buf, descs, len(imgs), total))
 eng.close()
 """
 _KNOBS = [{}, {"FX_SCHED": "0"}, {"FX_SCHED": "1"}, {"FX_FLAT2": "0"}, {"FX_FLAT2": "1"}, {"FX_FLAT128X2": "0"}, {"FX_TC_RESB": "0"},
-          {"FX_TC_S2PLANES": "0"}, {"FX_GRAPHS": "0"}, {"FX_TC_FUSEDS": "0"}, {"FX_STEMW": "0"}, {"FX_STEMW": "1"}, {"FX_FLAT2W": "0"}]
+          {"FX_TC_S2PLANES": "0"}, {"FX_GRAPHS": "0"}, {"FX_TC_FUSEDS": "0"}, {"FX_STEMW": "0"}, {"FX_STEMW": "1"}, {"FX_FLAT2W": "0"}, {"FX_TC_STAGED256": "0"}]
 
 
 def test_kernel_selection_knobs_do_not_change_the_embeddings(tmp_path):
@@ -411,7 +411,7 @@ def test_kernel_selection_knobs_do_not_change_the_embeddings(tmp_path):
     procs = []
     for k, env in enumerate(_KNOBS):
         e = dict(os.environ)
-        for name in ("FX_SCHED", "FX_FLAT2", "FX_FLAT128X2", "FX_TC_RESB", "FX_TC_S2PLANES", "FX_GRAPHS", "FX_TC_FUSEDS", "FX_STEMW", "FX_FLAT2W"):
+        for name in ("FX_SCHED", "FX_FLAT2", "FX_FLAT128X2", "FX_TC_RESB", "FX_TC_S2PLANES", "FX_GRAPHS", "FX_TC_FUSEDS", "FX_STEMW", "FX_FLAT2W", "FX_TC_STAGED256"):
             e.pop(name, None)
         e.update(env)
         procs.append(subprocess.Popen([sys.executable, str(script), root, str(tmp_path / f"emb{k}.npy")], env=e, stdout=subprocess.PIPE,
