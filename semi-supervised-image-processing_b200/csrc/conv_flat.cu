@@ -2518,12 +2518,12 @@ static int flat2_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
 }
 
 // layer 1 on flat2w_conv_kernel (two outputs per accumulator row); FX_FLAT2W=0 keeps flat2_conv_kernel.
-static bool flat2w_supported(const LayerGeom& g) {
+static bool flat2w_supported(const LayerGeom& g, bool has_residual) {
     static const bool on = [] {
         const char* v = getenv("FX_FLAT2W");
         return !(v && v[0] == '0');
     }();
-    return on && flat2_mode() >= 1 && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin == 64 && g.cout == 64 && g.win % 2 == 0 &&
+    return on && flat2_mode() >= (has_residual ? 2 : 1) && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad == 1 && g.cin == 64 && g.cout == 64 && g.win % 2 == 0 &&
            g.win >= 8 && g.win / 2 + 1 <= 128 - g.win / 2 && g.hin == g.hout && g.win == g.wout;
 }
 
@@ -2654,7 +2654,7 @@ int flat_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* in, const
     }
     if (pool) return set_error(e, FX_ERR_INVALID, "flat_conv: only the stem has a fused max-pool");
     if (flat128_supported(g)) return flat128_conv(e, L, in, residual, out, n, relu, stream);
-    if (flat2w_supported(g)) return flat2w_conv(e, L, in, residual, out, n, relu, stream, sched);
+    if (flat2w_supported(g, residual != nullptr)) return flat2w_conv(e, L, in, residual, out, n, relu, stream, sched);
     if (flat2_supported(g, residual != nullptr)) return flat2_conv(e, L, in, residual, out, n, relu, stream, sched);
     p.P = g.win + 2;
     p.chunks = g.cin / 64;
