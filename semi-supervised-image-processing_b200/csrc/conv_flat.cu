@@ -854,6 +854,8 @@ stemw_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // 4 + 4 (48 cycles of the shared-memory pipe for 64 cycles of math), an N = 64 step 4 + 1.  The leader's half is always the
 // even output's weights, the peer's the odd output's, so no tile is stored twice: 33 KB per CTA.  Protocol as flat2_conv_kernel.
 constexpr int kStemw2WBytes = 33 * 1024;
+constexpr int kStemw2Ring = 8;                          // conv rows kept for the pool
+constexpr int kStemw2RowBytes = kStemwPairs * 128;      // ring row: [pair][64 ch] bf16, one (pre-maxed) value per pair
 __host__ __device__ constexpr uint32_t stemw2_w_off(int ty, int t) {  // byte offset of step (ty, t)'s half operand in issue order
     return (uint32_t)((ty == 0 ? 2 * t : 9 + (ty - 1) * 8 + (t == 0 ? 0 : 2 * t - 1)) * 1024);
 }
@@ -866,8 +868,9 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sW = sbase;
     const uint32_t sA = sW + kStemw2WBytes;
-    const uint32_t ring0 = sA + 2 * kStemwStage;
-    const uint32_t bias0 = ring0 + kStemwRing * kStemwRowBytes;
+    const uint32_t ring0 = sA + 2 * kStemwStage;                      // conv-row ring: [row][pair][64 ch] of hmax values (see the epilogue)
+    const uint32_t side0 = ring0 + kStemw2Ring * kStemw2RowBytes;     // [row][2][64 ch]: odd outputs handed across warp boundaries
+    const uint32_t bias0 = side0 + kStemw2Ring * 2 * 128;
     const uint32_t bars = bias0 + 256;
     const uint32_t full0 = bars, empty0 = full0 + 16, tfull0 = empty0 + 16, tempty0 = tfull0 + 8 * kStemwSlots;
     const uint32_t mdone0 = tempty0 + 8 * kStemwSlots, wbar = mdone0 + 8 * kStemwSlots, tslot = wbar + 8, pool_sync0 = tslot + 8;
@@ -1028,14 +1031,21 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const bool valid = jp < kStemwPairs;
                 const int gr = tile_idx * R + i;  // CTA-wide conv row number
                 if (valid) {
-                    while (*rows_released < gr - kStemwRing + 1) __nanosleep(64);
+                    while (*rows_released < gr - kStemw2Ring + 1) __nanosleep(64);
                 }
                 __syncwarp();
                 mbar_wait(tfull0 + 8 * slot, use & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + slot * 128 + chalf * 32 + ((uint32_t)(q * 32) << 16);
-                const uint32_t srow = ring0 + (uint32_t)(gr % kStemwRing) * kStemwRowBytes + (uint32_t)jp * 256;
+                const uint32_t rslot = (uint32_t)(gr % kStemw2Ring);
+                const uint32_t srow = ring0 + rslot * kStemw2RowBytes + (uint32_t)jp * 128;
                 const bool keep = y0 + i >= 0;  // conv row -1 is stored as zeros: neutral for a max over post-ReLU values
+                // The ring holds ONE value per pair: hmax[j'] = max(odd[j'-1], even[j'], odd[j']) = the three conv columns 2j'-1 .. 2j'+1
+                // of pooled column j'.  odd[j'-1] comes from the neighbouring lane by shuffle; where that neighbour sits in another
+                // warp (lane 0), the neighbour (its lane 31) leaves its odd value in a small side array and the pool adds it.
+                const bool from_left = lane > 0 && jp > 0;
+                const bool hand_over = lane == 31 && valid && jp + 1 < kStemwPairs;
+                const uint32_t sside = side0 + (rslot * 2 + (uint32_t)(((m + 1) >> 5) - ((i * P) >> 5) - 1)) * 128;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t ve[16], vo[16];
@@ -1046,30 +1056,31 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                         tc_fence_before();
                         mbar_arrive_leader(tempty0 + 8 * slot);
                     }
-                    if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8 + 4);
-                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                            uint4 om, oo;
-                            unsigned* um = &om.x;
-                            unsigned* uo = &oo.x;
+                    for (int j = 0; j < 2; ++j) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + h * 16 + j * 8 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        uint4 om, oo;
+                        unsigned* um = &om.x;
+                        unsigned* uo = &oo.x;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float e0 = fmaxf(__uint_as_float(ve[8 * j + 2 * k]) + bb[2 * k], 0.f);
-                                const float e1 = fmaxf(__uint_as_float(ve[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
-                                const float o0 = fmaxf(__uint_as_float(vo[8 * j + 2 * k]) + bb[2 * k], 0.f);
-                                const float o1 = fmaxf(__uint_as_float(vo[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
-                                const __nv_bfloat162 hm = __floats2bfloat162_rn(fmaxf(e0, o0), fmaxf(e1, o1));
-                                const __nv_bfloat162 ho = __floats2bfloat162_rn(o0, o1);
-                                um[k] = keep ? *reinterpret_cast<const unsigned*>(&hm) : 0u;
-                                uo[k] = keep ? *reinterpret_cast<const unsigned*>(&ho) : 0u;
-                            }
-                            const uint32_t chunk = (uint32_t)((chalf * 4 + h * 2 + j) ^ (jp & 7)) << 4;
-                            sts128(srow + chunk, om);
-                            sts128(srow + 128 + chunk, oo);
+                        for (int k = 0; k < 4; ++k) {
+                            const float e0 = fmaxf(__uint_as_float(ve[8 * j + 2 * k]) + bb[2 * k], 0.f);
+                            const float e1 = fmaxf(__uint_as_float(ve[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
+                            const float o0 = fmaxf(__uint_as_float(vo[8 * j + 2 * k]) + bb[2 * k], 0.f);
+                            const float o1 = fmaxf(__uint_as_float(vo[8 * j + 2 * k + 1]) + bb[2 * k + 1], 0.f);
+                            const __nv_bfloat162 ho = __floats2bfloat162_rn(o0, o1);
+                            const unsigned odd = (keep && valid) ? *reinterpret_cast<const unsigned*>(&ho) : 0u;
+                            const unsigned left = __shfl_up_sync(0xffffffffu, odd, 1);
+                            __nv_bfloat162 hm = __floats2bfloat162_rn(fmaxf(e0, o0), fmaxf(e1, o1));
+                            if (from_left) hm = __hmax2(hm, *reinterpret_cast<const __nv_bfloat162*>(&left));
+                            um[k] = keep ? *reinterpret_cast<const unsigned*>(&hm) : 0u;
+                            uo[k] = odd;
                         }
+                        const uint32_t cidx = (uint32_t)(chalf * 4 + h * 2 + j);
+                        if (valid) sts128(srow + ((cidx ^ (uint32_t)(jp & 7)) << 4), om);
+                        if (hand_over) sts128(sside + (cidx << 4), oo);
                     }
                 }
                 mbar_arrive(mdone0 + 8 * slot);
@@ -1095,36 +1106,37 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const int j = jnext++;
                     const int prow = (y0 + 1) / 2 + j;
                     const int gr0 = tile_idx * R + 2 * j;
-                    const uint32_t r0 = ring0 + (uint32_t)(gr0 % kStemwRing) * kStemwRowBytes;
-                    const uint32_t r1 = ring0 + (uint32_t)((gr0 + 1) % kStemwRing) * kStemwRowBytes;
-                    const uint32_t r2 = ring0 + (uint32_t)((gr0 + 2) % kStemwRing) * kStemwRowBytes;
-                    // a thread keeps its (column, channel chunk) items for the whole tile: the horizontal max of conv row 2j+2 is
-                    // carried in registers to pooled row j+1, whose first row it is (two ring rows read per pooled row, not three)
+                    const uint32_t s0 = (uint32_t)(gr0 % kStemw2Ring), s1 = (uint32_t)((gr0 + 1) % kStemw2Ring), s2 = (uint32_t)((gr0 + 2) % kStemw2Ring);
+                    // a thread keeps its (column, channel chunk) items for the whole tile: the value of conv row 2j+2 is carried in
+                    // registers to pooled row j+1, whose first row it is (two ring rows read per pooled row, not three)
 #pragma unroll
                     for (int it = 0; it < 2; ++it) {
                         const int item = te + it * 256;
                         if (item < p.Wp * 8) {
                             const int pw = item >> 3, ch = item & 7;
-                            // conv columns 2pw-1, 2pw, 2pw+1 = odd of pair pw-1, max(even, odd) of pair pw
-                            const uint32_t offm = (uint32_t)pw * 256 + ((uint32_t)(ch ^ (pw & 7)) << 4);
-                            const uint32_t offo = (uint32_t)max(pw - 1, 0) * 256 + 128 + ((uint32_t)(ch ^ (max(pw - 1, 0) & 7)) << 4);
-                            auto hrow = [&](uint32_t rb, __nv_bfloat162 (&h)[4]) {
-                                const uint4 a = lds128(rb + offm);
-                                const uint4 o = lds128(rb + (pw > 0 ? offo : offm));  // column -1 is padding: the pair's own max again
+                            const uint32_t offm = (uint32_t)pw * 128 + ((uint32_t)(ch ^ (pw & 7)) << 4);
+                            auto hrow = [&](uint32_t rs, int irow, __nv_bfloat162 (&h)[4]) {
+                                const uint4 a = lds128(ring0 + rs * kStemw2RowBytes + offm);
                                 const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-                                const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&o);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) h[k] = __hmax2(ha[k], ho[k]);
+                                for (int k = 0; k < 4; ++k) h[k] = ha[k];
+                                const int pos = irow * P + pw;  // position of the pair inside the work tile: lane 0 of an epilogue warp?
+                                if (pw > 0 && (pos & 31) == 0) {
+                                    const uint4 o = lds128(side0 + (rs * 2 + (uint32_t)((pos >> 5) - ((irow * P) >> 5) - 1)) * 128 + ((uint32_t)ch << 4));
+                                    const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], ho[k]);
+                                }
                             };
                             __nv_bfloat162 h0[4], h1[4], h2[4];
                             if (j == 0) {
-                                hrow(r0, h0);
+                                hrow(s0, 2 * j, h0);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) h0[k] = carry[it][k];
                             }
-                            hrow(r1, h1);
-                            hrow(r2, h2);
+                            hrow(s1, 2 * j + 1, h1);
+                            hrow(s2, 2 * j + 2, h2);
                             __nv_bfloat162 acc[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
