@@ -854,6 +854,7 @@ stemw_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // 4 + 4 (48 cycles of the shared-memory pipe for 64 cycles of math), an N = 64 step 4 + 1.  The leader's half is always the
 // even output's weights, the peer's the odd output's, so no tile is stored twice: 33 KB per CTA.  Protocol as flat2_conv_kernel.
 constexpr int kStemw2WBytes = 33 * 1024;
+constexpr int kStemw2Stages = 3;                        // A stages (the half-size ring rows below pay for the third)
 constexpr int kStemw2Ring = 8;                          // conv rows kept for the pool
 constexpr int kStemw2RowBytes = kStemwPairs * 128;      // ring row: [pair][64 ch] bf16, one (pre-maxed) value per pair
 __host__ __device__ constexpr uint32_t stemw2_w_off(int ty, int t) {  // byte offset of step (ty, t)'s half operand in issue order
@@ -868,11 +869,11 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sW = sbase;
     const uint32_t sA = sW + kStemw2WBytes;
-    const uint32_t ring0 = sA + 2 * kStemwStage;                      // conv-row ring: [row][pair][64 ch] of hmax values (see the epilogue)
+    const uint32_t ring0 = sA + kStemw2Stages * kStemwStage;                      // conv-row ring: [row][pair][64 ch] of hmax values (see the epilogue)
     const uint32_t side0 = ring0 + kStemw2Ring * kStemw2RowBytes;     // [row][2][64 ch]: odd outputs handed across warp boundaries
     const uint32_t bias0 = side0 + kStemw2Ring * 2 * 128;
     const uint32_t bars = bias0 + 256;
-    const uint32_t full0 = bars, empty0 = full0 + 16, tfull0 = empty0 + 16, tempty0 = tfull0 + 8 * kStemwSlots;
+    const uint32_t full0 = bars, empty0 = full0 + 8 * kStemw2Stages, tfull0 = empty0 + 8 * kStemw2Stages, tempty0 = tfull0 + 8 * kStemwSlots;
     const uint32_t mdone0 = tempty0 + 8 * kStemwSlots, wbar = mdone0 + 8 * kStemwSlots, tslot = wbar + 8, pool_sync0 = tslot + 8;
     uint32_t* tslot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tslot - smem_u32(smem_raw)));
 
@@ -888,7 +889,7 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tma_prefetch_desc(&map_bn);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStemw2Stages; ++i) {
             mbar_init(full0 + 8 * i, 2);   // leader's arrive.expect_tx + the peer producer's arrive
             mbar_init(empty0 + 8 * i, 1);  // multicast commit
         }
@@ -913,7 +914,7 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (!leader)
             for (int i = threadIdx.x; i < 2048 / 16; i += kStemwThreads) sts128(sW + i * 16, z);
         constexpr int kPad16 = (kStemwStage - kStemwBoxBytes) / 16;
-        for (int i = threadIdx.x; i < 2 * kPad16; i += kStemwThreads)
+        for (int i = threadIdx.x; i < kStemw2Stages * kPad16; i += kStemwThreads)
             sts128(sA + (i / kPad16) * kStemwStage + kStemwBoxBytes + (i % kPad16) * 16, z);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -955,7 +956,7 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 if (leader) mbar_expect_tx(full0 + 8 * stage, 2 * kStemwBoxBytes);
                 tma_load_4d_2cta(sA + stage * kStemwStage, &map_a, full0 + 8 * stage, 0, 0, y0, img);
                 if (!leader) mbar_arrive_leader(full0 + 8 * stage);
-                if (++stage == 2) {
+                if (++stage == kStemw2Stages) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -1006,7 +1007,7 @@ stemw2_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             if (elect_one_sync()) umma_commit_2cta(empty0 + 8 * stage);
             __syncwarp();
-            if (++stage == 2) {
+            if (++stage == kStemw2Stages) {
                 stage = 0;
                 phase ^= 1;
             }
@@ -2367,11 +2368,14 @@ static int stemw_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
     rc = tc_encode_map(e, &mb, L.w_bf16, 2, bd, bs, bbox, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stemw B");
     if (rc != FX_OK) return rc;
     constexpr int kSmem = 1024 + kStemwWBytes + 2 * kStemwStage + kStemwRing * kStemwRowBytes + 256 + 8 * (4 + 3 * kStemwSlots + 3) + 64;
+    constexpr int kSmem2 = 1024 + kStemw2WBytes + kStemw2Stages * kStemwStage + kStemw2Ring * (kStemw2RowBytes + 256) + 256 +
+                           8 * (2 * kStemw2Stages + 3 * kStemwSlots + 3) + 64;
+    static_assert(kSmem2 <= kSmemMax, "stemw2_conv_kernel: shared memory");
     static_assert(kSmem <= kSmemMax, "stemw_conv_kernel: shared memory");
     static bool attr_done[256] = {};  // per device ordinal
     if (!attr_done[e->device & 255]) {
         FX_CUDA(e, cudaFuncSetAttribute(stemw_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        FX_CUDA(e, cudaFuncSetAttribute(stemw2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        FX_CUDA(e, cudaFuncSetAttribute(stemw2_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
         attr_done[e->device & 255] = true;
     }
     if (stemw_mode() >= 2 && p.n_work % 2 == 0) {  // CTA pairs: unit = two work tiles
@@ -2380,7 +2384,7 @@ static int stemw_conv(fx_engine* e, const PackedLayer& L, const __nv_bfloat16* i
         rc = tc_encode_map(e, &mbn, L.w_bf16, 2, bd, bs, nbox, ones, CU_TENSOR_MAP_SWIZZLE_32B, "stemw B (32 channels)");
         if (rc != FX_OK) return rc;
         const int pairs = std::max(1, std::min(e->sm_count / 2, p.n_work / 2));
-        FX_CUDA(e, launch_pdl(stemw2_conv_kernel, dim3(2 * pairs), dim3(kStemwThreads), kSmem, stream, ma, mb, mbn, p));  // cluster dims are a kernel attribute
+        FX_CUDA(e, launch_pdl(stemw2_conv_kernel, dim3(2 * pairs), dim3(kStemwThreads), kSmem2, stream, ma, mb, mbn, p));  // cluster dims are a kernel attribute
         FX_LAUNCH_CHECK(e, "stemw2_conv_kernel");
         return FX_OK;
     }
